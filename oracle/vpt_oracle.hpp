@@ -1,0 +1,613 @@
+/* oracle/vpt_oracle.hpp -- TEST INFRASTRUCTURE ("oracle level 1"), not product code.
+ *
+ * A CPU restatement, in FP64 and in the reference's operation order, of the per-pixel radiance
+ * loop of gabo99cas/minimal_volumetric_path_tracer (src/rt.cpp:767-805 and everything it calls).
+ * Each function cites the reference file:line it follows.  It exists so that the CUDA product can
+ * be checked on identical random numbers:
+ *
+ *   - driven by an explicit draw stream (the reference's erand48 sequence) it reproduces the
+ *     reference's own per-path results to rounding -- that is how this restatement is PINNED
+ *     (tests/test_oracle_pinning.py against oracle/_ref/libvpt_l0.so here, and against the
+ *     committed vectors in tests/golden/ everywhere);
+ *   - driven by the Philox stream convention of oracle/philox.h it is the common-random-number
+ *     truth for the device kernels.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may use it.  The product
+ * (minimal_volumetric_path_tracer_b200/) never includes, links or calls anything in oracle/.
+ *
+ * Deliberate deviations from the reference, all of them definitions of behaviour the reference
+ * leaves undefined:
+ *   - more than 4 emitters: the reference overflows `int arr[4]` (vptShadeMethods.h:1293); here up
+ *     to VPT_ORACLE_MAX_EMITTERS are listed.
+ *   - `idHitted` / `sourceid` are uninitialised on a miss (volumetricBasicFunctions.h:324,
+ *     samplingFunctions.h:251): here they are -1 (matches nothing); none of the values read from
+ *     them in the reference can change a result when the ray missed.
+ *   - MISv2's `costhetaMax` is uninitialised when the scene has no area light and the BSDF sample
+ *     of a microfacet surface returns g.x <= 0 (misSamplingFunctions.h:162): here it starts at 0.
+ *   - materials 2 (dielectric) and 3 (volumetric sphere) are outside the hot-path scope table
+ *     (SURVEY.md section 8f item 3); scenes using them are rejected by the C API.
+ * Two reference behaviours are decided by FP64 rounding; both are
+ * reproduced by default and can be switched to a well-defined alternative:
+ *   quirk R0_FALLTHROUGH   on: as reference.  off: scene scans skip r == 0 spheres, so the point-light
+ *                          in-medium connection is never overwritten by the solid-angle block.
+ *   quirk EXACT_VISIBILITY on: `t > distance` as reference.  off: `t > distance * (1 - 1e-4)`.
+ */
+#ifndef VPT_ORACLE_HPP
+#define VPT_ORACLE_HPP
+
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <vector>
+#include "philox.h"
+
+namespace vpt_oracle {
+
+constexpr int VPT_ORACLE_MAX_EMITTERS = 16;
+constexpr double kMaxFloat = 3.40282346638528859811704183484516925e+38; /* MAXFLOAT, vptShadeMethods.h:1287 */
+constexpr double kPi = 3.14159265358979323846;                          /* M_PI */
+
+enum : unsigned { QUIRK_R0_FALLTHROUGH = 1u, QUIRK_EXACT_VISIBILITY = 2u };
+
+/* ---- Vector.h:10-34 ---------------------------------------------------------------------------- */
+struct Vec {
+    double x = 0, y = 0, z = 0;
+    Vec() = default;
+    Vec(double a, double b, double c) : x(a), y(b), z(c) {}
+};
+static inline Vec operator+(const Vec &a, const Vec &b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+static inline Vec operator-(const Vec &a, const Vec &b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+static inline Vec operator*(const Vec &a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+static inline double dot(const Vec &a, const Vec &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static inline Vec had(const Vec &a, const Vec &b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }               /* mult */
+static inline Vec cross(const Vec &a, const Vec &b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; } /* % */
+static inline Vec unit(const Vec &a) { return a * (1.0 / std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z)); }   /* normalize */
+
+struct Ray { Vec o, d; };
+
+/* ---- Sphere.h:12-37 ---------------------------------------------------------------------------- */
+struct Sphere {
+    double r; Vec p, c, radiance; int material; Vec eta, kappa; double alpha;
+    bool emits() const { return radiance.x > 0 || radiance.y > 0 || radiance.z > 0; } /* vptShadeMethods.h:1296 */
+};
+
+/* Sphere::intersect, Sphere.h:27-37 */
+static inline double sphere_t(const Sphere &s, const Ray &ray) {
+    const Vec op = ray.o - s.p;
+    const double b = dot(op, ray.d);
+    const double det = b * b - dot(op, op) + s.r * s.r;
+    if (det < 0) return 0.0;
+    const double root = std::sqrt(det);
+    const double far_t = -b + root, near_t = -b - root;
+    if (near_t < 0 || std::fabs(near_t) < 0.0001) return far_t;
+    return near_t;
+}
+
+struct Scene {
+    std::vector<Sphere> s;
+    unsigned quirks = QUIRK_R0_FALLTHROUGH | QUIRK_EXACT_VISIBILITY;
+    uint64_t scans = 0; /* scene scans performed (statistics only) */
+};
+
+/* intersect, pathTracingUtilities.h:12-36.  `id` is only written on a hit; t = 0 on a miss. */
+static inline bool scan(Scene &sc, const Ray &ray, double &t, int &id) {
+    double best = __DBL_MAX__;
+    bool any = false;
+    ++sc.scans;
+    const bool skip_r0 = !(sc.quirks & QUIRK_R0_FALLTHROUGH);
+    for (size_t i = 0; i < sc.s.size(); ++i) {
+        if (skip_r0 && sc.s[i].r == 0) continue;
+        const double ti = sphere_t(sc.s[i], ray);
+        if (ti > 0 && std::fabs(ti) > 0.0001) {
+            any = true;
+            if (ti < best) { best = ti; id = (int)i; }
+        }
+    }
+    t = any ? best : 0;
+    return any;
+}
+
+/* visibility, pathTracingUtilities.h:39-53 */
+static inline bool visible(Scene &sc, const Vec &light, const Vec &x) {
+    Vec lx = light - x;
+    const double distance = std::sqrt(dot(lx, lx));
+    lx = unit(lx);
+    lx = lx * -1;
+    int id = 0;
+    double t;
+    scan(sc, Ray{light, lx}, t, id);
+    if (sc.quirks & QUIRK_EXACT_VISIBILITY) return t > distance || t == 0;
+    return t == 0 || t > distance * (1.0 - 1e-4);
+}
+
+/* rayTracer, pathTracingUtilities.h:56-64 */
+static inline Vec first_hit_radiance(Scene &sc, const Vec &x, const Vec &wi, int &source) {
+    double t;
+    int id = 0;
+    if (!scan(sc, Ray{x, wi}, t, id)) return Vec();
+    source = id;
+    return sc.s[id].radiance;
+}
+
+/* cosinethetaMax, pathTracingUtilities.h:66-73 */
+static inline double cone_cos(const Scene &sc, int source, const Vec &x) {
+    const double radius = sc.s[source].r;
+    const Vec cx = sc.s[source].p - x;
+    const double len = std::sqrt(dot(cx, cx));
+    return std::sqrt(1 - (radius / len) * (radius / len));
+}
+
+/* coordinateSystem, mathUtilities.h:10-19 */
+static inline void frame(const Vec &n, Vec &s, Vec &t) {
+    if (std::fabs(n.x) > std::fabs(n.y)) {
+        const double inv = 1.0 / std::sqrt(n.x * n.x + n.z * n.z);
+        t = Vec(n.z * inv, 0.0, -n.x * inv);
+    } else {
+        const double inv = 1.0 / std::sqrt(n.y * n.y + n.z * n.z);
+        t = Vec(0.0, n.z * inv, -n.y * inv);
+    }
+    s = cross(t, n);
+}
+/* coordinateTraspose, mathUtilities.h:21-30: world -> local (s, t, n) */
+static inline Vec to_local(const Vec &n, const Vec &w) {
+    Vec s, t;
+    frame(n, s, t);
+    const Vec col0(s.x, t.x, n.x), col1(s.y, t.y, n.y), col2(s.z, t.z, n.z);
+    return col0 * w.x + col1 * w.y + col2 * w.z;
+}
+static inline Vec from_local(const Vec &n, double a, double b, double c) { /* s*x1 + t*y1 + n*z1, samplingFunctions.h:58 */
+    Vec s, t;
+    frame(n, s, t);
+    return s * a + t * b + n * c;
+}
+
+/* ---- vptSamplingFunctions.h ---------------------------------------------------------------------- */
+template <class Rng> static inline double free_flight_sample(Rng &rng, double sigma_t) { /* :11-16 */
+    const double xi = rng.next();
+    return -std::log(1 - xi) / sigma_t;
+}
+static inline double free_flight_pdf(double sigma_t, double d) { return sigma_t * std::exp(sigma_t * d * -1.0); } /* :20 */
+static inline double pdf_success(double sigma_t, double tmax) { return 1.0 - std::exp(-sigma_t * tmax); }           /* :24 */
+static inline double pdf_failure(double sigma_t, double tmax) { return std::exp(-sigma_t * tmax); }                 /* :29 */
+static inline Vec sph(double theta, double phi) { return Vec(std::sin(theta) * std::cos(phi), std::sin(theta) * std::sin(phi), std::cos(theta)); }
+template <class Rng> static inline Vec phase_sample(Rng &rng) { /* isotropicPhaseSample :34-46 */
+    const double xi1 = rng.next();
+    const double xi2 = rng.next();
+    return unit(sph(std::acos(1 - 2 * xi1), 2 * kPi * xi2));
+}
+static inline double phase_value() { return 1 / (4 * kPi); } /* isotropicPhaseFunction, volumetricBasicFunctions.h:59 */
+template <class Rng> static inline double equiangular_sample(Rng &rng, double D, double a, double b) { /* :54-57 */
+    const double xi = rng.next();
+    return D * std::tan((1 - xi) * a + xi * b);
+}
+static inline double equiangular_pdf(double D, double a, double b, double t) { return D / std::fabs(b - a) / (t * t + D * D); } /* :60 */
+
+/* transmitance, volumetricBasicFunctions.h:14-21 */
+static inline double transmittance(const Vec &x1, const Vec &x2, double sigma_t) {
+    const Vec v = x2 - x1;
+    const double d = std::sqrt(dot(v, v));
+    return std::exp(sigma_t * d * -1.0);
+}
+
+/* equiAngularParams2, volumetricBasicFunctions.h:209-223 */
+struct EquiAngular { double D, thetaA, thetaB, t_local, t_ray; };
+template <class Rng> static inline EquiAngular equiangular_setup(Rng &rng, const Scene &sc, int source, double tMax, const Ray &r) {
+    EquiAngular e;
+    const Vec dv = sc.s[source].p - r.o;
+    const double len = std::sqrt(dot(dv, dv));
+    const double proj = dot(dv, r.d) / dot(r.d, r.d);
+    e.D = std::sqrt(len * len - proj * proj);
+    e.thetaA = std::atan2(0.0 - proj, e.D);
+    e.thetaB = std::atan2(tMax - proj, e.D);
+    const double xi = rng.next();
+    e.t_local = e.D * std::tan((1 - xi) * e.thetaA + xi * e.thetaB);
+    e.t_ray = e.t_local + proj;
+    return e;
+}
+
+/* ---- samplingFunctions.h -------------------------------------------------------------------------- */
+template <class Rng> static inline Vec cosine_hemisphere(Rng &rng, const Vec &n) { /* :47-62 */
+    const double theta = std::acos(std::sqrt(1 - rng.next()));
+    const double phi = 2 * kPi * rng.next();
+    const Vec l = sph(theta, phi);
+    return unit(from_local(n, l.x, l.y, l.z));
+}
+template <class Rng> static inline Vec cone_sample(Rng &rng, const Vec &wc, double cos_max) { /* solidAngle, :65-82 */
+    const double e0 = rng.next();
+    const double theta = std::acos((1 - e0) + e0 * cos_max);
+    const double phi = 2 * kPi * rng.next();
+    const Vec l = sph(theta, phi);
+    return unit(from_local(wc, l.x, l.y, l.z));
+}
+static inline double cone_pdf(double cos_max) { return 1 / (2 * kPi * (1 - cos_max)); } /* solidAngleProb :85 */
+static inline double cosine_pdf(double c) { return c * 1 / kPi; }                       /* hemiCosineProb :92 */
+
+/* ---- microFacetUtilities.h ------------------------------------------------------------------------- */
+static inline double fresnel_channel(double c, double s, double eta, double kappa) { /* fresnelSpectre :11-18 */
+    const double a2b2 = std::sqrt((eta * eta - kappa * kappa - s * s) * (eta * eta - kappa * kappa - s * s) + 4 * eta * eta * kappa * kappa);
+    const double a = std::sqrt(0.5 * (a2b2 + eta * eta - kappa * kappa - s * s));
+    const double perp = (a2b2 + c * c - 2 * a * c) / (a2b2 + c * c + 2 * a * c);
+    const double par = perp * (a2b2 * c * c + s * s * s * s - 2 * a * c * s * s) / (a2b2 * c * c + s * s * s * s + 2 * a * c * s * s);
+    return 0.5 * (par + perp);
+}
+static inline Vec fresnel_conductor(double cos_h, const Vec &eta, const Vec &kappa) { /* fresnel :21-29 */
+    const double sin_h = std::sqrt(1 - cos_h * cos_h);
+    return Vec(fresnel_channel(cos_h, sin_h, eta.x, kappa.x), fresnel_channel(cos_h, sin_h, eta.y, kappa.y), fresnel_channel(cos_h, sin_h, eta.z, kappa.z));
+}
+static inline double beckmann(double c, double alpha) { /* NDF :34-45 */
+    if (c >= 0) {
+        const double s = std::sqrt(1 - c * c);
+        const double fac1 = kPi * alpha * alpha * c * c * c * c;
+        const double tang = s / c;
+        const double fac2 = std::exp((-1 * tang * tang) / (alpha * alpha));
+        return (1 / fac1) * fac2;
+    }
+    return 0;
+}
+static inline double smith_g1(const Vec &n, const Vec &wv, const Vec &wh, double alpha) { /* Gn :47-61 */
+    const double s = std::sqrt(1 - dot(n, wv) * dot(n, wv));
+    const double tg = s / dot(n, wv);
+    const double a = 1 / (alpha * tg);
+    if (dot(wv, wh) / dot(wv, n) > 0) {
+        if (a < 1.6) {
+            const double num = 3.535 * a + 2.181 * a * a;
+            const double den = 1 + 2.276 * a + 2.577 * a * a;
+            return num / den;
+        }
+        return 1;
+    }
+    return 0;
+}
+static inline double smith_g(const Vec &n, const Vec &wi, const Vec &wo, const Vec &wh, double alpha) { /* G_smith :63-68 */
+    const double g1 = smith_g1(n, wi, wh, alpha);
+    const double g2 = smith_g1(n, wo, wh, alpha);
+    return g1 * g2;
+}
+template <class Rng> static inline Vec facet_normal(Rng &rng, double alpha) { /* vectorFacet :71-84 */
+    const double theta = std::atan(std::sqrt(-alpha * alpha * std::log(1 - rng.next())));
+    const double phi = 2 * kPi * rng.next();
+    return unit(sph(theta, phi));
+}
+static inline double facet_pdf(const Vec &wo, const Vec &wh, double alpha, const Vec &n) { /* microFacetProb :86-92 */
+    const double num = dot(wh, n);
+    const double den = 4 * std::fabs(dot(wo, wh));
+    return beckmann(dot(wh, n), alpha) * num / den;
+}
+static inline Vec facet_brdf(const Vec &eta, const Vec &kappa, const Vec &wi, const Vec &wh, const Vec &wo, double alpha, const Vec &n) { /* frMicroFacet :95-100 */
+    const double den = (4 * std::fabs(dot(n, wi)) * std::fabs(dot(n, wo)));
+    return fresnel_conductor(dot(wi, wh), eta, kappa) * beckmann(dot(n, wh), alpha) * smith_g(n, wi, wo, wh, alpha) * (1 / den);
+}
+static inline double fresnel_dielectric(double etai, double etat, double ct, double ci) { /* fresnelDie :107-112 */
+    const double par = ((etat * ci - etai * ct) / (etat * ci + etai * ct)) * ((etat * ci - etai * ct) / (etat * ci + etai * ct));
+    const double perp = ((etai * ci - etat * ct) / (etai * ci + etat * ct)) * ((etai * ci - etat * ct) / (etai * ci + etat * ct));
+    return 0.5 * (par + perp);
+}
+
+/* powerHeuristics, misSamplingFunctions.h:12-16 */
+static inline double power_heuristic(double f, double g) {
+    const double f2 = f * f, g2 = g * g;
+    return f2 / (f2 + g2);
+}
+
+/* ---- direct light at a surface --------------------------------------------------------------------- */
+/* muestreoSA -> solidAngle(L), samplingFunctions.h:238-247 and :163-206 */
+template <class Rng>
+static inline Vec light_sampled_direct(Rng &rng, Scene &sc, int light, const Vec &x, const Sphere &obj, const Vec &n, const Vec &wray,
+                                       Vec &wi_out, double &cos_max_out, double alpha) {
+    const Sphere &src = sc.s[light];
+    Vec cx = src.p - x;
+    const double len = std::sqrt(dot(cx, cx));
+    cx = cx * (1 / len);
+    const double cos_max = std::sqrt(1 - (src.r / len) * (src.r / len));
+    cos_max_out = cos_max;
+    /* solidAngle(L) */
+    const Vec wi = cone_sample(rng, cx, cos_max);
+    wi_out = wi;
+    Vec wil = to_local(n, wi);
+    Vec wol = to_local(n, wray * -1);
+    wil = unit(wil);
+    wol = unit(wol);
+    const Vec wh = unit(wil + wol);
+    Vec fr;
+    if (obj.material == 0) fr = obj.c * (1 / kPi);
+    else if (obj.material == 2) fr = Vec(0, 0, 0);
+    else fr = facet_brdf(obj.eta, obj.kappa, wil, wh, wol, alpha, Vec(0, 0, 1));
+    double t;
+    int id = 0;
+    scan(sc, Ray{x, wi}, t, id);
+    const Vec Le = (light == id) ? sc.s[id].radiance : Vec();
+    return had(Le, fr) * dot(n, wi) * (1 / cone_pdf(cos_max));
+}
+
+/* uniform, samplingFunctions.h:250-261 */
+template <class Rng>
+static inline Vec bsdf_sampled_direct_lambert(Rng &rng, Scene &sc, const Vec &n, const Vec &x, const Vec &albedo, Vec &wi_out, int &source) {
+    Vec wi = cosine_hemisphere(rng, n);
+    wi = unit(wi);
+    int sid = -1;
+    const Vec Le = first_hit_radiance(sc, x, wi, sid);
+    source = sid;
+    const Vec L = Vec() + had(Le, albedo * (1 / kPi)) * dot(n, wi) * (1 / cosine_pdf(dot(n, wi)));
+    wi_out = wi;
+    return L;
+}
+
+/* microfacet, samplingFunctions.h:97-118 (wray = incoming ray direction, wh local) */
+static inline Vec bsdf_sampled_direct_facet(Scene &sc, const Vec &x, const Vec &wray, const Vec &wh, const Vec &n, const Sphere &obj, double alpha, int &source) {
+    const Vec nl(0, 0, 1);
+    Vec wo = wray * (-1);
+    wo = unit(to_local(n, wo));
+    Vec wi = unit(wo * (-1) + wh * 2 * dot(wh, wo));
+    const Vec wig = unit(from_local(n, wi.x, wi.y, wi.z));
+    int sid = -1;
+    const Vec Le = first_hit_radiance(sc, x, wig, sid);
+    source = sid;
+    const Vec fr = facet_brdf(obj.eta, obj.kappa, wi, wh, wo, alpha, nl);
+    return had(Le, fr) * dot(nl, wi) * (1 / facet_pdf(wo, wh, alpha, nl));
+}
+
+/* MISv2, misSamplingFunctions.h:96-170 (materials 0 and 1) */
+template <class Rng>
+static inline Vec surface_direct_mis(Rng &rng, Scene &sc, const Sphere &obj, const Vec &x, const Vec &n, const Vec &wray, double alpha, double sigma_t) {
+    Vec total;
+    Vec wo = wray * -1;
+    double cos_max = 0; /* reference: uninitialised */
+    const int count = (int)sc.s.size();
+    for (int light = 0; light < count; ++light) {
+        if (sc.s[light].r > 0 && sc.s[light].radiance.x > 0) {
+            Vec wi_light;
+            const Vec f = light_sampled_direct(rng, sc, light, x, obj, n, wray, wi_light, cos_max, alpha) * transmittance(x, sc.s[light].p, sigma_t);
+            const double fpdf = cone_pdf(cos_max);
+            double gpdf;
+            if (obj.material == 0) gpdf = cosine_pdf(dot(n, wi_light));
+            else {
+                const Vec wh = unit(wi_light + wo);
+                gpdf = facet_pdf(wo, wh, alpha, n);
+            }
+            const double wf = power_heuristic(fpdf, gpdf);
+            total = total + f * wf;
+        }
+    }
+    Vec g;
+    double wg;
+    if (obj.material == 0) {
+        Vec wi_b;
+        int source = -1;
+        g = bsdf_sampled_direct_lambert(rng, sc, n, x, obj.c, wi_b, source);
+        const double gpdf = cosine_pdf(dot(n, wi_b));
+        if (g.x > 0 && g.y > 0 && g.z > 0) {
+            cos_max = cone_cos(sc, source, x);
+            const double fpdf = cone_pdf(cos_max);
+            wg = power_heuristic(gpdf, fpdf);
+        } else wg = 0;
+    } else {
+        const Vec wh = facet_normal(rng, alpha);
+        wo = unit(to_local(n, wo));
+        int source = -1;
+        g = bsdf_sampled_direct_facet(sc, x, wray, wh, n, obj, alpha, source);
+        const double gpdf = facet_pdf(wo, wh, alpha, Vec(0, 0, 1));
+        if (g.x > 0) cos_max = cone_cos(sc, source, x);
+        const double fpdf = cone_pdf(cos_max);
+        wg = power_heuristic(gpdf, fpdf);
+    }
+    return total + g * wg;
+}
+/* pLight, vptShadeMethods.h:62-91.  Without material-3 spheres visibilityVPT == visibility and multipleT == 1,
+ * so the second branch (:70-74) cannot fire. */
+static inline Vec point_light_direct(Scene &sc, const Sphere &obj, const Vec &x, const Vec &n, const Vec &wray, const Vec &I, const Vec &light, double alpha) {
+    Vec Le;
+    if (visible(sc, light, x)) Le = I * (1 / dot(light - x, light - x));
+    else {
+        ++sc.scans; /* the reference repeats the scan through visibilityVPT (:70); same answer */
+    }
+    Vec wi = unit(light - x);
+    Vec wo = wray * -1;
+    wo = to_local(n, wo);
+    wi = to_local(n, wi);
+    wi = unit(wi);
+    wo = unit(wo);
+    const Vec wh = unit(wi + wo);
+    Vec fr;
+    if (obj.material == 1) fr = facet_brdf(obj.eta, obj.kappa, wi, wh, wo, alpha, Vec(0, 0, 1));
+    else fr = obj.c * (1 / kPi);
+    return had(Le, fr) * dot(n, unit(light - x));
+}
+
+/* bdsf, vptShadeMethods.h:16-59 (materials 0 and 1) */
+template <class Rng>
+static inline Vec bsdf_sample(Rng &rng, const Scene &sc, Vec &wi_out, const Vec &wray, const Vec &n, double &pdf, int id) {
+    const Sphere &obj = sc.s[id];
+    const Vec wo = wray * -1;
+    Vec fs;
+    if (obj.material == 0) {
+        const Vec wi = cosine_hemisphere(rng, n);
+        fs = obj.c * (1 / kPi);
+        pdf = cosine_pdf(dot(n, wi));
+        wi_out = wi;
+    } else {
+        const double alpha = obj.alpha;
+        Vec wh = facet_normal(rng, alpha);
+        wh = from_local(n, wh.x, wh.y, wh.z);
+        const Vec wi = wo * (-1) + wh * 2 * dot(wh, wo);
+        fs = facet_brdf(obj.eta, obj.kappa, wi, wh, wo, alpha, n);
+        pdf = facet_pdf(wo, wh, alpha, n);
+        wi_out = wi;
+    }
+    return fs;
+}
+
+/* ---- in-medium next-event estimation ------------------------------------------------------------- */
+/* shared body of freeSingleScattering (volumetricBasicFunctions.h:284-340, in_medium_factor = 1) and
+ * singleScattering (:225-281, in_medium_factor = transmitanceXT * sigma_s applied in the reference's order) */
+template <class Rng>
+static inline Vec medium_direct(Rng &rng, Scene &sc, const Vec &xt, int source, double sigma_t, double prob_source, bool equi, double sigma_s, double T_xt) {
+    const Sphere &src = sc.s[source];
+    Vec Ld;
+    if (src.r == 0) {
+        const Vec light = src.p;
+        if (visible(sc, light, xt)) {
+            Vec Le = src.radiance;
+            const double d2 = dot(light - xt, light - xt);
+            Le = Le * (1 / d2);
+            const Vec Ls = Le * transmittance(xt, light, sigma_t) * phase_value();
+            Ld = equi ? Ls * T_xt * sigma_s * (1 / prob_source) : Ls * (1 / prob_source);
+        }
+    }
+    Vec wc = src.p - xt;
+    const double len = std::sqrt(dot(wc, wc));
+    wc = wc * (1 / len);
+    const double cos_max = std::sqrt(1 - src.r / len * (src.r / len));
+    const Vec wl = cone_sample(rng, wc, cos_max);
+    const double prob_wl = cone_pdf(cos_max);
+    double dist;
+    int hit_id = -1;
+    scan(sc, Ray{xt, wl}, dist, hit_id);
+    if (source == hit_id) {
+        const Vec Le = src.radiance;
+        const double Tr = std::exp(sigma_t * dist * -1.0);
+        const Vec Ls = Le * Tr * phase_value();
+        Ld = equi ? Ls * T_xt * sigma_s * (1 / prob_wl) * (1 / prob_source) : Ls * (1 / prob_wl) * (1 / prob_source);
+    }
+    return Ld;
+}
+
+/* ---- estimators ------------------------------------------------------------------------------------ */
+struct Settings {
+    int method = 0;              /* 0 free-flight (vptShadeMethods.h:1263), 1 equi-angular (:1014), 2 "MIS" (:1345) */
+    double sigma_a = 0.001, sigma_s = 0.009; /* src/rt.cpp:794 */
+    double continue_prob = 0.6;  /* vptShadeMethods.h:1275 */
+    int max_depth = 0;           /* <= 0: unlimited (reference) */
+};
+struct PathStats { uint64_t events = 0; };
+
+/* One camera path.  The reference's recursion (methods 1, 2) is unrolled into throughput form
+ * (L += beta * A ; beta *= B): identical up to the rounding of the re-associated sum. */
+template <class Rng>
+static inline Vec radiance(Rng &rng, Scene &sc, Ray ray, const Settings &cfg, PathStats *stats = nullptr) {
+    Vec L, beta(1, 1, 1);
+    const double sigma_t = cfg.sigma_a + cfg.sigma_s;
+    const double cp = cfg.continue_prob, q = 1 - cp;
+    const int n_spheres = (int)sc.s.size();
+    for (int depth = 0; cfg.max_depth <= 0 || depth < cfg.max_depth; ++depth) {
+        rng.begin_bounce(depth);
+        if (rng.next() < q) break; /* :1282 / :1022 / :1353 */
+        if (stats) ++stats->events;
+
+        double t;
+        int id = 0;
+        const bool hit = scan(sc, ray, t, id);
+        if (!hit) t = kMaxFloat;
+        const Vec xs = ray.o + ray.d * t;
+        double Tr = 0;
+        if (cfg.method == 1 && hit) Tr = transmittance(ray.o, xs, sigma_t); /* :1046 */
+        const Vec n = unit(xs - sc.s[id].p);
+
+        int emitters[VPT_ORACLE_MAX_EMITTERS];
+        int count = 0;
+        for (int i = 0; i < n_spheres && count < VPT_ORACLE_MAX_EMITTERS; ++i)
+            if (sc.s[i].emits()) emitters[count++] = i;
+        if (count == 0) break;
+        const double prob_source = 1.0 / count;
+        const int source = emitters[static_cast<int>(rng.next() * count)];
+
+        bool surface;
+        double dist = 0, pdf_medium = 1;
+        if (cfg.method == 0) {
+            dist = free_flight_sample(rng, sigma_t); /* :1305 */
+            surface = dist > t;
+        } else {
+            if (cfg.method == 2) Tr = std::exp(sigma_t * t * -1.0); /* psurf :1407 */
+            const EquiAngular e = equiangular_setup(rng, sc, source, t, ray);
+            pdf_medium = equiangular_pdf(e.D, e.thetaA, e.thetaB, e.t_local) * (1.0 - Tr); /* :1093 / :1411 */
+            dist = e.t_ray;
+            const double xi = rng.next();
+            surface = (cfg.method == 1) ? (xi <= Tr) : (xi < Tr); /* :1096 / :1414 */
+        }
+
+        if (surface) {
+            const Sphere &obj = sc.s[id];
+            if (obj.emits()) { /* :1308-1313 / :1099-1106 */
+                if (depth == 0) L = had(obj.radiance, beta);
+                break;
+            }
+            const Sphere &src = sc.s[source];
+            const double Trs = transmittance(xs, src.p, sigma_t);
+            const Vec Ld_point = point_light_direct(sc, obj, xs, n, ray.d, src.radiance, src.p, obj.alpha) * Trs * (1 / prob_source);
+            const Vec Ld = surface_direct_mis(rng, sc, obj, xs, n, ray.d, obj.alpha, sigma_t);
+            Vec wi;
+            double pdf;
+            const Vec fs = bsdf_sample(rng, sc, wi, ray.d, n, pdf, id);
+            wi = unit(wi);
+            const double cosine = dot(n, wi);
+            L = L + had(Ld_point + Ld, beta) * (1 / cp);
+            beta = had(beta, fs) * (1 / cp) * cosine * (1 / pdf);
+            ray = Ray{xs, wi};
+        } else {
+            const Vec xt = ray.o + ray.d * dist;
+            if (cfg.method == 0) {
+                const Vec Ld = medium_direct(rng, sc, xt, source, sigma_t, prob_source, false, 0, 0);
+                const Vec wi = phase_sample(rng);
+                L = L + had(Ld, beta) * (cfg.sigma_s / sigma_t) * (1 / cp);
+                beta = beta * (cfg.sigma_s / sigma_t) * (1 / cp);
+                ray = Ray{xt, wi};
+            } else {
+                const double T = transmittance(ray.o, xt, sigma_t);
+                const Vec Ld = medium_direct(rng, sc, xt, source, sigma_t, prob_source, true, cfg.sigma_s, T);
+                const Vec wi = phase_sample(rng);
+                L = L + had(Ld * (1 / pdf_medium) * (1 / cp), beta);
+                beta = beta * cfg.sigma_s * T * (1 / cp) * (1 / pdf_medium);
+                ray = Ray{xt, wi};
+            }
+        }
+    }
+    return L;
+}
+
+/* ---- camera, src/rt.cpp:752-759 and :787 (parameters are the reference's literals by default) -------- */
+struct Camera {
+    Vec o, d, cx, cy;
+    int w, h;
+    Camera(int w_, int h_, Vec o_ = Vec(0, 11.2, 214), Vec dir = Vec(0, -0.042612, -1), double fov = 0.5095) : w(w_), h(h_) {
+        o = o_;
+        d = unit(dir);
+        cx = Vec(w * fov / h, 0., 0.);
+        cy = unit(cross(cx, d)) * fov;
+    }
+    Ray ray(int x, int y, double xi1, double xi2) const {
+        const Vec v = cx * ((static_cast<double>(x) + xi1 - 0.5) / w - .5) + cy * ((static_cast<double>(y) + xi2 - 0.5) / h - .5) + d;
+        return Ray{o, unit(v)};
+    }
+};
+
+/* ---- random streams ---------------------------------------------------------------------------------- */
+/* explicit list of uniforms (e.g. an erand48 sequence captured from the reference) */
+struct ListRng {
+    const double *u; size_t n, i = 0; bool overrun = false;
+    ListRng(const double *u_, size_t n_) : u(u_), n(n_) {}
+    void begin_bounce(int) {}
+    double next() { if (i >= n) { overrun = true; return 0.5; } return u[i++]; }
+};
+/* POSIX erand48, sequential (the reference's generator, Vector.h:38) */
+struct Erand48Rng {
+    unsigned short s[3]; uint64_t draws = 0;
+    Erand48Rng(unsigned a, unsigned b, unsigned c) { s[0] = (unsigned short)a; s[1] = (unsigned short)b; s[2] = (unsigned short)c; }
+    void begin_bounce(int) {}
+    double next() { ++draws; return erand48(s); }
+};
+/* Philox4x32-10 keyed (pixel, sample, bounce): the product's stream convention (oracle/philox.h).
+ * Bounce 0 starts at draw 0 = the two pixel-jitter draws, then the path's own draws. */
+struct PhiloxRng {
+    uint32_t key[2], ctr[4], out[4]; unsigned idx = 0;
+    PhiloxRng(uint64_t seed, uint32_t pixel, uint32_t sample) {
+        key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32);
+        ctr[0] = pixel; ctr[1] = sample; ctr[2] = 0; ctr[3] = 0;
+    }
+    void begin_bounce(int b) { if (b == 0) return; ctr[2] = (uint32_t)b; idx = 0; }
+    double next() {
+        if ((idx & 3u) == 0) { ctr[3] = idx >> 2; vpt_philox4x32_10(ctr, key, out); }
+        return vpt_u32_to_unit(out[idx++ & 3u]);
+    }
+};
+
+} /* namespace vpt_oracle */
+#endif
