@@ -1,0 +1,158 @@
+/* include/vpt.h -- C-ABI boundary of the B200-native volumetric path tracer (libvpt_b200.so).
+ *
+ * The reference (gabo99cas/minimal_volumetric_path_tracer) has no plugin/FFI interface: its hot path is
+ * the OpenMP pixel loop src/rt.cpp:767-805, which calls one shade method per sample
+ *     Color iterativeVPTracerFree      (const Ray&, double sigma_a, double sigma_s)        vptShadeMethods.h:1263
+ *     Color explicitVPTracerRecursive  (const Ray&, double sigma_a, double sigma_s, int)   vptShadeMethods.h:1014
+ *     Color MISVPTTracerRecursive      (const Ray&, double sigma_a, double sigma_s, int)   vptShadeMethods.h:1345
+ * with the scene in the global `std::vector<Sphere> spheres` (Sphere.h:49, Sphere.cpp:7-22) and the RNG in the
+ * global `seed` (Vector.h:38).  vpt_render() replaces that loop in ONE call: the host keeps the set-up
+ * (rt.cpp:744-762) and the tonemap / PPM write (rt.cpp:808-829).  INTEGRATION.md shows the call site.
+ *
+ * Conventions: plain C types only; every function returns 0 (VPT_OK) or a negative vpt_status and never throws;
+ * the library keeps no mutable global state; the caller owns every buffer; there is NO CPU fallback -- without a
+ * usable CUDA device every compute entry point returns VPT_ERR_NO_DEVICE / VPT_ERR_CUDA.
+ */
+#ifndef VPT_H
+#define VPT_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPT_MAX_SPHERES 32  /* reference: unbounded std::vector */
+#define VPT_MAX_EMITTERS 16 /* reference: `int arr[4]` overflows beyond 4 (vptShadeMethods.h:1293); here a checked limit */
+
+typedef enum {
+    VPT_OK = 0,
+    VPT_ERR_INVALID_ARGUMENT = -1, /* null pointer, non-positive size, bad enum, sample range outside [0, spp] ... */
+    VPT_ERR_SCENE = -2,            /* n_spheres out of range, too many emitters, negative radius, non-finite field */
+    VPT_ERR_UNSUPPORTED = -3,      /* material 2/3 (outside the hot-path scope); quirks requested in fp32 precision */
+    VPT_ERR_NO_DEVICE = -4,        /* no CUDA device / bad ordinal */
+    VPT_ERR_CUDA = -5,             /* a CUDA runtime call failed; vpt_last_cuda_error() has the text */
+    VPT_ERR_IO = -6                /* vpt_write_ppm could not write */
+} vpt_status;
+
+/* Sphere.h:14-21, same fields, same order as the Sphere constructor (Sphere.h:23). */
+typedef struct {
+    double r;           /* 0 = point light */
+    double p[3];        /* centre */
+    double c[3];        /* Lambert albedo */
+    double radiance[3]; /* > 0 in any channel = emitter (vptShadeMethods.h:1296) */
+    int32_t material;   /* 0 Lambert, 1 Beckmann conductor microfacet (2 dielectric, 3 volumetric: unsupported) */
+    int32_t _pad;
+    double eta[3], kappa[3];
+    double alpha; /* Beckmann roughness */
+} vpt_sphere;
+
+enum { VPT_METHOD_FREE_FLIGHT = 0, VPT_METHOD_EQUIANGULAR = 1, VPT_METHOD_MIS = 2 };
+enum { VPT_PRECISION_FP32 = 0, VPT_PRECISION_FP64_REF = 1 };
+enum { VPT_OUTPUT_SUM = 0, VPT_OUTPUT_MEAN = 1 };
+enum { VPT_KERNEL_AUTO = 0, VPT_KERNEL_MEGA = 1, VPT_KERNEL_WAVEFRONT = 2 };
+/* Two behaviours of the reference are decided by FP64 rounding (DESIGN.md "Parity hazards"):
+ *  R0_FALLTHROUGH   the in-medium point-light connection is overwritten with 0 whenever the r == 0 sphere registers as
+ *                   hit in the solid-angle block (volumetricBasicFunctions.h:310-337 / :251-278);
+ *  EXACT_VISIBILITY visibility() tests `t > distance` with no epsilon (pathTracingUtilities.h:48).
+ * They exist only in FP64_REF precision, where the reference's operation order is reproduced; FP32 precision implements
+ * the well-defined alternative (r == 0 spheres are not ray-intersected; `t > distance * (1 - 1e-4)`). */
+enum { VPT_QUIRK_R0_FALLTHROUGH = 1u, VPT_QUIRK_EXACT_VISIBILITY = 2u, VPT_QUIRKS_REFERENCE = 3u, VPT_QUIRKS_NONE = 0u };
+
+typedef struct {
+    int32_t width, height;            /* rt.cpp:752 (1024 x 768) */
+    int32_t spp;                      /* argv[1], rt.cpp:784: samples per pixel of the WHOLE render */
+    int32_t sample_begin, sample_end; /* this call renders samples [begin, end); 0,0 = [0, spp) (shard / resume) */
+    int32_t tile_rank, tile_count;    /* this call renders pixel tiles with tile_id % tile_count == tile_rank; 0,0 = all */
+    int32_t method;                   /* VPT_METHOD_*: which line of rt.cpp:791-796 is active */
+    int32_t max_depth;                /* <= 0: unlimited (reference) */
+    double sigma_a, sigma_s;          /* 0.001, 0.009 (rt.cpp:794) */
+    double continue_prob;             /* 0.6 (vptShadeMethods.h:1275) */
+    double cam_o[3], cam_dir[3], fov; /* (0,11.2,214), (0,-0.042612,-1), 0.5095 (rt.cpp:755-759) */
+    uint64_t seed;                    /* Philox key; replaces getentropy (rt.cpp:746) */
+    uint32_t quirks;                  /* VPT_QUIRK_* (FP64_REF only) */
+    int32_t precision;                /* VPT_PRECISION_* */
+    int32_t output;                   /* VPT_OUTPUT_SUM: per-pixel sum over the rendered samples; MEAN: sum / spp (rt.cpp:800) */
+    int32_t kernel;                   /* VPT_KERNEL_* */
+    int32_t device;                   /* CUDA ordinal */
+    int32_t _pad;
+} vpt_params;
+
+typedef struct {
+    uint64_t paths;       /* camera paths traced = pixels rendered x samples */
+    uint64_t events;      /* path vertices that survived Russian roulette */
+    uint64_t scene_scans; /* all-sphere intersection passes */
+    uint64_t nonfinite;   /* paths whose radiance was NaN/Inf and was dropped (0 in a healthy run) */
+    double kernel_ms;     /* CUDA-event time of the render kernels only */
+    double total_ms;      /* wall time of the call including copies */
+    uint64_t launches;    /* kernels launched by this call */
+} vpt_stats;
+
+/* The reference's literals (see the field comments); spp = 64, precision FP32, quirks NONE, output MEAN. */
+void vpt_default_params(vpt_params *p);
+/* Sphere.cpp:11-22 restated as data; returns the sphere count (10) or VPT_ERR_INVALID_ARGUMENT if cap is too small. */
+int vpt_default_scene(vpt_sphere *out, int32_t cap);
+
+/* Replaces the pixel loop rt.cpp:767-805.  hdr_rgb: HOST buffer, width*height*3 floats, pixel index (h-y-1)*w+x as
+ * rt.cpp:773 (row 0 = top of the image), UNCLAMPED linear radiance; pixels outside this call's tiles are written as 0. */
+int vpt_render(const vpt_params *p, const vpt_sphere *spheres, int32_t n_spheres, float *hdr_rgb, vpt_stats *stats /* nullable */);
+/* Same, but hdr_rgb is a DEVICE buffer on p->device and the work is enqueued on `cuda_stream` (a cudaStream_t, may be 0).
+ * With stats == NULL the call does not synchronise; with stats != NULL it synchronises the stream before returning. */
+int vpt_render_device(const vpt_params *p, const vpt_sphere *spheres, int32_t n_spheres, float *hdr_rgb_device, void *cuda_stream, vpt_stats *stats);
+/* One frame sharded over n_devices GPUs of this process by interleaved pixel tiles (one host thread per device).  The tiles
+ * are disjoint, so each device copies its own strided tile ranges straight into the caller's buffer: no reduction step.
+ * (Multi-process sharding -- one rank per GPU and one NCCL reduce of the HDR buffers -- lives in the host layer,
+ * minimal_volumetric_path_tracer_b200/distributed.py.) */
+int vpt_render_multi(const vpt_params *p, const vpt_sphere *spheres, int32_t n_spheres, const int32_t *devices, int32_t n_devices, float *hdr_rgb, vpt_stats *stats);
+
+/* Host output stage, byte-identical to rt.cpp:803,812-820 + mathUtilities.h:34-45: clamp, gamma 2.2, "P3" text.
+ * hdr_rgb holds per-pixel MEAN radiance. */
+int vpt_tonemap(const float *hdr_rgb, int32_t width, int32_t height, uint8_t *rgb8_out);
+int vpt_write_ppm(const float *hdr_rgb, int32_t width, int32_t height, const char *path);
+
+/* Unit kernels: one device thread per row evaluates the device implementation of one reference function, so that it
+ * can be compared with the reference's C++ function on identical inputs (tolerance 1e-5 relative in FP32).
+ * `in` is n x in_stride doubles, `out` is n x out_stride doubles (host).  Row layouts: see vpt_unit below. */
+typedef enum {
+    VPT_UNIT_SPHERE_INTERSECT = 0, /* Sphere.h:27            in: sphere_index, o[3], d[3]              out: t */
+    VPT_UNIT_INTERSECT = 1,        /* pathTracingUtilities.h:12  in: o[3], d[3]                        out: hit, t, id */
+    VPT_UNIT_VISIBILITY = 2,       /* pathTracingUtilities.h:39  in: light[3], x[3]                    out: visible */
+    VPT_UNIT_TRANSMITTANCE = 3,    /* volumetricBasicFunctions.h:14  in: x1[3], x2[3], sigma_t         out: T */
+    VPT_UNIT_FREE_FLIGHT = 4,      /* vptSamplingFunctions.h:11-31  in: sigma_t, xi                    out: d, freeFlightProb(d), pdfSuccess(d), pdfFailure(d) */
+    VPT_UNIT_PHASE_SAMPLE = 5,     /* vptSamplingFunctions.h:34  in: xi1, xi2                          out: w[3] */
+    VPT_UNIT_EQUIANGULAR = 6,      /* volumetricBasicFunctions.h:209 + vptSamplingFunctions.h:60
+                                      in: source_index, tMax, o[3], d[3], xi                          out: D, thetaA, thetaB, t_local, t_ray, pdf */
+    VPT_UNIT_POWER_HEURISTIC = 7,  /* misSamplingFunctions.h:12  in: f, g                              out: w */
+    VPT_UNIT_COSINE_HEMISPHERE = 8,/* samplingFunctions.h:47     in: n[3], xi1, xi2                    out: w[3], hemiCosineProb(n.w) */
+    VPT_UNIT_CONE_SAMPLE = 9,      /* samplingFunctions.h:65,85  in: wc[3], r, dist, xi1, xi2 (cos_max = sqrt(1-(r/dist)^2))  out: w[3], solidAngleProb */
+    VPT_UNIT_MICROFACET = 10,      /* microFacetUtilities.h:21-100  in: eta[3], kappa[3], alpha, wi[3], wo[3] (local, n = z; wh = normalize(wi+wo))
+                                                                                                     out: fr[3], microFacetProb, NDF, G_smith */
+    VPT_UNIT_FACET_NORMAL = 11,    /* microFacetUtilities.h:71   in: alpha, xi1, xi2                   out: wh[3] */
+    VPT_UNIT_MEDIUM_NEE = 12,      /* volumetricBasicFunctions.h:284 (T_xt < 0) / :225 (T_xt >= 0)
+                                      in: xt[3], source_index, sigma_t, sigma_s, T_xt, prob_source, xi1, xi2   out: Ld[3] */
+    VPT_UNIT_POINT_LIGHT = 13,     /* vptShadeMethods.h:62       in: obj_index, x[3], n[3], wray[3], source_index   out: L[3] */
+    VPT_UNIT_SURFACE_MIS = 14,     /* misSamplingFunctions.h:96  in: obj_index, x[3], n[3], wray[3], sigma_t, xi[8]   out: L[3] */
+    VPT_UNIT_BSDF_SAMPLE = 15,     /* vptShadeMethods.h:16       in: obj_index, n[3], wray[3], xi1, xi2      out: fs[3], wi[3], pdf */
+    VPT_UNIT_RADIANCE = 16,        /* the three shade methods    in: o[3], d[3], pixel, sample  (Philox stream (pixel, sample), jitter draws skipped;
+                                      method, sigma_*, continue_prob, max_depth, seed, quirks from `p`)  out: L[3], events */
+    VPT_UNIT_CAMERA_RAY = 17,      /* rt.cpp:787                 in: x, y, xi1, xi2 (width, height, camera from `p`)   out: d[3] */
+    VPT_UNIT_COUNT_
+} vpt_unit_fn;
+int vpt_unit(int32_t fn, const vpt_params *p, const vpt_sphere *spheres, int32_t n_spheres, int32_t n, const double *in, int32_t in_stride,
+             double *out, int32_t out_stride);
+int vpt_unit_strides(int32_t fn, int32_t *in_stride, int32_t *out_stride);
+
+/* Philox4x32-10 on the device (the stream the renders use): ctr/key/out are host arrays of n x 4 / n x 2 / n x 4 words. */
+int vpt_philox(int32_t device, int32_t n, const uint32_t *ctr, const uint32_t *key, uint32_t *out);
+
+/* Register-resident FFMA microbenchmark: the measured FP32 roofline denominator. */
+int vpt_measure_fp32_peak(int32_t device, double *tflops_out, double *sm_clock_mhz_out /* nullable */);
+
+int vpt_device_count(void);
+const char *vpt_strerror(int status);
+const char *vpt_last_cuda_error(void); /* thread-local text of the last CUDA failure seen by this thread */
+const char *vpt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPT_H */

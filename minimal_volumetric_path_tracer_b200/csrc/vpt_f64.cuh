@@ -1,0 +1,405 @@
+// vpt_f64.cuh -- FP64 "REF mode" device implementation: the reference's estimators in the reference's own operation
+// order (this translation unit is compiled with -fmad=false, so no contraction changes a rounding), including its two
+// rounding-decided behaviours when the corresponding VPT_QUIRK_* bit is set.  Purpose: renders that are statistically
+// indistinguishable from the as-shipped CPU reference, and per-path agreement with the FP64
+// CPU oracle to libm level.  B200 keeps a full-rate FP64 pipe (unlike sm_103), so this mode is a usable product path,
+// just slower than vpt_f32.cuh.
+//
+// Undefined behaviour of the reference that is defined here (same choices as oracle/vpt_oracle.hpp): `idHitted` /
+// `sourceid` on a miss = -1; MISv2's stale `costhetaMax` starts at 0; up to VPT_MAX_EMITTERS emitters.
+#pragma once
+#include <cuda_runtime.h>
+#include "vpt_internal.h"
+#include "vpt_philox.cuh"
+
+namespace vpt {
+namespace f64 {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kMaxFloat = 3.40282346638528859811704183484516925e+38;
+constexpr double kDblMax = 1.7976931348623157e+308;
+
+struct D3 { double x, y, z; };
+__device__ __forceinline__ D3 mk(double x, double y, double z) { return D3{x, y, z}; }
+__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ D3 operator*(D3 a, double s) { return mk(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }             // Vector.h:27
+__device__ __forceinline__ D3 had(D3 a, D3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }                // Vector.h:30
+__device__ __forceinline__ D3 cross(D3 a, D3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); } // :24
+__device__ __forceinline__ D3 unit(D3 a) { return a * (1.0 / sqrt(a.x * a.x + a.y * a.y + a.z * a.z)); }      // Vector.h:33
+
+__device__ __forceinline__ D3 pos(const SphereD &s) { return mk(s.px, s.py, s.pz); }
+__device__ __forceinline__ D3 rad(const SphereD &s) { return mk(s.lr, s.lg, s.lb); }
+__device__ __forceinline__ D3 alb(const SphereD &s) { return mk(s.cr, s.cg, s.cb); }
+__device__ __forceinline__ D3 v3(const double *p) { return mk(p[0], p[1], p[2]); }
+
+struct Ctx { // everything a path needs besides its own state
+    const SphereD *s; // shared-memory copy of the scene
+    int n_spheres, n_emitters;
+    const int *emitters;
+    unsigned quirks;
+    double sigma_a, sigma_s, sigma_t, cp, q;
+    int method, max_depth;
+};
+struct Tally { unsigned events, scans; };
+
+// Sphere::intersect, Sphere.h:27-37
+__device__ __forceinline__ double sphere_t(const SphereD &s, D3 o, D3 d) {
+    const D3 op = o - pos(s);
+    const double b = dot(op, d);
+    const double det = b * b - dot(op, op) + s.r * s.r;
+    if (det < 0) return 0.0;
+    const double root = sqrt(det);
+    const double t_far = -b + root, t_near = -b - root;
+    if (t_near < 0 || fabs(t_near) < 0.0001) return t_far;
+    return t_near;
+}
+// intersect, pathTracingUtilities.h:12-36 (id only written on a hit; t = 0 on a miss)
+__device__ __forceinline__ bool scan(const Ctx &c, D3 o, D3 d, double &t, int &id, Tally &tl) {
+    double best = kDblMax;
+    bool any = false;
+    ++tl.scans;
+    const bool skip_r0 = !(c.quirks & VPT_QUIRK_R0_FALLTHROUGH);
+    for (int i = 0; i < c.n_spheres; ++i) {
+        if (skip_r0 && c.s[i].r == 0) continue;
+        const double ti = sphere_t(c.s[i], o, d);
+        if (ti > 0 && fabs(ti) > 0.0001) {
+            any = true;
+            if (ti < best) { best = ti; id = i; }
+        }
+    }
+    t = any ? best : 0;
+    return any;
+}
+// visibility, pathTracingUtilities.h:39-53
+__device__ __forceinline__ bool visible(const Ctx &c, D3 light, D3 x, Tally &tl) {
+    D3 lx = light - x;
+    const double distance = sqrt(dot(lx, lx));
+    lx = unit(lx);
+    lx = lx * -1;
+    int id = 0;
+    double t;
+    scan(c, light, lx, t, id, tl);
+    if (c.quirks & VPT_QUIRK_EXACT_VISIBILITY) return t > distance || t == 0;
+    return t == 0 || t > distance * (1.0 - 1e-4);
+}
+// rayTracer, pathTracingUtilities.h:56-64
+__device__ __forceinline__ D3 first_hit_radiance(const Ctx &c, D3 x, D3 wi, int &source, Tally &tl) {
+    double t;
+    int id = 0;
+    if (!scan(c, x, wi, t, id, tl)) return mk(0, 0, 0);
+    source = id;
+    return rad(c.s[id]);
+}
+// cosinethetaMax, pathTracingUtilities.h:66-73
+__device__ __forceinline__ double cone_cos(const Ctx &c, int source, D3 x) {
+    const double radius = c.s[source].r;
+    const D3 cx = pos(c.s[source]) - x;
+    const double len = sqrt(dot(cx, cx));
+    return sqrt(1 - (radius / len) * (radius / len));
+}
+// coordinateSystem / coordinateTraspose, mathUtilities.h:10-30
+__device__ __forceinline__ void frame(D3 n, D3 &s, D3 &t) {
+    if (fabs(n.x) > fabs(n.y)) {
+        const double inv = 1.0 / sqrt(n.x * n.x + n.z * n.z);
+        t = mk(n.z * inv, 0.0, -n.x * inv);
+    } else {
+        const double inv = 1.0 / sqrt(n.y * n.y + n.z * n.z);
+        t = mk(0.0, n.z * inv, -n.y * inv);
+    }
+    s = cross(t, n);
+}
+__device__ __forceinline__ D3 to_local(D3 n, D3 w) {
+    D3 s, t;
+    frame(n, s, t);
+    return mk(s.x, t.x, n.x) * w.x + mk(s.y, t.y, n.y) * w.y + mk(s.z, t.z, n.z) * w.z;
+}
+__device__ __forceinline__ D3 from_local(D3 n, D3 l) {
+    D3 s, t;
+    frame(n, s, t);
+    return s * l.x + t * l.y + n * l.z;
+}
+__device__ __forceinline__ D3 sph(double theta, double phi) {
+    double st, ct, sp, cp;
+    sincos(theta, &st, &ct);
+    sincos(phi, &sp, &cp);
+    return mk(st * cp, st * sp, ct);
+}
+// vptSamplingFunctions.h:34-46 / samplingFunctions.h:47-62 / :65-82
+__device__ __forceinline__ D3 phase_sample(double xi1, double xi2) { return unit(sph(acos(1 - 2 * xi1), 2 * kPi * xi2)); }
+__device__ __forceinline__ D3 cosine_hemisphere(D3 n, double xi1, double xi2) { return unit(from_local(n, sph(acos(sqrt(1 - xi1)), 2 * kPi * xi2))); }
+__device__ __forceinline__ D3 cone_sample(D3 wc, double cos_max, double e0, double xi2) { return unit(from_local(wc, sph(acos((1 - e0) + e0 * cos_max), 2 * kPi * xi2))); }
+__device__ __forceinline__ double cone_pdf(double cos_max) { return 1 / (2 * kPi * (1 - cos_max)); } // samplingFunctions.h:85
+__device__ __forceinline__ double cosine_pdf(double c) { return c * 1 / kPi; }                       // samplingFunctions.h:92
+__device__ __forceinline__ double phase_value() { return 1 / (4 * kPi); }                            // volumetricBasicFunctions.h:59
+__device__ __forceinline__ double transmittance(D3 a, D3 b, double sigma_t) {                        // volumetricBasicFunctions.h:14-21
+    const D3 v = b - a;
+    return exp(sigma_t * sqrt(dot(v, v)) * -1.0);
+}
+__device__ __forceinline__ double power_heuristic(double f, double g) { const double f2 = f * f, g2 = g * g; return f2 / (f2 + g2); }
+
+// microFacetUtilities.h
+__device__ __forceinline__ double fresnel_channel(double c, double s, double eta, double kappa) { // :11-18
+    const double a2b2 = sqrt((eta * eta - kappa * kappa - s * s) * (eta * eta - kappa * kappa - s * s) + 4 * eta * eta * kappa * kappa);
+    const double a = sqrt(0.5 * (a2b2 + eta * eta - kappa * kappa - s * s));
+    const double perp = (a2b2 + c * c - 2 * a * c) / (a2b2 + c * c + 2 * a * c);
+    const double par = perp * (a2b2 * c * c + s * s * s * s - 2 * a * c * s * s) / (a2b2 * c * c + s * s * s * s + 2 * a * c * s * s);
+    return 0.5 * (par + perp);
+}
+__device__ __forceinline__ D3 fresnel_conductor(double ch, const double *eta, const double *kappa) { // :21-29
+    const double sh = sqrt(1 - ch * ch);
+    return mk(fresnel_channel(ch, sh, eta[0], kappa[0]), fresnel_channel(ch, sh, eta[1], kappa[1]), fresnel_channel(ch, sh, eta[2], kappa[2]));
+}
+__device__ __forceinline__ double beckmann(double c, double alpha) { // NDF :34-45
+    if (c >= 0) {
+        const double s = sqrt(1 - c * c);
+        const double fac1 = kPi * alpha * alpha * c * c * c * c;
+        const double tg = s / c;
+        const double fac2 = exp((-1 * tg * tg) / (alpha * alpha));
+        return (1 / fac1) * fac2;
+    }
+    return 0;
+}
+__device__ __forceinline__ double smith_g1(D3 n, D3 wv, D3 wh, double alpha) { // Gn :47-61
+    const double s = sqrt(1 - dot(n, wv) * dot(n, wv));
+    const double tg = s / dot(n, wv);
+    const double a = 1 / (alpha * tg);
+    if (dot(wv, wh) / dot(wv, n) > 0) {
+        if (a < 1.6) return (3.535 * a + 2.181 * a * a) / (1 + 2.276 * a + 2.577 * a * a);
+        return 1;
+    }
+    return 0;
+}
+__device__ __forceinline__ D3 facet_normal(double alpha, double xi1, double xi2) { // vectorFacet :71-84
+    return unit(sph(atan(sqrt(-alpha * alpha * log(1 - xi1))), 2 * kPi * xi2));
+}
+__device__ __forceinline__ double facet_pdf(D3 wo, D3 wh, double alpha, D3 n) { // microFacetProb :86-92
+    const double num = dot(wh, n);
+    const double den = 4 * fabs(dot(wo, wh));
+    return beckmann(dot(wh, n), alpha) * num / den;
+}
+__device__ __forceinline__ D3 facet_brdf(const SphereD &m, D3 wi, D3 wh, D3 wo, double alpha, D3 n) { // frMicroFacet :95-100
+    const double den = (4 * fabs(dot(n, wi)) * fabs(dot(n, wo)));
+    const double g = smith_g1(n, wi, wh, alpha) * smith_g1(n, wo, wh, alpha);
+    return fresnel_conductor(dot(wi, wh), m.eta, m.kappa) * beckmann(dot(n, wh), alpha) * g * (1 / den);
+}
+
+// muestreoSA -> solidAngle(L), samplingFunctions.h:238-247 and :163-206
+template <class RngT>
+__device__ __forceinline__ D3 light_sampled_direct(const Ctx &c, int light, D3 x, const SphereD &obj, D3 n, D3 wray, double alpha, D3 &wi_out, double &cos_max_out,
+                                                   RngT &rng, Tally &tl) {
+    const SphereD &src = c.s[light];
+    D3 cx = pos(src) - x;
+    const double len = sqrt(dot(cx, cx));
+    cx = cx * (1 / len);
+    const double cos_max = sqrt(1 - (src.r / len) * (src.r / len));
+    cos_max_out = cos_max;
+    const double e0 = rng.next_f64(), e1 = rng.next_f64();
+    const D3 wi = cone_sample(cx, cos_max, e0, e1);
+    wi_out = wi;
+    const D3 wil = unit(to_local(n, wi));
+    const D3 wol = unit(to_local(n, wray * -1));
+    const D3 wh = unit(wil + wol);
+    D3 fr;
+    if (obj.material == 0) fr = alb(obj) * (1 / kPi);
+    else fr = facet_brdf(obj, wil, wh, wol, alpha, mk(0, 0, 1));
+    double t;
+    int id = 0;
+    scan(c, x, wi, t, id, tl);
+    const D3 Le = (light == id) ? rad(c.s[id]) : mk(0, 0, 0);
+    return had(Le, fr) * dot(n, wi) * (1 / cone_pdf(cos_max));
+}
+
+// MISv2, misSamplingFunctions.h:96-170
+template <class RngT>
+__device__ __forceinline__ D3 surface_direct_mis(const Ctx &c, const SphereD &obj, D3 x, D3 n, D3 wray, double alpha, RngT &rng, Tally &tl) {
+    D3 total = mk(0, 0, 0);
+    D3 wo = wray * -1;
+    double cos_max = 0;
+    for (int light = 0; light < c.n_spheres; ++light) {
+        if (c.s[light].r > 0 && c.s[light].lr > 0) {
+            D3 wi_light;
+            const D3 f = light_sampled_direct(c, light, x, obj, n, wray, alpha, wi_light, cos_max, rng, tl) * transmittance(x, pos(c.s[light]), c.sigma_t);
+            const double fpdf = cone_pdf(cos_max);
+            double gpdf;
+            if (obj.material == 0) gpdf = cosine_pdf(dot(n, wi_light));
+            else gpdf = facet_pdf(wo, unit(wi_light + wo), alpha, n);
+            total = total + f * power_heuristic(fpdf, gpdf);
+        }
+    }
+    D3 g;
+    double wg;
+    if (obj.material == 0) {
+        const double xi1 = rng.next_f64(), xi2 = rng.next_f64();
+        const D3 wi = unit(cosine_hemisphere(n, xi1, xi2)); // uniform, samplingFunctions.h:250-261
+        int source = -1;
+        const D3 Le = first_hit_radiance(c, x, wi, source, tl);
+        g = mk(0, 0, 0) + had(Le, alb(obj) * (1 / kPi)) * dot(n, wi) * (1 / cosine_pdf(dot(n, wi)));
+        const double gpdf = cosine_pdf(dot(n, wi));
+        if (g.x > 0 && g.y > 0 && g.z > 0) wg = power_heuristic(gpdf, cone_pdf(cone_cos(c, source, x)));
+        else wg = 0;
+    } else {
+        const double xi1 = rng.next_f64(), xi2 = rng.next_f64();
+        const D3 wh = facet_normal(alpha, xi1, xi2);
+        wo = unit(to_local(n, wo));
+        const D3 nl = mk(0, 0, 1); // microfacet, samplingFunctions.h:97-118
+        const D3 wi = unit(wo * (-1) + wh * 2 * dot(wh, wo));
+        const D3 wig = unit(from_local(n, wi));
+        int source = -1;
+        const D3 Le = first_hit_radiance(c, x, wig, source, tl);
+        g = had(Le, facet_brdf(obj, wi, wh, wo, alpha, nl)) * dot(nl, wi) * (1 / facet_pdf(wo, wh, alpha, nl));
+        const double gpdf = facet_pdf(wo, wh, alpha, nl);
+        if (g.x > 0) cos_max = cone_cos(c, source, x);
+        wg = power_heuristic(gpdf, cone_pdf(cos_max));
+    }
+    return total + g * wg;
+}
+
+// pLight, vptShadeMethods.h:62-91 (no material-3 spheres: the visibilityVPT branch repeats the scan with the same answer)
+__device__ __forceinline__ D3 point_light_direct(const Ctx &c, const SphereD &obj, D3 x, D3 n, D3 wray, D3 I, D3 light, double alpha, Tally &tl) {
+    D3 Le = mk(0, 0, 0);
+    if (visible(c, light, x, tl)) Le = I * (1 / dot(light - x, light - x));
+    D3 wi = unit(light - x);
+    D3 wo = wray * -1;
+    wo = to_local(n, wo);
+    wi = to_local(n, wi);
+    wi = unit(wi);
+    wo = unit(wo);
+    const D3 wh = unit(wi + wo);
+    D3 fr;
+    if (obj.material == 1) fr = facet_brdf(obj, wi, wh, wo, alpha, mk(0, 0, 1));
+    else fr = alb(obj) * (1 / kPi);
+    return had(Le, fr) * dot(n, unit(light - x));
+}
+
+// bdsf, vptShadeMethods.h:16-59
+template <class RngT>
+__device__ __forceinline__ D3 bsdf_sample(const SphereD &obj, D3 &wi_out, D3 wray, D3 n, double &pdf, RngT &rng) {
+    const D3 wo = wray * -1;
+    const double xi1 = rng.next_f64(), xi2 = rng.next_f64();
+    if (obj.material == 0) {
+        const D3 wi = cosine_hemisphere(n, xi1, xi2);
+        pdf = cosine_pdf(dot(n, wi));
+        wi_out = wi;
+        return alb(obj) * (1 / kPi);
+    }
+    D3 wh = facet_normal(obj.alpha, xi1, xi2);
+    wh = from_local(n, wh);
+    const D3 wi = wo * (-1) + wh * 2 * dot(wh, wo);
+    pdf = facet_pdf(wo, wh, obj.alpha, n);
+    wi_out = wi;
+    return facet_brdf(obj, wi, wh, wo, obj.alpha, n);
+}
+
+// freeSingleScattering (volumetricBasicFunctions.h:284-340) / singleScattering (:225-281)
+template <class RngT>
+__device__ __forceinline__ D3 medium_direct(const Ctx &c, D3 xt, int source, double prob_source, bool equi, double T_xt, RngT &rng, Tally &tl) {
+    const SphereD &src = c.s[source];
+    D3 Ld = mk(0, 0, 0);
+    if (src.r == 0) {
+        const D3 light = pos(src);
+        if (visible(c, light, xt, tl)) {
+            D3 Le = rad(src);
+            const double d2 = dot(light - xt, light - xt);
+            Le = Le * (1 / d2);
+            const D3 Ls = Le * transmittance(xt, light, c.sigma_t) * phase_value();
+            Ld = equi ? Ls * T_xt * c.sigma_s * (1 / prob_source) : Ls * (1 / prob_source);
+        }
+    }
+    D3 wc = pos(src) - xt;
+    const double len = sqrt(dot(wc, wc));
+    wc = wc * (1 / len);
+    const double cos_max = sqrt(1 - src.r / len * (src.r / len));
+    const double e0 = rng.next_f64(), e1 = rng.next_f64();
+    const D3 wl = cone_sample(wc, cos_max, e0, e1);
+    const double prob_wl = cone_pdf(cos_max);
+    double dist;
+    int hit_id = -1;
+    scan(c, xt, wl, dist, hit_id, tl);
+    if (source == hit_id) {
+        const D3 Ls = rad(src) * exp(c.sigma_t * dist * -1.0) * phase_value();
+        Ld = equi ? Ls * T_xt * c.sigma_s * (1 / prob_wl) * (1 / prob_source) : Ls * (1 / prob_wl) * (1 / prob_source);
+    }
+    return Ld;
+}
+
+struct Path { D3 o, d, beta, L; int depth; };
+
+// one vertex after a successful roulette draw; vptShadeMethods.h:1263-1340 / :1014-1149 / :1345-1481 in throughput form
+template <class RngT>
+__device__ __forceinline__ bool vertex(const Ctx &c, Path &p, RngT &rng, Tally &tl) {
+    ++tl.events;
+    double t;
+    int id = 0;
+    const bool hit = scan(c, p.o, p.d, t, id, tl);
+    if (!hit) t = kMaxFloat;
+    const D3 xs = p.o + p.d * t;
+    double Tr = 0;
+    if (c.method == 1 && hit) Tr = transmittance(p.o, xs, c.sigma_t);
+    const D3 n = unit(xs - pos(c.s[id]));
+    if (c.n_emitters == 0) return false;
+    const double prob_source = 1.0 / c.n_emitters;
+    const int source = c.emitters[static_cast<int>(rng.next_f64() * c.n_emitters)];
+
+    bool surface;
+    double dist, pdf_medium = 1;
+    if (c.method == 0) {
+        dist = -log(1 - rng.next_f64()) / c.sigma_t;
+        surface = dist > t;
+    } else {
+        if (c.method == 2) Tr = exp(c.sigma_t * t * -1.0);
+        // equiAngularParams2, volumetricBasicFunctions.h:209-223
+        const D3 dv = pos(c.s[source]) - p.o;
+        const double len = sqrt(dot(dv, dv));
+        const double proj = dot(dv, p.d) / dot(p.d, p.d);
+        const double D = sqrt(len * len - proj * proj);
+        const double thA = atan2(0.0 - proj, D), thB = atan2(t - proj, D);
+        const double xi = rng.next_f64();
+        const double t_local = D * tan((1 - xi) * thA + xi * thB);
+        dist = t_local + proj;
+        pdf_medium = D / fabs(thB - thA) / (t_local * t_local + D * D) * (1.0 - Tr);
+        const double xs_ = rng.next_f64();
+        surface = (c.method == 1) ? (xs_ <= Tr) : (xs_ < Tr);
+    }
+
+    if (surface) {
+        const SphereD &obj = c.s[id];
+        if (obj.emits) {
+            if (p.depth == 0) p.L = had(rad(obj), p.beta);
+            return false;
+        }
+        const SphereD &src = c.s[source];
+        const double Trs = transmittance(xs, pos(src), c.sigma_t);
+        const D3 Ld_point = point_light_direct(c, obj, xs, n, p.d, rad(src), pos(src), obj.alpha, tl) * Trs * (1 / prob_source);
+        const D3 Ld = surface_direct_mis(c, obj, xs, n, p.d, obj.alpha, rng, tl);
+        D3 wi;
+        double pdf;
+        const D3 fs = bsdf_sample(obj, wi, p.d, n, pdf, rng);
+        wi = unit(wi);
+        const double cosine = dot(n, wi);
+        p.L = p.L + had(Ld_point + Ld, p.beta) * (1 / c.cp);
+        p.beta = had(p.beta, fs) * (1 / c.cp) * cosine * (1 / pdf);
+        p.o = xs; p.d = wi;
+    } else {
+        const D3 xt = p.o + p.d * dist;
+        if (c.method == 0) {
+            const D3 Ld = medium_direct(c, xt, source, prob_source, false, 0.0, rng, tl);
+            const double xi1 = rng.next_f64(), xi2 = rng.next_f64();
+            p.L = p.L + had(Ld, p.beta) * (c.sigma_s / c.sigma_t) * (1 / c.cp);
+            p.beta = p.beta * (c.sigma_s / c.sigma_t) * (1 / c.cp);
+            p.o = xt; p.d = phase_sample(xi1, xi2);
+        } else {
+            const double T = transmittance(p.o, xt, c.sigma_t);
+            const D3 Ld = medium_direct(c, xt, source, prob_source, true, T, rng, tl);
+            const double xi1 = rng.next_f64(), xi2 = rng.next_f64();
+            p.L = p.L + had(Ld * (1 / pdf_medium) * (1 / c.cp), p.beta);
+            p.beta = p.beta * c.sigma_s * T * (1 / c.cp) * (1 / pdf_medium);
+            p.o = xt; p.d = phase_sample(xi1, xi2);
+        }
+    }
+    return true;
+}
+
+} // namespace f64
+} // namespace vpt

@@ -1,0 +1,92 @@
+// vpt_internal.h -- structures shared by the host side (vpt_api.cpp) and the device side (*.cu) of libvpt_b200.
+// Not part of the public boundary (that is include/vpt.h).
+#pragma once
+#include <stdint.h>
+#include "../../include/vpt.h"
+
+namespace vpt {
+
+constexpr int kMaxSpheres = VPT_MAX_SPHERES;
+constexpr int kMaxEmitters = VPT_MAX_EMITTERS;
+constexpr int kThreadsPerBlock = 128; // one pixel tile = kTile consecutive storage-order pixels
+constexpr int kTile = 128;
+
+// ---- fp32 scene ----------------------------------------------------------------------------------------------
+// Ray/sphere record for the scan loop (lives in kernel-parameter constant memory; uniform index -> broadcast).
+// Re-anchored form (DESIGN.md "fp32 geometry"): for a sphere with centre p and radius r the
+// host picks, in double, an anchor q and m = q - p so that for a ray origin o
+//     c = |o-p|^2 - r^2 = |o-q|^2 + 2 (o-q).m + c0 ,  c0 = |m|^2 - r^2
+// has no 1e10-sized cancellation: huge spheres (the r = 1e5 walls) use q = surface point nearest the scene (c0 ~ 0),
+// ordinary spheres use q = p (m = 0, c0 = -r^2).
+struct GeomF {
+    float qx, qy, qz;
+    float mx, my, mz;
+    float c0;
+    float r2;     // ordinary spheres: det = r^2 - |op - (op.d) d|^2
+    int32_t id;   // index into the caller's sphere array
+    int32_t big;  // 1: det = b^2 - c
+};
+// Shading record, indexed by the caller's sphere index (divergent index -> staged in shared memory).
+struct MatF {
+    float px, py, pz, r;
+    float cr, cg, cb;       // albedo
+    float lr, lg, lb;       // radiance
+    float eta[3], kappa[3];
+    float alpha;
+    int32_t material;
+    int32_t emits;          // any radiance channel > 0 (vptShadeMethods.h:1296)
+    int32_t pad;
+};
+struct SceneF {
+    int32_t n_spheres, n_geom, n_emitters, n_area;
+    int32_t emitters[kMaxEmitters]; // spheres with any radiance channel > 0, in index order
+    int32_t area[kMaxEmitters];     // spheres with r > 0 && radiance.x > 0 (misSamplingFunctions.h:106), in index order
+    GeomF geom[kMaxSpheres];
+    MatF mat[kMaxSpheres];
+};
+
+// ---- fp64 scene (REF mode: the reference's own representation and operation order) ----------------------------------
+struct SphereD {
+    double r, px, py, pz;
+    double cr, cg, cb;
+    double lr, lg, lb;
+    double eta[3], kappa[3];
+    double alpha;
+    int32_t material;
+    int32_t emits;
+};
+struct SceneD {
+    int32_t n_spheres, n_emitters;
+    int32_t emitters[kMaxEmitters];
+    SphereD s[kMaxSpheres];
+};
+
+// ---- per-launch parameters ----------------------------------------------------------------------------------------
+struct LaunchParams {
+    int32_t width, height, n_pixels;
+    int32_t sample_begin, sample_end;
+    int32_t tile_rank, tile_count, n_tiles_total;
+    int32_t method, max_depth;
+    uint32_t key0, key1;
+    uint32_t quirks;
+    double out_scale; // 1 (SUM) or 1/spp (MEAN)
+    // medium / roulette, both precisions
+    double sigma_a, sigma_s, continue_prob;
+    // camera (rt.cpp:755-759), prepared on the host in double
+    double cam_o[3], cam_d[3], cam_cx[3], cam_cy[3];
+};
+
+struct Counters { // device-side, accumulated with atomics at thread exit
+    unsigned long long events, scans, nonfinite, paths;
+};
+
+// entry points implemented in the .cu files, called from vpt_api.cpp
+int launch_render_f32(const SceneF &scene, const LaunchParams &lp, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks);
+int launch_render_f64(const SceneD &scene, const LaunchParams &lp, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks);
+int launch_unit_f32(int fn, const SceneF &scene, const LaunchParams &lp, int n, const double *in_dev, int in_stride, double *out_dev, int out_stride, void *stream);
+int launch_unit_f64(int fn, const SceneD &scene, const LaunchParams &lp, int n, const double *in_dev, int in_stride, double *out_dev, int out_stride, void *stream);
+int launch_philox(int n, const uint32_t *ctr_dev, const uint32_t *key_dev, uint32_t *out_dev, void *stream);
+int launch_fma_peak(float *sink_dev, int n_blocks, int n_threads, int iters, void *stream);
+constexpr int kFmaPeakFlopsPerThreadIter = 2 * 16 * 8; // see vpt_kernels_f32.cu fma_peak_kernel
+
+} // namespace vpt
