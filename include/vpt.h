@@ -135,6 +135,8 @@ typedef enum {
     VPT_UNIT_RADIANCE = 16,        /* the three shade methods    in: o[3], d[3], pixel, sample  (Philox stream (pixel, sample), jitter draws skipped;
                                       method, sigma_*, continue_prob, max_depth, seed, quirks from `p`)  out: L[3], events */
     VPT_UNIT_CAMERA_RAY = 17,      /* rt.cpp:787                 in: x, y, xi1, xi2 (width, height, camera from `p`)   out: d[3] */
+    VPT_UNIT_RADIANCE_LIST = 18,   /* the three shade methods on an EXPLICIT list of uniforms (e.g. the reference's erand48 sequence)
+                                      in: o[3], d[3], n_u, u[120]                                      out: L[3], draws used (-1: list too short) */
     VPT_UNIT_COUNT_
 } vpt_unit_fn;
 int vpt_unit(int32_t fn, const vpt_params *p, const vpt_sphere *spheres, int32_t n_spheres, int32_t n, const double *in, int32_t in_stride,

@@ -309,8 +309,8 @@ __device__ __forceinline__ F3 medium_direct(const SceneF &sc, const MatF &src, i
 // One path vertex after a successful roulette draw: iterativeVPTracerFree (vptShadeMethods.h:1263-1340),
 // explicitVPTracerRecursive (:1014-1149) and MISVPTTracerRecursive (:1345-1481) in throughput form.
 // Returns false when the path ends here.
-template <int METHOD>
-__device__ __forceinline__ bool vertex(const SceneF &sc, const MatF *mats, const Consts &k, Path &p, Rng &rng, Tally &tally) {
+template <int METHOD, class RngT>
+__device__ __forceinline__ bool vertex(const SceneF &sc, const MatF *mats, const Consts &k, Path &p, RngT &rng, Tally &tally) {
     ++tally.events;
     float t; int id = 0;
     const bool hit = scan(sc, p.o, p.d, t, id, tally.scans);

@@ -144,9 +144,10 @@ __device__ __forceinline__ void st3(double *p, F3 v) { p[0] = v.x; p[1] = v.y; p
 
 // explicit uniforms of a test row, served through the stream interface the render code uses
 struct ListRng {
-    const double *u; int i;
-    __device__ float next_f32() { return (float)u[i++]; }
-    __device__ void skip(int n) { i += n; }
+    const double *u; int i; int n = 1 << 30; bool overrun = false;
+    __device__ float next_f32() { if (i >= n) { overrun = true; return 0.5f; } return (float)u[i++]; }
+    __device__ void skip(int k) { i += k; }
+    __device__ void begin_bounce(uint32_t) {}
 };
 
 __global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const __grid_constant__ LaunchParams lp, int n, const double *__restrict__ in,
@@ -271,6 +272,21 @@ __global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const
             ++p.depth;
         }
         st3(o, p.L); o[3] = tally.events;
+    } break;
+    case VPT_UNIT_RADIANCE_LIST: {
+        Path p; p.o = ld3(a); p.d = ld3(a + 3); p.beta = mk(1, 1, 1); p.L = mk(0, 0, 0); p.depth = 0;
+        ListRng rng{a + 7, 0, min((int)a[6], 120)};
+        Tally tally{0u, 0u};
+        for (;;) {
+            if ((k.max_depth > 0 && p.depth >= k.max_depth) || rng.next_f32() < k.q) break;
+            bool alive;
+            if (lp.method == 0) alive = vertex<0>(sc, mats, k, p, rng, tally);
+            else if (lp.method == 1) alive = vertex<1>(sc, mats, k, p, rng, tally);
+            else alive = vertex<2>(sc, mats, k, p, rng, tally);
+            if (!alive) break;
+            ++p.depth;
+        }
+        st3(o, p.L); o[3] = rng.overrun ? -1.0 : (double)rng.i;
     } break;
     case VPT_UNIT_CAMERA_RAY: {
         const CameraF cam = make_camera(lp);

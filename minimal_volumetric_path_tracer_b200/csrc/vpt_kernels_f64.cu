@@ -98,8 +98,9 @@ int launch_render_f64(const SceneD &scene, const LaunchParams &lp, float *hdr_de
 
 // ---- unit kernels ---------------------------------------------------------------------------------------------------------
 struct ListRng {
-    const double *u; int i;
-    __device__ double next_f64() { return u[i++]; }
+    const double *u; int i; int n = 1 << 30; bool overrun = false;
+    __device__ double next_f64() { if (i >= n) { overrun = true; return 0.5; } return u[i++]; }
+    __device__ void begin_bounce(uint32_t) {}
 };
 __device__ __forceinline__ void st3(double *p, D3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
 
@@ -190,6 +191,16 @@ __global__ void unit_f64_kernel(int fn, const __grid_constant__ SceneD sc, const
             ++p.depth;
         }
         st3(o, p.L); o[3] = tl.events;
+    } break;
+    case VPT_UNIT_RADIANCE_LIST: {
+        Path p; p.o = v3(a); p.d = v3(a + 3); p.beta = mk(1, 1, 1); p.L = mk(0, 0, 0); p.depth = 0;
+        ListRng rng{a + 7, 0, min((int)a[6], 120)};
+        for (;;) {
+            if ((c.max_depth > 0 && p.depth >= c.max_depth) || rng.next_f64() < c.q) break;
+            if (!vertex(c, p, rng, tl)) break;
+            ++p.depth;
+        }
+        st3(o, p.L); o[3] = rng.overrun ? -1.0 : (double)rng.i;
     } break;
     case VPT_UNIT_CAMERA_RAY: st3(o, camera_dir(lp, (int)a[0], (int)a[1], a[2], a[3])); break;
     default: break;

@@ -82,7 +82,9 @@ static inline bool vpt_l0_hook_visibility(Point light, Point x) {
 #include "misSamplingFunctions.h"
 #include "vptShadeMethods.h" /* pulls rayMarchingMethods.h (non-inline definitions: one TU only) */
 
-static const std::vector<Sphere> g_default_scene = spheres; /* include/Sphere.cpp:7-22 as linked */
+/* include/Sphere.cpp:7-22 as linked.  Captured on first use (not at static-init time: the order of dynamic initialisation
+ * across translation units is unspecified, `spheres` might still be empty then); always called before any modification. */
+static const std::vector<Sphere> &default_scene() { static const std::vector<Sphere> d = spheres; return d; }
 
 static inline Vector V(const double *p) { return Vector(p[0], p[1], p[2]); }
 static inline void put(double *o, const Vector &v) { o[0] = v.x; o[1] = v.y; o[2] = v.z; }
@@ -109,11 +111,12 @@ void l0_scene_get(int i, double *o) {
     put(o + 11, s.eta); put(o + 14, s.kappa); o[17] = s.alpha;
 }
 void l0_scene_set(int n, const double *d) {
+    (void)default_scene();
     spheres.clear();
     for (int i = 0; i < n; i++, d += 18)
         spheres.emplace_back(d[0], V(d + 1), V(d + 4), V(d + 7), (int)d[10], V(d + 11), V(d + 14), d[17]);
 }
-void l0_scene_reset(void) { spheres = g_default_scene; }
+void l0_scene_reset(void) { spheres = default_scene(); }
 
 /* ---- geometry: Sphere.h:27, pathTracingUtilities.h:12/39/56/66 ------------------------------ */
 double l0_sphere_intersect(int i, const double *o, const double *d) { return spheres[i].intersect(Ray(V(o), V(d))); }

@@ -1,0 +1,137 @@
+"""GPU: unit kernels (through the C-ABI, vpt_unit) against the reference's own C++ functions on identical inputs
+(tests/golden/units.npz).  Tolerances: FP32 <= 1e-5 relative (north_star), FP64 REF <= 1e-11."""
+import numpy as np
+import pytest
+
+from conftest import vec_rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {0: 1e-5, 1: 1e-11}  # precision -> relative tolerance
+
+
+def run(gpu, fn, rows, precision, **kw):
+    p = gpu.default_params(precision=precision, **kw)
+    return gpu.unit(fn, rows, p)
+
+
+def assert_rel(got, want, tol, scale=None):
+    got = np.asarray(got, float); want = np.asarray(want, float)
+    den = np.abs(want) if scale is None else np.maximum(np.abs(want), scale)
+    bad = np.abs(got - want) > tol * den + 1e-300
+    assert not bad.any(), "max rel err %.3e at %s" % (np.max(np.abs(got - want) / np.maximum(den, 1e-300)), np.argwhere(bad)[:5].tolist())
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_ray_sphere_t(gpu, units, precision):
+    """Sphere::intersect (Sphere.h:27): includes the r = 1e5 wall spheres, which need the re-anchored form in fp32"""
+    rows, want = units["sphere_intersect_in"], units["sphere_intersect_out"][:, 0]
+    got = run(gpu, gpu.UNIT.SPHERE_INTERSECT, rows, precision)[:, 0]
+    if precision == 0:
+        keep = rows[:, 0] != 8  # fp32 semantics: the r = 0 sphere has no scan record
+        got, want = got[keep], want[keep]
+    assert np.array_equal(got == 0, want == 0), "hit / miss decision differs"
+    assert_rel(got, want, TOL[precision])
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_scene_intersect(gpu, units, precision):
+    got = run(gpu, gpu.UNIT.INTERSECT, units["intersect_in"], precision)
+    want = units["intersect_out"]
+    assert np.array_equal(got[:, 0], want[:, 0]) and np.array_equal(got[:, 2], want[:, 2])
+    assert_rel(got[:, 1], want[:, 1], TOL[precision])
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_visibility_transmittance(gpu, units, precision):
+    got = run(gpu, gpu.UNIT.VISIBILITY, units["visibility_in"], precision, quirks=3 if precision else 0)
+    assert np.array_equal(got, units["visibility_out"])
+    got = run(gpu, gpu.UNIT.TRANSMITTANCE, units["transmittance_in"], precision)
+    assert_rel(got, units["transmittance_out"], TOL[precision])
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_free_flight(gpu, units, precision):
+    """freeFlightSample / freeFlightProb / pdfSuccess / pdfFailure (vptSamplingFunctions.h:11-31)"""
+    got = run(gpu, gpu.UNIT.FREE_FLIGHT, units["free_flight_in"], precision)
+    want = units["free_flight_out"]
+    assert_rel(got[:, [0, 1, 3]], want[:, [0, 1, 3]], TOL[precision])
+    assert_rel(got[:, 2], want[:, 2], TOL[precision], scale=1.0)  # 1 - exp(-x): a probability, absolute 1e-5
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_equiangular_sample_and_pdf(gpu, units, precision):
+    """equiAngularParams2 + equiAngularProb (volumetricBasicFunctions.h:209, vptSamplingFunctions.h:60)"""
+    got = run(gpu, gpu.UNIT.EQUIANGULAR, units["equiangular_in"], precision)
+    want = units["equiangular_out"]
+    tol = TOL[precision]
+    assert_rel(got[:, 0], want[:, 0], tol)                                    # D
+    assert_rel(got[:, 1:3], want[:, 1:3], tol, scale=1.0)                      # angles (radians, O(1))
+    length = np.maximum(np.abs(want[:, 3]), want[:, 0])[:, None]              # distances along the ray: relative to max(|t'|, D)
+    assert_rel(got[:, 3:5], want[:, 3:5], 4 * tol, scale=length)
+    assert_rel(got[:, 5], want[:, 5], 4 * tol)                                 # pdf
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_power_heuristic(gpu, units, precision):
+    got = run(gpu, gpu.UNIT.POWER_HEURISTIC, units["power_heuristic_in"], precision)
+    assert_rel(got, units["power_heuristic_out"], TOL[precision])
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_direction_sampling(gpu, units, precision):
+    tol = TOL[precision]
+    got = run(gpu, gpu.UNIT.PHASE_SAMPLE, units["phase_sample_in"], precision)
+    assert vec_rel_err(got, units["phase_sample_out"]).max() < tol
+    got = run(gpu, gpu.UNIT.COSINE_HEMISPHERE, units["cosine_hemisphere_in"], precision)
+    assert vec_rel_err(got[:, :3], units["cosine_hemisphere_out"][:, :3]).max() < tol
+    assert_rel(got[:, 3], units["cosine_hemisphere_out"][:, 3], 4 * tol)
+    got = run(gpu, gpu.UNIT.CONE_SAMPLE, units["cone_sample_in"], precision)
+    assert vec_rel_err(got[:, :3], units["cone_sample_out"][:, :3]).max() < tol
+    # fp64 follows the reference's 1/(2 pi (1 - cos)) whose cancellation the fp32 form avoids: compare at the reference's own accuracy
+    assert_rel(got[:, 3], units["cone_sample_out"][:, 3], 1e-5 if precision == 0 else 1e-9)
+    got = run(gpu, gpu.UNIT.FACET_NORMAL, units["facet_normal_in"], precision)
+    assert vec_rel_err(got, units["facet_normal_out"]).max() < tol
+    got = run(gpu, gpu.UNIT.CAMERA_RAY, units["camera_ray_in"], precision, width=1024, height=768)
+    assert vec_rel_err(got, units["camera_ray_out"]).max() < (1e-6 if precision == 0 else 1e-15)
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_microfacet_model(gpu, units, precision):
+    got = run(gpu, gpu.UNIT.MICROFACET, units["microfacet_in"], precision)
+    want = units["microfacet_out"]
+    tol = 3 * TOL[precision]  # Beckmann exp(-tan^2/alpha^2) at alpha = 0.03 amplifies the input rounding
+    assert vec_rel_err(got[:, :3], want[:, :3]).max() < tol
+    assert_rel(got[:, 3:6], want[:, 3:6], tol)
+
+
+def composite(got, want, tol, max_outliers):
+    """composite functions contain hit/miss decisions: nearly all rows within tol, a few may flip a branch in fp32"""
+    err = vec_rel_err(got, want)
+    err[(np.abs(want).max(axis=1) == 0) & (np.abs(got).max(axis=1) == 0)] = 0
+    assert np.mean(err > tol) <= max_outliers, "outlier fraction %.4f, median %.2e" % (np.mean(err > tol), np.median(err))
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_direct_lighting_blocks(gpu, units, precision):
+    tol, outl = (5e-5, 0.02) if precision == 0 else (1e-10, 0.0)
+    q = dict(quirks=3) if precision else {}
+    composite(run(gpu, gpu.UNIT.MEDIUM_NEE, units["medium_nee_in"], precision, **q), units["medium_nee_out"], tol, outl)
+    composite(run(gpu, gpu.UNIT.MEDIUM_NEE, units["medium_nee_point_robust_in"], precision), units["medium_nee_point_robust_out"], tol, outl)
+    composite(run(gpu, gpu.UNIT.POINT_LIGHT, units["point_light_robust_in"], precision), units["point_light_robust_out"], tol, outl)
+    composite(run(gpu, gpu.UNIT.SURFACE_MIS, units["surface_mis_in"], precision), units["surface_mis_out"], tol, outl)
+    composite(run(gpu, gpu.UNIT.BSDF_SAMPLE, units["bsdf_sample_in"], precision), units["bsdf_sample_out"], tol, outl)
+
+
+def test_philox_matches_oracle_and_known_answers(gpu, l1):
+    kat = gpu.philox([[0, 0, 0, 0], [0xffffffff] * 4, [0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344]],
+                     [[0, 0], [0xffffffff] * 2, [0xa4093822, 0x299f31d0]])
+    assert [hex(x) for x in kat[0]] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    assert [hex(x) for x in kat[1]] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+    assert [hex(x) for x in kat[2]] == ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+    rng = np.random.default_rng(1)
+    ctr = rng.integers(0, 2 ** 32, size=(4096, 4), dtype=np.uint64).astype(np.uint32)
+    key = rng.integers(0, 2 ** 32, size=(4096, 2), dtype=np.uint64).astype(np.uint32)
+    dev = gpu.philox(ctr, key)
+    ref = np.array([l1.philox(c, k) for c, k in zip(ctr[:512], key[:512])])
+    assert np.array_equal(dev[:512], ref)

@@ -1,0 +1,82 @@
+"""CPU: host-side logic around the kernels -- the output stage (clamp, gamma, P3 text; rt.cpp:803-820, mathUtilities.h:34-45),
+shard arithmetic, the CLI surface."""
+import os
+
+import numpy as np
+import pytest
+
+
+def test_tonemap_is_the_references(vpt, units):
+    x = units["tonemap_in"].astype(np.float32)
+    hdr = np.stack([x, x, x], axis=-1).reshape(1, -1, 3)
+    got = vpt.tonemap(hdr)[0, :, 0]
+    # the golden values were computed by the reference on the float64 inputs; float32 rounding of x may move a value that
+    # sits exactly on a bucket edge by one step -- compare on the rounded inputs instead
+    want = np.array([int(np.clip(float(v), 0, 1) ** (1 / 2.2) * 255 + .5) for v in x])
+    assert np.array_equal(got, want)
+    exact = units["tonemap_out"]
+    assert np.mean(got == exact) > 0.99 and np.max(np.abs(got.astype(int) - exact)) <= 1
+
+
+def test_ppm_bytes(vpt, tmp_path):
+    rng = np.random.default_rng(0)
+    hdr = rng.uniform(-0.1, 1.2, size=(3, 5, 3)).astype(np.float32)
+    path = tmp_path / "image.ppm"
+    vpt.write_ppm(hdr, str(path))
+    text = path.read_text()
+    rgb = vpt.tonemap(hdr).reshape(-1, 3)
+    want = "P3\n5 3\n255\n" + "".join("%d %d %d " % tuple(px) for px in rgb)  # rt.cpp:814-820: no newlines after the header
+    assert text == want
+
+
+def test_sample_shards_partition_the_range():
+    from minimal_volumetric_path_tracer_b200 import distributed as d
+    for spp in (1, 7, 64, 1024, 16384):
+        for world in (1, 2, 3, 4, 8):
+            edges = [d.sample_shard(spp, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == spp
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+            sizes = [e - b for b, e in edges]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        d.sample_shard(8, 2, 2)
+
+
+def test_tile_ownership_is_interleaved():
+    from minimal_volumetric_path_tracer_b200 import distributed as d
+    owners = [d.tile_owner(p, 4) for p in range(0, 128 * 9, 128)]
+    assert owners == [0, 1, 2, 3, 0, 1, 2, 3, 0]
+
+
+def test_shard_params(vpt):
+    from minimal_volumetric_path_tracer_b200 import distributed as d
+    p = vpt.default_params(spp=10)
+    q, work = d.shard_params(p, "samples", 1, 4)
+    assert (q.sample_begin, q.sample_end, q.output, work) == (3, 6, vpt.OUTPUT_SUM, True)
+    q, work = d.shard_params(vpt.default_params(spp=2), "samples", 3, 4)
+    assert not work
+    q, work = d.shard_params(p, "tiles", 2, 4)
+    assert (q.tile_rank, q.tile_count, q.sample_begin, q.sample_end) == (2, 4, 0, 0)
+    assert p.tile_count == 0  # the caller's params are not modified
+
+
+def test_cli_surface(vpt):
+    from minimal_volumetric_path_tracer_b200 import cli
+    a = cli.parse_args(["16"])
+    p = cli.params_from_args(a)
+    assert (p.spp, p.width, p.height, p.method, a.output) == (16, 1024, 768, 0, "image.ppm")  # the reference's `rt <spp>`
+    a = cli.parse_args(["4", "--method", "equi", "--size", "64x48", "--ref", "--seed", "9", "-o", "x.ppm"])
+    p = cli.params_from_args(a)
+    assert (p.method, p.width, p.height, p.precision, p.quirks, p.seed) == (1, 64, 48, vpt.PRECISION_FP64_REF, 3, 9)
+    with pytest.raises(SystemExit):
+        cli.parse_args([])  # the reference segfaults on a missing argument; here it is a usage error
+    with pytest.raises(SystemExit):
+        cli.parse_args(["0"])
+
+
+def test_cpp_host_binary_exists_and_reports_usage(vpt):
+    import subprocess
+    from minimal_volumetric_path_tracer_b200 import build
+    assert os.path.exists(build.RT)
+    r = subprocess.run([build.RT], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage: rt <spp>" in r.stderr
