@@ -145,7 +145,7 @@ __device__ __forceinline__ void st3(double *p, F3 v) { p[0] = v.x; p[1] = v.y; p
 // explicit uniforms of a test row, served through the stream interface the render code uses
 struct ListRng {
     const double *u; int i; int n = 1 << 30; bool overrun = false;
-    __device__ float next_f32() { if (i >= n) { overrun = true; return 0.5f; } return (float)u[i++]; }
+    __device__ float next_f32() { if (i >= n) { overrun = true; return 0.0f; } /* 0 < q: the next roulette draw ends the path */ return (float)u[i++]; }
     __device__ void skip(int k) { i += k; }
     __device__ void begin_bounce(uint32_t) {}
 };

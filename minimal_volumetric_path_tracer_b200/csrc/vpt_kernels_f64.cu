@@ -99,7 +99,7 @@ int launch_render_f64(const SceneD &scene, const LaunchParams &lp, float *hdr_de
 // ---- unit kernels ---------------------------------------------------------------------------------------------------------
 struct ListRng {
     const double *u; int i; int n = 1 << 30; bool overrun = false;
-    __device__ double next_f64() { if (i >= n) { overrun = true; return 0.5; } return u[i++]; }
+    __device__ double next_f64() { if (i >= n) { overrun = true; return 0.0; } /* 0 < q: the next roulette draw ends the path */ return u[i++]; }
     __device__ void begin_bounce(uint32_t) {}
 };
 __device__ __forceinline__ void st3(double *p, D3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }

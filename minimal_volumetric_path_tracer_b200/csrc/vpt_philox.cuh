@@ -4,7 +4,8 @@
 // Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11).  Stream convention (DESIGN.md "RNG"):
 //   key     = (seed & 0xffffffff, seed >> 32)
 //   counter = (pixel, sample, bounce, block)       block = draw_index / 4, lane = draw_index % 4
-//   uniform = (word >> 8) * 2^-24                  in [0,1), exact in fp32 and fp64 -> both precisions see the same numbers
+//   uniform = (2 * (word >> 9) + 1) * 2^-24        in (0,1), never 0 or 1 (the reference's 48-bit erand48 practically never
+//                                                  returns 0 either); exact in fp32 and fp64 -> both precisions see the same numbers
 // Draw order inside a bounce is the reference's consumption order (SURVEY.md section 8a pseudo-code).  Bounce 0 starts
 // with the two pixel-jitter draws of rt.cpp:787.
 #pragma once
@@ -45,8 +46,8 @@ struct Rng {
         ++idx;
         return lane == 0 ? buf.x : lane == 1 ? buf.y : lane == 2 ? buf.z : buf.w;
     }
-    __device__ __forceinline__ float next_f32() { return (float)(next_word() >> 8) * 5.9604644775390625e-8f; }
-    __device__ __forceinline__ double next_f64() { return (double)(next_word() >> 8) * 5.9604644775390625e-8; }
+    __device__ __forceinline__ float next_f32() { return (float)(2u * (next_word() >> 9) + 1u) * 5.9604644775390625e-8f; }
+    __device__ __forceinline__ double next_f64() { return (double)(2u * (next_word() >> 9) + 1u) * 5.9604644775390625e-8; }
 };
 
 } // namespace vpt

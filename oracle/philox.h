@@ -6,7 +6,7 @@
  * Stream convention shared with the product (DESIGN.md "RNG"):
  *   key     = (seed & 0xffffffff, seed >> 32)
  *   counter = (pixel, sample, bounce, block)     block = draw_index / 4, lane = draw_index % 4
- *   uniform = (word >> 8) * 2^-24                in [0, 1), exactly representable in fp32 and fp64
+ *   uniform = (2 * (word >> 9) + 1) * 2^-24      in (0, 1): never 0 or 1, exactly representable in fp32 and fp64
  */
 #ifndef VPT_ORACLE_PHILOX_H
 #define VPT_ORACLE_PHILOX_H
@@ -28,6 +28,6 @@ static inline void vpt_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-static inline double vpt_u32_to_unit(uint32_t w) { return (double)(w >> 8) * (1.0 / 16777216.0); }
+static inline double vpt_u32_to_unit(uint32_t w) { return (double)(2u * (w >> 9) + 1u) * (1.0 / 16777216.0); }
 
 #endif

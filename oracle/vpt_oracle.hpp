@@ -585,7 +585,7 @@ struct ListRng {
     const double *u; size_t n, i = 0; bool overrun = false;
     ListRng(const double *u_, size_t n_) : u(u_), n(n_) {}
     void begin_bounce(int) {}
-    double next() { if (i >= n) { overrun = true; return 0.5; } return u[i++]; }
+    double next() { if (i >= n) { overrun = true; return 0.0; } /* 0 < q: the next roulette draw ends the path */ return u[i++]; }
 };
 /* POSIX erand48, sequential (the reference's generator, Vector.h:38) */
 struct Erand48Rng {

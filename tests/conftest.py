@@ -71,3 +71,10 @@ def vec_rel_err(got, want):
     """norm-wise relative error of row vectors"""
     got = np.asarray(got, dtype=np.float64); want = np.asarray(want, dtype=np.float64)
     return np.linalg.norm(got - want, axis=-1) / np.maximum(np.linalg.norm(want, axis=-1), 1e-300)
+
+
+def pytest_collection_modifyitems(config, items):
+    """every test gets a hard time limit (pytest-timeout): a hung kernel must not eat the GPU lease"""
+    for item in items:
+        if item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(240 if item.get_closest_marker("gpu") else 600))

@@ -60,57 +60,78 @@ def block_means(hdr, block=16):
     return hdr[:h // block * block, :w // block * block].reshape(h // block, block, w // block, block, 3).mean(axis=(1, 3))
 
 
-def z_scores(gpu, golden_name, precision, quirks, spp, scene_rows=None, seed=77):
+def z_scores(gpu, golden_name, precision, quirks, spp, scene_rows=None, seed=77, batches=16, stand_ins=6):
+    """Is the reference render one more draw from the distribution the GPU samples?
+
+    Block means at the reference's 256-512 spp are right-skewed (the estimator has fireflies: throughput grows 1.5x per
+    medium bounce, 1/d^2 near the point light), so a normalised difference is NOT a unit normal even when both sides sample the
+    same distribution.  The test therefore compares the reference with an ensemble of GPU stand-ins (other seeds, the
+    reference's spp) through identical statistics:
+      z        (main - X) / sigma per block and channel, main = a high-spp GPU render, sigma from a third independent
+               render (batch-to-batch variance: correlated with neither side); summarised by clipped mean, median,
+               median |z| and the 3-sigma tail fraction, for X = reference and X = each stand-in;
+      sign     fraction of blocks where a stand-in exceeds the reference: 1/2 under H0 by symmetry, no variance model;
+      glob_z   whole-image mean (a sum of ~1e8 samples: a clean normal test)."""
     g = np.load(os.path.join(GOLDEN, "image_%s.npz" % golden_name))
-    w, h, method = int(g["width"]), int(g["height"]), int(g["method"])
+    w, h, method, spp_ref = int(g["width"]), int(g["height"]), int(g["method"]), int(g["spp"])
     p = gpu.default_params(width=w, height=h, spp=spp, method=method, precision=precision, quirks=quirks, seed=seed)
     scene = gpu.scene_from_rows(scene_rows) if scene_rows is not None else None
-    hdr, st = gpu.render(p, scene, stats=True)
+    main, st = gpu.render(p, scene, stats=True)
     assert st.nonfinite == 0
-    m = block_means(hdr.astype(np.float64))
-    ref_m, ref_v = g["block_mean"].astype(np.float64), g["block_var"].astype(np.float64)
-    var = ref_v * (1.0 + float(g["spp"]) / spp)               # same estimator on both sides: the GPU's variance scales with 1/spp
-    ok = var > 0
-    z = (m - ref_m)[ok] / np.sqrt(var[ok])
-    glob_sigma = np.sqrt(var.sum(axis=(0, 1))) / (var.shape[0] * var.shape[1])
-    glob_z = (m.mean(axis=(0, 1)) - ref_m.mean(axis=(0, 1))) / glob_sigma
-    rmse2 = np.mean((m - ref_m)[ok] ** 2); expect2 = np.mean(var[ok])
-    return z, glob_z, rmse2 / expect2
+    main = block_means(main.astype(np.float64))
+    per = max(spp // (4 * batches), 4)
+    q = p.copy(spp=per * batches, seed=seed + 2, output=gpu.OUTPUT_SUM)
+    parts = np.stack([block_means(gpu.render(q.copy(sample_begin=b * per, sample_end=(b + 1) * per), scene).astype(np.float64)) / per for b in range(batches)])
+    sigma = np.sqrt(np.maximum(parts.var(axis=0, ddof=1) * per * (1.0 / spp_ref + 1.0 / spp), 1e-300))
+    ref = g["block_mean"].astype(np.float64)
+    nulls, signs = [], []
+    for k in range(stand_ins):
+        s_in = block_means(gpu.render(p.copy(spp=spp_ref, seed=seed + 100 + k), scene).astype(np.float64))
+        nulls.append(summary(((main - s_in) / sigma).ravel()))
+        signs.append(np.mean(s_in > ref))
+    glob = parts.mean(axis=(1, 2))
+    glob_sigma = np.sqrt(glob.var(axis=0, ddof=1) * per * (1.0 / spp_ref + 1.0 / spp))
+    return dict(ref=summary(((main - ref) / sigma).ravel()), nulls=np.array(nulls), sign=float(np.mean(signs)),
+                glob_z=(main.mean(axis=(0, 1)) - ref.mean(axis=(0, 1))) / glob_sigma)
 
 
-def check_statistically_equal(z, glob_z, rmse_ratio):
-    n = z.size
-    assert abs(np.mean(z)) < 5 / np.sqrt(n) + 0.02, "mean z = %.4f" % np.mean(z)      # no systematic bias over the blocks
-    assert 0.55 < np.median(np.abs(z)) < 0.80, "median |z| = %.3f (0.674 for a unit normal)" % np.median(np.abs(z))
-    assert np.mean(np.abs(z) > 3) < 0.02                                                # heavy tails (fireflies) allowed, not a shift
-    assert np.all(np.abs(glob_z) < 4.5), "whole-image mean off by z = %s" % glob_z
-    assert 0.5 < rmse_ratio < 2.0, "block RMSE^2 / expected variance = %.3f" % rmse_ratio  # image RMSE within noise
+def summary(z):
+    return np.array([np.mean(np.clip(z, -6, 6)), np.median(z), np.median(np.abs(z)), np.mean(np.abs(z) > 3)])
+
+
+def check_statistically_equal(r):
+    mu, sd = r["nulls"].mean(axis=0), r["nulls"].std(axis=0, ddof=1)
+    tol = np.maximum(5 * sd, [0.06, 0.06, 0.04, 0.015])  # floors: sd from 6 stand-ins is itself coarse; a 1 % block bias is a 0.2 shift
+    assert np.all(np.abs(r["ref"] - mu) < tol), "reference %s outside the stand-in ensemble %s +- %s" % (r["ref"], mu, tol)
+    assert abs(r["sign"] - 0.5) < 0.02, "sign test: %.4f" % r["sign"]
+    assert np.all(np.abs(r["glob_z"]) < 4.5), "whole-image mean off by z = %s" % r["glob_z"]
 
 
 @pytest.mark.parametrize("method", [0, 1, 2])
 def test_ref_mode_matches_the_as_shipped_reference(gpu, method):
     """FP64 REF mode with both quirks = the reference exactly as it ships, point light and rounding-decided branches included"""
-    check_statistically_equal(*z_scores(gpu, "strict_m%d" % method, gpu.PRECISION_FP64_REF, gpu.QUIRKS_REFERENCE, spp=256))
+    check_statistically_equal(z_scores(gpu, "strict_m%d" % method, gpu.PRECISION_FP64_REF, gpu.QUIRKS_REFERENCE, spp=512))
 
 
 @pytest.mark.parametrize("method", [0, 1, 2])
 def test_fp32_matches_reference_with_robust_hooks(gpu, method):
     """FP32 = the reference with its two rounding-decided behaviours replaced by the well-defined alternative"""
-    check_statistically_equal(*z_scores(gpu, "robust_m%d" % method, gpu.PRECISION_FP32, 0, spp=1024))
+    check_statistically_equal(z_scores(gpu, "robust_m%d" % method, gpu.PRECISION_FP32, 0, spp=4096))
 
 
 @pytest.mark.parametrize("method", [0, 1, 2])
 def test_fp32_matches_unmodified_reference_without_point_light(gpu, method):
     """without the r = 0 sphere the UNMODIFIED reference has no rounding-decided branch: direct comparison, no hooks"""
-    check_statistically_equal(*z_scores(gpu, "no8_m%d" % method, gpu.PRECISION_FP32, 0, spp=1024, scene_rows=scene_without([8])))
+    check_statistically_equal(z_scores(gpu, "no8_m%d" % method, gpu.PRECISION_FP32, 0, spp=4096, scene_rows=scene_without([8])))
 
 
 def test_fp64_robust_matches_reference_with_robust_hooks(gpu):
-    check_statistically_equal(*z_scores(gpu, "robust_m0", gpu.PRECISION_FP64_REF, 0, spp=256))
+    check_statistically_equal(z_scores(gpu, "robust_m0", gpu.PRECISION_FP64_REF, 0, spp=512))
 
 
 def test_the_statistical_test_has_power(gpu):
-    """the same machinery must REJECT a render that is wrong by a few per cent (fog 5 % denser)"""
+    """the same machinery must REJECT renders that are wrong by a few per cent: fog 5 % denser; FP32 semantics against the
+    as-shipped reference (whose point light is attenuated by the rounding-decided branches)"""
     g = np.load(os.path.join(GOLDEN, "image_robust_m0.npz"))
     p = gpu.default_params(width=1024, height=768, spp=1024, method=0, seed=5, sigma_s=0.009 * 1.05)
     m = block_means(gpu.render(p).astype(np.float64))
@@ -118,6 +139,10 @@ def test_the_statistical_test_has_power(gpu):
     glob_sigma = np.sqrt(var.sum(axis=(0, 1))) / (var.shape[0] * var.shape[1])
     glob_z = (m.mean(axis=(0, 1)) - g["block_mean"].astype(np.float64).mean(axis=(0, 1))) / glob_sigma
     assert np.max(np.abs(glob_z)) > 6
+    r = z_scores(gpu, "strict_m0", gpu.PRECISION_FP32, 0, spp=1024)
+    assert abs(r["glob_z"][0]) > 20 and np.all(np.abs(r["glob_z"][1:]) < 4.5)   # red (point light) differs, green and blue do not
+    with pytest.raises(AssertionError):
+        check_statistically_equal(r)
 
 
 def test_noise_floor_self_check(gpu):
@@ -186,7 +211,7 @@ def test_edge_cases(gpu):
     solo = np.zeros((1, 18)); solo[0, 0] = 20; solo[0, 1:4] = [0, 11.2, 100]; solo[0, 7:10] = [3, 2, 1]
     img = gpu.render(gpu.default_params(width=64, height=48, spp=512, sigma_s=1e-9, sigma_a=1e-9), gpu.scene_from_rows(solo))
     np.testing.assert_allclose(img[24, 32], [1.8, 1.2, 0.6], rtol=0.15)
-    assert not img[0, 0].any()
+    assert img[0, 0].max() < 1e-9                                            # only in-scattered light from the (almost) clear medium
     # more than four emitters (the reference overflows arr[4]): a checked, working configuration here
     rows = np.vstack([DEFAULT_SCENE] + [DEFAULT_SCENE[9:10] + np.r_[0, 6.0 * k, 0, 0, np.zeros(14)] for k in range(1, 4)])
     many = gpu.render(gpu.default_params(width=64, height=48, spp=8), gpu.scene_from_rows(rows))
