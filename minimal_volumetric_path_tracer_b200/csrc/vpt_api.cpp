@@ -76,7 +76,7 @@ int validate_params(const vpt_params *p, bool need_image) {
     if (p->quirks & ~(uint32_t)VPT_QUIRKS_REFERENCE) return VPT_ERR_INVALID_ARGUMENT;
     if (p->precision == VPT_PRECISION_FP32 && p->quirks != 0) return VPT_ERR_UNSUPPORTED; // rounding-decided behaviours exist in FP64 only
     if (p->kernel == VPT_KERNEL_WAVEFRONT) return VPT_ERR_UNSUPPORTED;
-    if (p->kernel != VPT_KERNEL_AUTO && p->kernel != VPT_KERNEL_MEGA) return VPT_ERR_INVALID_ARGUMENT;
+    if (p->kernel != VPT_KERNEL_AUTO && p->kernel != VPT_KERNEL_MEGA && p->kernel != VPT_KERNEL_MEGA_SCAN) return VPT_ERR_INVALID_ARGUMENT;
     return VPT_OK;
 }
 
@@ -102,11 +102,14 @@ void build_scene_f32(const vpt_sphere *s, int n, SceneF &out) {
         m.emits = emits(s[i]);
         if (m.emits) out.emitters[out.n_emitters++] = i;
         if (s[i].r > 0 && s[i].radiance[0] > 0) out.area[out.n_area++] = i; // misSamplingFunctions.h:106
-        if (s[i].r > 0) {
+    }
+    for (int pass = 0; pass < 2; ++pass) { // scan records: huge (re-anchored) spheres first, then ordinary ones
+        for (int i = 0; i < n; ++i) {
+            if (!(s[i].r > 0) || (s[i].r >= kHuge) != (pass == 0)) continue;
             GeomF &g = out.geom[out.n_geom++];
             g.id = i;
             const V3 p = v3(s[i].p);
-            if (s[i].r >= kHuge) {
+            if (pass == 0) {
                 V3 dir = sub(ref, p);
                 dir = dot(dir, dir) > 0 ? unit(dir) : V3{1, 0, 0};
                 const V3 q = add(p, mul(dir, s[i].r)); // surface point nearest the scene
@@ -117,8 +120,9 @@ void build_scene_f32(const vpt_sphere *s, int n, SceneF &out) {
                 g.c0 = (float)(dot(mm, mm) - s[i].r * s[i].r); // true |q_f - p|^2 - r^2 (tiny)
                 g.r2 = (float)(s[i].r * s[i].r);
                 g.big = 1;
+                ++out.n_big;
             } else {
-                g.qx = m.px; g.qy = m.py; g.qz = m.pz;
+                g.qx = (float)p.x; g.qy = (float)p.y; g.qz = (float)p.z;
                 g.mx = g.my = g.mz = 0.0f;
                 g.r2 = (float)(s[i].r * s[i].r);
                 g.c0 = -g.r2;
@@ -169,6 +173,21 @@ void build_launch(const vpt_params *p, LaunchParams &lp) {
     for (int k = 0; k < 4; ++k) { dst[k][0] = src[k].x; dst[k][1] = src[k].y; dst[k][2] = src[k].z; }
 }
 
+void build_consts_f32(const LaunchParams &lp, int n_emitters, ConstsF &k) {
+    std::memset(&k, 0, sizeof(k));
+    const double st = lp.sigma_a + lp.sigma_s;
+    k.sigma_t = (float)st;
+    k.inv_sigma_t = (float)(1.0 / st);
+    k.sigma_s = (float)lp.sigma_s;
+    k.albedo_over_cp = (float)(lp.sigma_s / st / lp.continue_prob);
+    k.inv_cp = (float)(1.0 / lp.continue_prob);
+    k.q = (float)(1.0 - lp.continue_prob);
+    k.n_emitters = (float)n_emitters;
+    k.method = lp.method; k.max_depth = lp.max_depth;
+    for (int i = 0; i < 3; ++i) { k.cam_o[i] = (float)lp.cam_o[i]; k.cam_d[i] = (float)lp.cam_d[i]; k.cam_cx[i] = (float)lp.cam_cx[i]; k.cam_cy[i] = (float)lp.cam_cy[i]; }
+    k.inv_w = (float)(1.0 / lp.width); k.inv_h = (float)(1.0 / lp.height);
+}
+
 int owned_tiles(const LaunchParams &lp) { return (lp.n_tiles_total - lp.tile_rank + lp.tile_count - 1) / lp.tile_count; }
 
 int select_device(int device) {
@@ -193,7 +212,9 @@ int enqueue_render(const vpt_params *p, const vpt_sphere *spheres, int n_spheres
     if (p->precision == VPT_PRECISION_FP32) {
         SceneF sc;
         build_scene_f32(spheres, n_spheres, sc);
-        rc = launch_render_f32(sc, lp, hdr_dev, counters_dev, stream, blocks);
+        ConstsF cf;
+        build_consts_f32(lp, sc.n_emitters, cf);
+        rc = launch_render_f32(sc, lp, cf, hdr_dev, counters_dev, stream, blocks, p->kernel == VPT_KERNEL_MEGA ? VPT_KERNEL_MEGA : VPT_KERNEL_MEGA_SCAN);
     } else {
         SceneD sc;
         build_scene_f64(spheres, n_spheres, sc);
@@ -456,7 +477,9 @@ int vpt_unit(int32_t fn, const vpt_params *p, const vpt_sphere *spheres, int32_t
         if (p->precision == VPT_PRECISION_FP32) {
             SceneF sc;
             build_scene_f32(spheres, n_spheres, sc);
-            launch_rc = launch_unit_f32(fn, sc, lp, n, din, in_stride, dout, out_stride, nullptr);
+            ConstsF cf;
+            build_consts_f32(lp, sc.n_emitters, cf);
+            launch_rc = launch_unit_f32(fn, sc, lp, cf, n, din, in_stride, dout, out_stride, nullptr);
         } else {
             SceneD sc;
             build_scene_f64(spheres, n_spheres, sc);

@@ -209,7 +209,7 @@ __device__ __forceinline__ F3 surface_direct_mis(const SceneF &sc, const MatF *m
     for (int a = 0; a < sc.n_area; ++a) {
         const int lid = sc.area[a];
         const MatF &src = mats[lid];
-        const float xi1 = rng.next_f32(), xi2 = rng.next_f32();
+        const float xi1 = rng.next_f32(S_AREA + 2 * a), xi2 = rng.next_f32(S_AREA + 2 * a + 1);
         const F3 cx = mk(src.px, src.py, src.pz) - x;
         const float len2 = dot(cx, cx), inv_len = rsqrtf(len2);
         const float omc_max = one_minus_cos_max(src.r * src.r / len2);
@@ -235,7 +235,7 @@ __device__ __forceinline__ F3 surface_direct_mis(const SceneF &sc, const MatF *m
         total = total + had(mk(src.lr, src.lg, src.lb), f) * (cos_i * inv_fpdf * Tr * w);
     }
     // one BSDF sample (uniform :250 / microfacet :97)
-    const float xi1 = rng.next_f32(), xi2 = rng.next_f32();
+    const float xi1 = rng.next_f32(S_MIS), xi2 = rng.next_f32(S_MIS + 1);
     if (obj.material == 1) {
         const F3 wh = facet_normal(obj.alpha, xi1, xi2);
         const F3 wi_l = unit(fma3(wh, 2.0f * dot(wh, wo_l), -wo_l));
@@ -286,18 +286,18 @@ __device__ __forceinline__ F3 bsdf_sample(const MatF &obj, const Frame &fr, F3 w
 }
 
 // freeSingleScattering (volumetricBasicFunctions.h:284-340) / singleScattering (:225-281) without the 1/probSource,
-// transmitanceXT and sigma_s factors (the caller applies them).  Always consumes the reference's two cone draws.
+// transmitanceXT and sigma_s factors (the caller applies them).  The reference always draws two cone numbers (slots S_NEE); the point-light case needs none.
 template <class RngT>
 __device__ __forceinline__ F3 medium_direct(const SceneF &sc, const MatF &src, int src_id, F3 xt, const Consts &k, RngT &rng, unsigned &n_scans) {
     const F3 light = mk(src.px, src.py, src.pz);
     const F3 wc = light - xt;
     const float d2 = dot(wc, wc), inv = rsqrtf(d2);
-    if (src.r == 0.0f) {
-        rng.skip(2);
+    if (src.r == 0.0f) { // the reference draws two cone numbers here too (sequential list streams must still consume them)
+        rng.next_f32(S_NEE); rng.next_f32(S_NEE + 1);
         if (!visible(sc, light, xt, n_scans)) return mk(0, 0, 0);
         return mk(src.lr, src.lg, src.lb) * (expf(-k.sigma_t * d2 * inv) * kInv4Pi / d2);
     }
-    const float xi1 = rng.next_f32(), xi2 = rng.next_f32();
+    const float xi1 = rng.next_f32(S_NEE), xi2 = rng.next_f32(S_NEE + 1);
     const float omc_max = one_minus_cos_max(src.r * src.r / d2);
     const F3 wl = cone_sample(wc * inv, omc_max, xi1, xi2);
     float t; int hit_id = -1;
@@ -316,14 +316,14 @@ __device__ __forceinline__ bool vertex(const SceneF &sc, const MatF *mats, const
     const bool hit = scan(sc, p.o, p.d, t, id, tally.scans);
     if (!hit) t = kMaxFloat;
 
-    const int pick = min((int)(rng.next_f32() * k.n_emitters), sc.n_emitters - 1);
+    const int pick = min((int)(rng.next_f32(S_SRC) * k.n_emitters), sc.n_emitters - 1);
     const int src_id = sc.emitters[pick];
     const MatF &src = mats[src_id];
 
     bool surface;
     float dist, inv_pdf = 1.0f;
     if (METHOD == 0) {
-        dist = -logf(1.0f - rng.next_f32()) * k.inv_sigma_t; // freeFlightSample, vptSamplingFunctions.h:11
+        dist = -logf(1.0f - rng.next_f32(S_DIST)) * k.inv_sigma_t; // freeFlightSample, vptSamplingFunctions.h:11
         surface = dist > t;
     } else {
         // equiAngularParams2 (volumetricBasicFunctions.h:209-223) + equiAngularProb (vptSamplingFunctions.h:60)
@@ -333,11 +333,11 @@ __device__ __forceinline__ bool vertex(const SceneF &sc, const MatF *mats, const
         const F3 perp = fma3(p.d, -proj, dv);
         const float D = sqrtf(dot(perp, perp));
         const float thA = atan2f(-proj, D), thB = atan2f(t - proj, D);
-        const float xi = rng.next_f32();
+        const float xi = rng.next_f32(S_DIST);
         const float tl = D * tanf((1.0f - xi) * thA + xi * thB);
         dist = tl + proj;
         inv_pdf = fabsf(thB - thA) * (tl * tl + D * D) / (D * (1.0f - Tr));
-        const float xs = rng.next_f32();
+        const float xs = rng.next_f32(S_DECIDE);
         surface = (METHOD == 1) ? (xs <= Tr) : (xs < Tr);
     }
 
@@ -353,7 +353,7 @@ __device__ __forceinline__ bool vertex(const SceneF &sc, const MatF *mats, const
         const F3 Ld_point = point_light_direct(sc, obj, src, x, fr, wo_l, k, tally.scans);
         const F3 Ld = surface_direct_mis(sc, mats, obj, x, fr, wo_l, k, rng, tally.scans);
         p.L = p.L + had(Ld_point + Ld, p.beta) * k.inv_cp;
-        const float xi1 = rng.next_f32(), xi2 = rng.next_f32();
+        const float xi1 = rng.next_f32(S_BSDF), xi2 = rng.next_f32(S_BSDF + 1);
         F3 wi;
         const F3 weight = bsdf_sample(obj, fr, wo_l, xi1, xi2, wi);
         p.beta = had(p.beta, weight) * k.inv_cp;
@@ -362,7 +362,7 @@ __device__ __forceinline__ bool vertex(const SceneF &sc, const MatF *mats, const
     } else {
         const F3 xt = fma3(p.d, dist, p.o);
         const F3 Ld = medium_direct(sc, src, src_id, xt, k, rng, tally.scans) * k.n_emitters;
-        const float xi1 = rng.next_f32(), xi2 = rng.next_f32();
+        const float xi1 = rng.next_f32(S_PHASE), xi2 = rng.next_f32(S_PHASE + 1);
         if (METHOD == 0) {
             p.L = p.L + had(Ld, p.beta) * k.albedo_over_cp;
             p.beta = p.beta * k.albedo_over_cp;

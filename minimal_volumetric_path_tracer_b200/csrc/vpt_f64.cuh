@@ -188,14 +188,14 @@ __device__ __forceinline__ D3 facet_brdf(const SphereD &m, D3 wi, D3 wh, D3 wo, 
 // muestreoSA -> solidAngle(L), samplingFunctions.h:238-247 and :163-206
 template <class RngT>
 __device__ __forceinline__ D3 light_sampled_direct(const Ctx &c, int light, D3 x, const SphereD &obj, D3 n, D3 wray, double alpha, D3 &wi_out, double &cos_max_out,
-                                                   RngT &rng, Tally &tl) {
+                                                   RngT &rng, Tally &tl, uint32_t slot) {
     const SphereD &src = c.s[light];
     D3 cx = pos(src) - x;
     const double len = sqrt(dot(cx, cx));
     cx = cx * (1 / len);
     const double cos_max = sqrt(1 - (src.r / len) * (src.r / len));
     cos_max_out = cos_max;
-    const double e0 = rng.next_f64(), e1 = rng.next_f64();
+    const double e0 = rng.next_f64(slot), e1 = rng.next_f64(slot + 1);
     const D3 wi = cone_sample(cx, cos_max, e0, e1);
     wi_out = wi;
     const D3 wil = unit(to_local(n, wi));
@@ -217,10 +217,11 @@ __device__ __forceinline__ D3 surface_direct_mis(const Ctx &c, const SphereD &ob
     D3 total = mk(0, 0, 0);
     D3 wo = wray * -1;
     double cos_max = 0;
+    uint32_t area_index = 0;
     for (int light = 0; light < c.n_spheres; ++light) {
         if (c.s[light].r > 0 && c.s[light].lr > 0) {
             D3 wi_light;
-            const D3 f = light_sampled_direct(c, light, x, obj, n, wray, alpha, wi_light, cos_max, rng, tl) * transmittance(x, pos(c.s[light]), c.sigma_t);
+            const D3 f = light_sampled_direct(c, light, x, obj, n, wray, alpha, wi_light, cos_max, rng, tl, S_AREA + 2 * area_index++) * transmittance(x, pos(c.s[light]), c.sigma_t);
             const double fpdf = cone_pdf(cos_max);
             double gpdf;
             if (obj.material == 0) gpdf = cosine_pdf(dot(n, wi_light));
@@ -231,7 +232,7 @@ __device__ __forceinline__ D3 surface_direct_mis(const Ctx &c, const SphereD &ob
     D3 g;
     double wg;
     if (obj.material == 0) {
-        const double xi1 = rng.next_f64(), xi2 = rng.next_f64();
+        const double xi1 = rng.next_f64(S_MIS), xi2 = rng.next_f64(S_MIS + 1);
         const D3 wi = unit(cosine_hemisphere(n, xi1, xi2)); // uniform, samplingFunctions.h:250-261
         int source = -1;
         const D3 Le = first_hit_radiance(c, x, wi, source, tl);
@@ -240,7 +241,7 @@ __device__ __forceinline__ D3 surface_direct_mis(const Ctx &c, const SphereD &ob
         if (g.x > 0 && g.y > 0 && g.z > 0) wg = power_heuristic(gpdf, cone_pdf(cone_cos(c, source, x)));
         else wg = 0;
     } else {
-        const double xi1 = rng.next_f64(), xi2 = rng.next_f64();
+        const double xi1 = rng.next_f64(S_MIS), xi2 = rng.next_f64(S_MIS + 1);
         const D3 wh = facet_normal(alpha, xi1, xi2);
         wo = unit(to_local(n, wo));
         const D3 nl = mk(0, 0, 1); // microfacet, samplingFunctions.h:97-118
@@ -277,7 +278,7 @@ __device__ __forceinline__ D3 point_light_direct(const Ctx &c, const SphereD &ob
 template <class RngT>
 __device__ __forceinline__ D3 bsdf_sample(const SphereD &obj, D3 &wi_out, D3 wray, D3 n, double &pdf, RngT &rng) {
     const D3 wo = wray * -1;
-    const double xi1 = rng.next_f64(), xi2 = rng.next_f64();
+    const double xi1 = rng.next_f64(S_BSDF), xi2 = rng.next_f64(S_BSDF + 1);
     if (obj.material == 0) {
         const D3 wi = cosine_hemisphere(n, xi1, xi2);
         pdf = cosine_pdf(dot(n, wi));
@@ -311,7 +312,7 @@ __device__ __forceinline__ D3 medium_direct(const Ctx &c, D3 xt, int source, dou
     const double len = sqrt(dot(wc, wc));
     wc = wc * (1 / len);
     const double cos_max = sqrt(1 - src.r / len * (src.r / len));
-    const double e0 = rng.next_f64(), e1 = rng.next_f64();
+    const double e0 = rng.next_f64(S_NEE), e1 = rng.next_f64(S_NEE + 1);
     const D3 wl = cone_sample(wc, cos_max, e0, e1);
     const double prob_wl = cone_pdf(cos_max);
     double dist;
@@ -340,12 +341,12 @@ __device__ __forceinline__ bool vertex(const Ctx &c, Path &p, RngT &rng, Tally &
     const D3 n = unit(xs - pos(c.s[id]));
     if (c.n_emitters == 0) return false;
     const double prob_source = 1.0 / c.n_emitters;
-    const int source = c.emitters[static_cast<int>(rng.next_f64() * c.n_emitters)];
+    const int source = c.emitters[static_cast<int>(rng.next_f64(S_SRC) * c.n_emitters)];
 
     bool surface;
     double dist, pdf_medium = 1;
     if (c.method == 0) {
-        dist = -log(1 - rng.next_f64()) / c.sigma_t;
+        dist = -log(1 - rng.next_f64(S_DIST)) / c.sigma_t;
         surface = dist > t;
     } else {
         if (c.method == 2) Tr = exp(c.sigma_t * t * -1.0);
@@ -355,11 +356,11 @@ __device__ __forceinline__ bool vertex(const Ctx &c, Path &p, RngT &rng, Tally &
         const double proj = dot(dv, p.d) / dot(p.d, p.d);
         const double D = sqrt(len * len - proj * proj);
         const double thA = atan2(0.0 - proj, D), thB = atan2(t - proj, D);
-        const double xi = rng.next_f64();
+        const double xi = rng.next_f64(S_DIST);
         const double t_local = D * tan((1 - xi) * thA + xi * thB);
         dist = t_local + proj;
         pdf_medium = D / fabs(thB - thA) / (t_local * t_local + D * D) * (1.0 - Tr);
-        const double xs_ = rng.next_f64();
+        const double xs_ = rng.next_f64(S_DECIDE);
         surface = (c.method == 1) ? (xs_ <= Tr) : (xs_ < Tr);
     }
 
@@ -385,14 +386,14 @@ __device__ __forceinline__ bool vertex(const Ctx &c, Path &p, RngT &rng, Tally &
         const D3 xt = p.o + p.d * dist;
         if (c.method == 0) {
             const D3 Ld = medium_direct(c, xt, source, prob_source, false, 0.0, rng, tl);
-            const double xi1 = rng.next_f64(), xi2 = rng.next_f64();
+            const double xi1 = rng.next_f64(S_PHASE), xi2 = rng.next_f64(S_PHASE + 1);
             p.L = p.L + had(Ld, p.beta) * (c.sigma_s / c.sigma_t) * (1 / c.cp);
             p.beta = p.beta * (c.sigma_s / c.sigma_t) * (1 / c.cp);
             p.o = xt; p.d = phase_sample(xi1, xi2);
         } else {
             const double T = transmittance(p.o, xt, c.sigma_t);
             const D3 Ld = medium_direct(c, xt, source, prob_source, true, T, rng, tl);
-            const double xi1 = rng.next_f64(), xi2 = rng.next_f64();
+            const double xi1 = rng.next_f64(S_PHASE), xi2 = rng.next_f64(S_PHASE + 1);
             p.L = p.L + had(Ld * (1 / pdf_medium) * (1 / c.cp), p.beta);
             p.beta = p.beta * c.sigma_s * T * (1 / c.cp) * (1 / pdf_medium);
             p.o = xt; p.d = phase_sample(xi1, xi2);

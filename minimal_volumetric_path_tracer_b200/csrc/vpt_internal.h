@@ -39,6 +39,7 @@ struct MatF {
 };
 struct SceneF {
     int32_t n_spheres, n_geom, n_emitters, n_area;
+    int32_t n_big, pad0, pad1, pad2; // geom[0 .. n_big) are the re-anchored huge spheres, the rest ordinary ones
     int32_t emitters[kMaxEmitters]; // spheres with any radiance channel > 0, in index order
     int32_t area[kMaxEmitters];     // spheres with r > 0 && radiance.x > 0 (misSamplingFunctions.h:106), in index order
     GeomF geom[kMaxSpheres];
@@ -76,14 +77,22 @@ struct LaunchParams {
     double cam_o[3], cam_d[3], cam_cx[3], cam_cy[3];
 };
 
+// fp32 constants derived from LaunchParams on the host (double arithmetic), so that no kernel converts doubles in its hot loop
+struct ConstsF {
+    float sigma_t, inv_sigma_t, sigma_s, albedo_over_cp, inv_cp, q;
+    float n_emitters; // 1 / probSource
+    int32_t method, max_depth;
+    float cam_o[3], cam_d[3], cam_cx[3], cam_cy[3], inv_w, inv_h;
+};
+
 struct Counters { // device-side, accumulated with atomics at thread exit
     unsigned long long events, scans, nonfinite, paths;
 };
 
 // entry points implemented in the .cu files, called from vpt_api.cpp
-int launch_render_f32(const SceneF &scene, const LaunchParams &lp, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks);
+int launch_render_f32(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks, int kernel);
 int launch_render_f64(const SceneD &scene, const LaunchParams &lp, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks);
-int launch_unit_f32(int fn, const SceneF &scene, const LaunchParams &lp, int n, const double *in_dev, int in_stride, double *out_dev, int out_stride, void *stream);
+int launch_unit_f32(int fn, const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, int n, const double *in_dev, int in_stride, double *out_dev, int out_stride, void *stream);
 int launch_unit_f64(int fn, const SceneD &scene, const LaunchParams &lp, int n, const double *in_dev, int in_stride, double *out_dev, int out_stride, void *stream);
 int launch_philox(int n, const uint32_t *ctr_dev, const uint32_t *key_dev, uint32_t *out_dev, void *stream);
 int launch_fma_peak(float *sink_dev, int n_blocks, int n_threads, int iters, void *stream);

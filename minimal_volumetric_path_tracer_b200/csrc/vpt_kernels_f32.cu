@@ -9,36 +9,24 @@
 // 12 B / pixel store.
 #include <cuda_runtime.h>
 #include "vpt_f32.cuh"
+#include "vpt_mega_scan.cuh"
 
 namespace vpt {
 
 using namespace f32;
 
-__device__ __forceinline__ Consts make_consts(const LaunchParams &lp, const SceneF &sc) {
+__device__ __forceinline__ Consts make_consts(const ConstsF &c) {
     Consts k;
-    const double st = lp.sigma_a + lp.sigma_s;
-    k.sigma_t = (float)st;
-    k.inv_sigma_t = (float)(1.0 / st);
-    k.sigma_s = (float)lp.sigma_s;
-    k.albedo_over_cp = (float)(lp.sigma_s / st / lp.continue_prob);
-    k.inv_cp = (float)(1.0 / lp.continue_prob);
-    k.q = (float)(1.0 - lp.continue_prob);
-    k.n_emitters = (float)sc.n_emitters;
-    k.method = lp.method;
-    k.max_depth = lp.max_depth;
+    k.sigma_t = c.sigma_t; k.inv_sigma_t = c.inv_sigma_t; k.sigma_s = c.sigma_s; k.albedo_over_cp = c.albedo_over_cp;
+    k.inv_cp = c.inv_cp; k.q = c.q; k.n_emitters = c.n_emitters; k.method = c.method; k.max_depth = c.max_depth;
     return k;
 }
-
-struct CameraF { F3 o, d, cx, cy; float inv_w, inv_h; };
-__device__ __forceinline__ CameraF make_camera(const LaunchParams &lp) {
-    CameraF c;
-    c.o = mk((float)lp.cam_o[0], (float)lp.cam_o[1], (float)lp.cam_o[2]);
-    c.d = mk((float)lp.cam_d[0], (float)lp.cam_d[1], (float)lp.cam_d[2]);
-    c.cx = mk((float)lp.cam_cx[0], (float)lp.cam_cx[1], (float)lp.cam_cx[2]);
-    c.cy = mk((float)lp.cam_cy[0], (float)lp.cam_cy[1], (float)lp.cam_cy[2]);
-    c.inv_w = 1.0f / (float)lp.width;
-    c.inv_h = 1.0f / (float)lp.height;
-    return c;
+__device__ __forceinline__ CameraF make_camera(const ConstsF &c) {
+    CameraF cam;
+    cam.o = mk(c.cam_o[0], c.cam_o[1], c.cam_o[2]); cam.d = mk(c.cam_d[0], c.cam_d[1], c.cam_d[2]);
+    cam.cx = mk(c.cam_cx[0], c.cam_cx[1], c.cam_cx[2]); cam.cy = mk(c.cam_cy[0], c.cam_cy[1], c.cam_cy[2]);
+    cam.inv_w = c.inv_w; cam.inv_h = c.inv_h;
+    return cam;
 }
 // rt.cpp:787
 __device__ __forceinline__ F3 camera_dir(const CameraF &c, float x, float y, float xi1, float xi2) {
@@ -48,7 +36,7 @@ __device__ __forceinline__ F3 camera_dir(const CameraF &c, float x, float y, flo
 
 template <int METHOD>
 __global__ void __launch_bounds__(kThreadsPerBlock) render_f32_kernel(const __grid_constant__ SceneF sc, const __grid_constant__ LaunchParams lp,
-                                                                       float *__restrict__ hdr, Counters *__restrict__ counters) {
+                                                                       const __grid_constant__ ConstsF cf, float *__restrict__ hdr, Counters *__restrict__ counters) {
     __shared__ MatF mats[kMaxSpheres];
     for (int i = threadIdx.x; i < sc.n_spheres * (int)(sizeof(MatF) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t *>(mats)[i] = reinterpret_cast<const uint32_t *>(sc.mat)[i];
@@ -58,8 +46,8 @@ __global__ void __launch_bounds__(kThreadsPerBlock) render_f32_kernel(const __gr
     const long long pixel = tile * kTile + threadIdx.x;
     if (pixel >= lp.n_pixels) return;
 
-    const Consts k = make_consts(lp, sc);
-    const CameraF cam = make_camera(lp);
+    const Consts k = make_consts(cf);
+    const CameraF cam = make_camera(cf);
     const int row = (int)(pixel / lp.width), col = (int)(pixel - (long long)row * lp.width);
     const float fx = (float)col, fy = (float)(lp.height - 1 - row); // rt.cpp:773: storage row 0 is the top of the image
 
@@ -79,15 +67,15 @@ __global__ void __launch_bounds__(kThreadsPerBlock) render_f32_kernel(const __gr
             if (!active) {
                 if (s >= lp.sample_end) break;
                 rng.start((uint32_t)pixel, (uint32_t)s, lp.key0, lp.key1);
-                const float j1 = rng.next_f32(), j2 = rng.next_f32();
+                float j1, j2;
+                rng.jitter_f32(j1, j2);
                 p.o = cam.o; p.d = camera_dir(cam, fx, fy, j1, j2);
                 p.beta = mk(1, 1, 1); p.L = mk(0, 0, 0); p.depth = 0;
                 active = true; ++s;
-            } else {
-                rng.begin_bounce((uint32_t)p.depth);
             }
+            rng.begin_bounce((uint32_t)p.depth);
             const bool too_deep = k.max_depth > 0 && p.depth >= k.max_depth;
-            if (too_deep || rng.next_f32() < k.q) { // roulette at every vertex including the first (:1282)
+            if (too_deep || rng.next_f32(S_RR) < k.q) { // roulette at every vertex including the first (:1282)
                 const float sum = p.L.x + p.L.y + p.L.z;
                 if (isfinite(sum)) { acc_r += p.L.x; acc_g += p.L.y; acc_b += p.L.z; } else ++nonfinite;
                 active = false;
@@ -128,12 +116,48 @@ __global__ void __launch_bounds__(kThreadsPerBlock) render_f32_kernel(const __gr
     }
 }
 
-int launch_render_f32(const SceneF &scene, const LaunchParams &lp, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks) {
+// ---- scan-converged megakernel (vpt_mega_scan.cuh) ------------------------------------------------------------------------------
+template <int METHOD>
+__global__ void __launch_bounds__(kThreadsPerBlock) render_f32_scan_kernel(const __grid_constant__ SceneF sc, const __grid_constant__ LaunchParams lp,
+                                                                            const __grid_constant__ ConstsF cf, float *__restrict__ hdr, Counters *__restrict__ counters) {
+    __shared__ MatF mats[kMaxSpheres];
+    for (int i = threadIdx.x; i < sc.n_spheres * (int)(sizeof(MatF) / 4); i += blockDim.x)
+        reinterpret_cast<uint32_t *>(mats)[i] = reinterpret_cast<const uint32_t *>(sc.mat)[i];
+    __syncthreads();
+    const long long tile = (long long)blockIdx.x * lp.tile_count + lp.tile_rank;
+    const long long pixel = tile * kTile + threadIdx.x;
+    if (pixel >= lp.n_pixels) return;
+    const Consts k = make_consts(cf);
+    const CameraF cam = make_camera(cf);
+    const int row = (int)(pixel / lp.width), col = (int)(pixel - (long long)row * lp.width);
+    double acc[3] = {0, 0, 0};
+    Tally tally{0u, 0u};
+    unsigned nonfinite = 0;
+    render_pixel_scan<METHOD>(sc, mats, k, cam, (float)col, (float)(lp.height - 1 - row), (uint32_t)pixel, lp.sample_begin, lp.sample_end, lp.key0, lp.key1, acc, tally, nonfinite);
+    float *out = hdr + pixel * 3;
+    out[0] = (float)(acc[0] * lp.out_scale);
+    out[1] = (float)(acc[1] * lp.out_scale);
+    out[2] = (float)(acc[2] * lp.out_scale);
+    if (!counters) return;
+    atomicAdd(&counters->events, (unsigned long long)tally.events); atomicAdd(&counters->scans, (unsigned long long)tally.scans);
+    if (nonfinite) atomicAdd(&counters->nonfinite, (unsigned long long)nonfinite);
+    atomicAdd(&counters->paths, (unsigned long long)(lp.sample_end - lp.sample_begin));
+}
+
+int launch_render_f32(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks, int kernel) {
     cudaStream_t st = (cudaStream_t)stream;
-    switch (lp.method) {
-    case 0: render_f32_kernel<0><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, hdr_dev, counters_dev); break;
-    case 1: render_f32_kernel<1><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, hdr_dev, counters_dev); break;
-    default: render_f32_kernel<2><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, hdr_dev, counters_dev); break;
+    if (kernel == VPT_KERNEL_MEGA) {
+        switch (lp.method) {
+        case 0: render_f32_kernel<0><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
+        case 1: render_f32_kernel<1><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
+        default: render_f32_kernel<2><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
+        }
+    } else {
+        switch (lp.method) {
+        case 0: render_f32_scan_kernel<0><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
+        case 1: render_f32_scan_kernel<1><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
+        default: render_f32_scan_kernel<2><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
+        }
     }
     return (int)cudaGetLastError();
 }
@@ -145,12 +169,11 @@ __device__ __forceinline__ void st3(double *p, F3 v) { p[0] = v.x; p[1] = v.y; p
 // explicit uniforms of a test row, served through the stream interface the render code uses
 struct ListRng {
     const double *u; int i; int n = 1 << 30; bool overrun = false;
-    __device__ float next_f32() { if (i >= n) { overrun = true; return 0.0f; } /* 0 < q: the next roulette draw ends the path */ return (float)u[i++]; }
-    __device__ void skip(int k) { i += k; }
+    __device__ float next_f32(uint32_t = 0) { if (i >= n) { overrun = true; return 0.0f; } /* 0 < q: the next roulette draw ends the path */ return (float)u[i++]; }
     __device__ void begin_bounce(uint32_t) {}
 };
 
-__global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const __grid_constant__ LaunchParams lp, int n, const double *__restrict__ in,
+__global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const __grid_constant__ LaunchParams lp, const __grid_constant__ ConstsF cf, int n, const double *__restrict__ in,
                                 int in_stride, double *__restrict__ out, int out_stride) {
     __shared__ MatF mats[kMaxSpheres];
     for (int i = threadIdx.x; i < sc.n_spheres * (int)(sizeof(MatF) / 4); i += blockDim.x)
@@ -160,7 +183,7 @@ __global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const
     if (row >= n) return;
     const double *a = in + (size_t)row * in_stride;
     double *o = out + (size_t)row * out_stride;
-    const Consts k = make_consts(lp, sc);
+    const Consts k = make_consts(cf);
     unsigned scans = 0;
     switch (fn) {
     case VPT_UNIT_SPHERE_INTERSECT: {
@@ -259,11 +282,11 @@ __global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const
     } break;
     case VPT_UNIT_RADIANCE: {
         Path p; p.o = ld3(a); p.d = ld3(a + 3); p.beta = mk(1, 1, 1); p.L = mk(0, 0, 0); p.depth = 0;
-        Rng rng; rng.start((uint32_t)a[6], (uint32_t)a[7], lp.key0, lp.key1); rng.skip(2);
+        Rng rng; rng.start((uint32_t)a[6], (uint32_t)a[7], lp.key0, lp.key1);
         Tally tally{0u, 0u};
         for (;;) {
             rng.begin_bounce((uint32_t)p.depth);
-            if ((k.max_depth > 0 && p.depth >= k.max_depth) || rng.next_f32() < k.q) break;
+            if ((k.max_depth > 0 && p.depth >= k.max_depth) || rng.next_f32(S_RR) < k.q) break;
             bool alive;
             if (lp.method == 0) alive = vertex<0>(sc, mats, k, p, rng, tally);
             else if (lp.method == 1) alive = vertex<1>(sc, mats, k, p, rng, tally);
@@ -278,7 +301,7 @@ __global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const
         ListRng rng{a + 7, 0, min((int)a[6], 120)};
         Tally tally{0u, 0u};
         for (;;) {
-            if ((k.max_depth > 0 && p.depth >= k.max_depth) || rng.next_f32() < k.q) break;
+            if ((k.max_depth > 0 && p.depth >= k.max_depth) || rng.next_f32(S_RR) < k.q) break;
             bool alive;
             if (lp.method == 0) alive = vertex<0>(sc, mats, k, p, rng, tally);
             else if (lp.method == 1) alive = vertex<1>(sc, mats, k, p, rng, tally);
@@ -289,16 +312,16 @@ __global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const
         st3(o, p.L); o[3] = rng.overrun ? -1.0 : (double)rng.i;
     } break;
     case VPT_UNIT_CAMERA_RAY: {
-        const CameraF cam = make_camera(lp);
+        const CameraF cam = make_camera(cf);
         st3(o, camera_dir(cam, (float)a[0], (float)a[1], (float)a[2], (float)a[3]));
     } break;
     default: break;
     }
 }
 
-int launch_unit_f32(int fn, const SceneF &scene, const LaunchParams &lp, int n, const double *in_dev, int in_stride, double *out_dev, int out_stride, void *stream) {
+int launch_unit_f32(int fn, const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, int n, const double *in_dev, int in_stride, double *out_dev, int out_stride, void *stream) {
     const int tpb = 64;
-    unit_f32_kernel<<<(n + tpb - 1) / tpb, tpb, 0, (cudaStream_t)stream>>>(fn, scene, lp, n, in_dev, in_stride, out_dev, out_stride);
+    unit_f32_kernel<<<(n + tpb - 1) / tpb, tpb, 0, (cudaStream_t)stream>>>(fn, scene, lp, cf, n, in_dev, in_stride, out_dev, out_stride);
     return (int)cudaGetLastError();
 }
 

@@ -56,15 +56,15 @@ __global__ void __launch_bounds__(kThreadsPerBlock) render_f64_kernel(const __gr
             if (!active) {
                 if (s >= lp.sample_end) break;
                 rng.start((uint32_t)pixel, (uint32_t)s, lp.key0, lp.key1);
-                const double j1 = rng.next_f64(), j2 = rng.next_f64();
+                double j1, j2;
+                rng.jitter_f64(j1, j2);
                 p.o = v3(lp.cam_o); p.d = camera_dir(lp, col, cam_y, j1, j2);
                 p.beta = mk(1, 1, 1); p.L = mk(0, 0, 0); p.depth = 0;
                 active = true; ++s;
-            } else {
-                rng.begin_bounce((uint32_t)p.depth);
             }
+            rng.begin_bounce((uint32_t)p.depth);
             const bool too_deep = c.max_depth > 0 && p.depth >= c.max_depth;
-            if (too_deep || rng.next_f64() < c.q) {
+            if (too_deep || rng.next_f64(S_RR) < c.q) {
                 if (isfinite(p.L.x + p.L.y + p.L.z)) { acc_r += p.L.x; acc_g += p.L.y; acc_b += p.L.z; } else ++nonfinite;
                 active = false;
                 continue;
@@ -99,7 +99,7 @@ int launch_render_f64(const SceneD &scene, const LaunchParams &lp, float *hdr_de
 // ---- unit kernels ---------------------------------------------------------------------------------------------------------
 struct ListRng {
     const double *u; int i; int n = 1 << 30; bool overrun = false;
-    __device__ double next_f64() { if (i >= n) { overrun = true; return 0.0; } /* 0 < q: the next roulette draw ends the path */ return u[i++]; }
+    __device__ double next_f64(uint32_t = 0) { if (i >= n) { overrun = true; return 0.0; } /* 0 < q: the next roulette draw ends the path */ return u[i++]; }
     __device__ void begin_bounce(uint32_t) {}
 };
 __device__ __forceinline__ void st3(double *p, D3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
@@ -183,10 +183,10 @@ __global__ void unit_f64_kernel(int fn, const __grid_constant__ SceneD sc, const
     } break;
     case VPT_UNIT_RADIANCE: {
         Path p; p.o = v3(a); p.d = v3(a + 3); p.beta = mk(1, 1, 1); p.L = mk(0, 0, 0); p.depth = 0;
-        Rng rng; rng.start((uint32_t)a[6], (uint32_t)a[7], lp.key0, lp.key1); rng.skip(2);
+        Rng rng; rng.start((uint32_t)a[6], (uint32_t)a[7], lp.key0, lp.key1);
         for (;;) {
             rng.begin_bounce((uint32_t)p.depth);
-            if ((c.max_depth > 0 && p.depth >= c.max_depth) || rng.next_f64() < c.q) break;
+            if ((c.max_depth > 0 && p.depth >= c.max_depth) || rng.next_f64(S_RR) < c.q) break;
             if (!vertex(c, p, rng, tl)) break;
             ++p.depth;
         }
@@ -196,7 +196,7 @@ __global__ void unit_f64_kernel(int fn, const __grid_constant__ SceneD sc, const
         Path p; p.o = v3(a); p.d = v3(a + 3); p.beta = mk(1, 1, 1); p.L = mk(0, 0, 0); p.depth = 0;
         ListRng rng{a + 7, 0, min((int)a[6], 120)};
         for (;;) {
-            if ((c.max_depth > 0 && p.depth >= c.max_depth) || rng.next_f64() < c.q) break;
+            if ((c.max_depth > 0 && p.depth >= c.max_depth) || rng.next_f64(S_RR) < c.q) break;
             if (!vertex(c, p, rng, tl)) break;
             ++p.depth;
         }

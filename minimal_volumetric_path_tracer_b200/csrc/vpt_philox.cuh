@@ -3,15 +3,22 @@
 //
 // Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11).  Stream convention (DESIGN.md "RNG"):
 //   key     = (seed & 0xffffffff, seed >> 32)
-//   counter = (pixel, sample, bounce, block)       block = draw_index / 4, lane = draw_index % 4
+//   counter = (pixel, sample, bounce, block)       block = slot / 4, lane = slot % 4
 //   uniform = (2 * (word >> 9) + 1) * 2^-24        in (0,1), never 0 or 1 (the reference's 48-bit erand48 practically never
 //                                                  returns 0 either); exact in fp32 and fp64 -> both precisions see the same numbers
-// Draw order inside a bounce is the reference's consumption order (SURVEY.md section 8a pseudo-code).  Bounce 0 starts
-// with the two pixel-jitter draws of rt.cpp:787.
+// One fixed slot per PURPOSE inside a bounce, so a kernel may generate blocks where it needs them instead of in the
+// reference's consumption order (the FP64 CPU oracle uses the same table, oracle/philox.h):
+//   0 roulette   1 light pick   2 distance (free-flight xi or equi-angular xi)   3 equi-angular surface/medium decision
+//   medium vertex : 4,5 NEE cone sample      6,7 phase-function sample
+//   surface vertex: 4,5 BSDF sample (next direction)   6,7 BSDF-sampled direct light (MISv2)   8+2a, 9+2a cone sample of area light a
+//   pixel jitter (rt.cpp:787): slots 0,1 of the pseudo-bounce 0xffffffff
 #pragma once
 #include <stdint.h>
 
 namespace vpt {
+
+enum : uint32_t { S_RR = 0, S_SRC = 1, S_DIST = 2, S_DECIDE = 3, S_NEE = 4, S_PHASE = 6, S_BSDF = 4, S_MIS = 6, S_AREA = 8 };
+constexpr uint32_t kJitterBounce = 0xffffffffu;
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
 #pragma unroll
@@ -24,30 +31,38 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1
     }
     return c;
 }
+// out-of-line copy: the megakernels call this from several places and must stay small enough for the instruction cache
+static __device__ __noinline__ uint4 philox_block(uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t block, uint32_t k0, uint32_t k1) {
+    return philox4x32_10(make_uint4(pixel, sample, bounce, block), k0, k1);
+}
+__device__ __forceinline__ float u32_to_unit_f32(uint32_t w) { return (float)(2u * (w >> 9) + 1u) * 5.9604644775390625e-8f; }
+__device__ __forceinline__ double u32_to_unit_f64(uint32_t w) { return (double)(2u * (w >> 9) + 1u) * 5.9604644775390625e-8; }
+__device__ __forceinline__ uint32_t pick_lane(const uint4 &b, uint32_t lane) { return lane == 0 ? b.x : lane == 1 ? b.y : lane == 2 ? b.z : b.w; }
 
 struct Rng {
     uint32_t pixel, sample, bounce, k0, k1;
-    uint32_t idx;    // next draw index inside this bounce
     uint32_t loaded; // block currently held in buf (0xffffffff: none)
     uint4 buf;
 
     __device__ __forceinline__ void start(uint32_t pixel_, uint32_t sample_, uint32_t key0, uint32_t key1) {
-        pixel = pixel_; sample = sample_; bounce = 0; k0 = key0; k1 = key1; idx = 0; loaded = 0xffffffffu;
+        pixel = pixel_; sample = sample_; bounce = 0; k0 = key0; k1 = key1; loaded = 0xffffffffu;
     }
-    __device__ __forceinline__ void begin_bounce(uint32_t b) {
-        if (b == 0) return; // bounce 0 continues after the jitter draws
-        bounce = b; idx = 0; loaded = 0xffffffffu;
+    __device__ __forceinline__ void begin_bounce(uint32_t b) { bounce = b; loaded = 0xffffffffu; }
+    __device__ __forceinline__ uint32_t word(uint32_t slot) {
+        const uint32_t blk = slot >> 2;
+        if (blk != loaded) { buf = philox_block(pixel, sample, bounce, blk, k0, k1); loaded = blk; }
+        return pick_lane(buf, slot & 3u);
     }
-    __device__ __forceinline__ void skip(uint32_t n) { idx += n; }
-    __device__ __forceinline__ uint32_t next_word() {
-        const uint32_t blk = idx >> 2;
-        if (blk != loaded) { buf = philox4x32_10(make_uint4(pixel, sample, bounce, blk), k0, k1); loaded = blk; }
-        const uint32_t lane = idx & 3u;
-        ++idx;
-        return lane == 0 ? buf.x : lane == 1 ? buf.y : lane == 2 ? buf.z : buf.w;
+    __device__ __forceinline__ float next_f32(uint32_t slot) { return u32_to_unit_f32(word(slot)); }
+    __device__ __forceinline__ double next_f64(uint32_t slot) { return u32_to_unit_f64(word(slot)); }
+    __device__ __forceinline__ void jitter_f32(float &a, float &b) {
+        const uint4 r = philox_block(pixel, sample, kJitterBounce, 0, k0, k1);
+        a = u32_to_unit_f32(r.x); b = u32_to_unit_f32(r.y);
     }
-    __device__ __forceinline__ float next_f32() { return (float)(2u * (next_word() >> 9) + 1u) * 5.9604644775390625e-8f; }
-    __device__ __forceinline__ double next_f64() { return (double)(2u * (next_word() >> 9) + 1u) * 5.9604644775390625e-8; }
+    __device__ __forceinline__ void jitter_f64(double &a, double &b) {
+        const uint4 r = philox_block(pixel, sample, kJitterBounce, 0, k0, k1);
+        a = u32_to_unit_f64(r.x); b = u32_to_unit_f64(r.y);
+    }
 };
 
 } // namespace vpt

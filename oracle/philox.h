@@ -5,7 +5,12 @@
  *
  * Stream convention shared with the product (DESIGN.md "RNG"):
  *   key     = (seed & 0xffffffff, seed >> 32)
- *   counter = (pixel, sample, bounce, block)     block = draw_index / 4, lane = draw_index % 4
+ *   counter = (pixel, sample, bounce, block)     block = slot / 4, lane = slot % 4
+ *   slots of one bounce (a fixed slot per PURPOSE, so that a GPU kernel may generate blocks out of consumption order):
+ *       0 roulette   1 light pick   2 distance (free-flight xi or equi-angular xi)   3 equi-angular surface/medium decision
+ *       medium vertex : 4,5 NEE cone sample      6,7 phase-function sample
+ *       surface vertex: 4,5 BSDF sample (next direction)   6,7 BSDF-sampled direct light (MISv2)   8+2a, 9+2a cone sample of area light a
+ *   pixel jitter (rt.cpp:787): slots 0,1 of the pseudo-bounce 0xffffffff
  *   uniform = (2 * (word >> 9) + 1) * 2^-24      in (0, 1): never 0 or 1, exactly representable in fp32 and fp64
  */
 #ifndef VPT_ORACLE_PHILOX_H

@@ -46,6 +46,9 @@ namespace vpt_oracle {
 constexpr int VPT_ORACLE_MAX_EMITTERS = 16;
 constexpr double kMaxFloat = 3.40282346638528859811704183484516925e+38; /* MAXFLOAT, vptShadeMethods.h:1287 */
 constexpr double kPi = 3.14159265358979323846;                          /* M_PI */
+/* Philox slot of every draw (oracle/philox.h); sequential streams (erand48, explicit lists) ignore the slot, so the
+ * CONSUMPTION ORDER below stays the reference's. */
+enum : unsigned { S_RR = 0, S_SRC = 1, S_DIST = 2, S_DECIDE = 3, S_NEE = 4, S_PHASE = 6, S_BSDF = 4, S_MIS = 6, S_AREA = 8 };
 
 enum : unsigned { QUIRK_R0_FALLTHROUGH = 1u, QUIRK_EXACT_VISIBILITY = 2u };
 
@@ -163,7 +166,7 @@ static inline Vec from_local(const Vec &n, double a, double b, double c) { /* s*
 
 /* ---- vptSamplingFunctions.h ---------------------------------------------------------------------- */
 template <class Rng> static inline double free_flight_sample(Rng &rng, double sigma_t) { /* :11-16 */
-    const double xi = rng.next();
+    const double xi = rng.next(S_DIST);
     return -std::log(1 - xi) / sigma_t;
 }
 static inline double free_flight_pdf(double sigma_t, double d) { return sigma_t * std::exp(sigma_t * d * -1.0); } /* :20 */
@@ -171,13 +174,13 @@ static inline double pdf_success(double sigma_t, double tmax) { return 1.0 - std
 static inline double pdf_failure(double sigma_t, double tmax) { return std::exp(-sigma_t * tmax); }                 /* :29 */
 static inline Vec sph(double theta, double phi) { return Vec(std::sin(theta) * std::cos(phi), std::sin(theta) * std::sin(phi), std::cos(theta)); }
 template <class Rng> static inline Vec phase_sample(Rng &rng) { /* isotropicPhaseSample :34-46 */
-    const double xi1 = rng.next();
-    const double xi2 = rng.next();
+    const double xi1 = rng.next(S_PHASE);
+    const double xi2 = rng.next(S_PHASE + 1);
     return unit(sph(std::acos(1 - 2 * xi1), 2 * kPi * xi2));
 }
 static inline double phase_value() { return 1 / (4 * kPi); } /* isotropicPhaseFunction, volumetricBasicFunctions.h:59 */
 template <class Rng> static inline double equiangular_sample(Rng &rng, double D, double a, double b) { /* :54-57 */
-    const double xi = rng.next();
+    const double xi = rng.next(S_DIST);
     return D * std::tan((1 - xi) * a + xi * b);
 }
 static inline double equiangular_pdf(double D, double a, double b, double t) { return D / std::fabs(b - a) / (t * t + D * D); } /* :60 */
@@ -199,23 +202,23 @@ template <class Rng> static inline EquiAngular equiangular_setup(Rng &rng, const
     e.D = std::sqrt(len * len - proj * proj);
     e.thetaA = std::atan2(0.0 - proj, e.D);
     e.thetaB = std::atan2(tMax - proj, e.D);
-    const double xi = rng.next();
+    const double xi = rng.next(S_DIST);
     e.t_local = e.D * std::tan((1 - xi) * e.thetaA + xi * e.thetaB);
     e.t_ray = e.t_local + proj;
     return e;
 }
 
 /* ---- samplingFunctions.h -------------------------------------------------------------------------- */
-template <class Rng> static inline Vec cosine_hemisphere(Rng &rng, const Vec &n) { /* :47-62 */
-    const double theta = std::acos(std::sqrt(1 - rng.next()));
-    const double phi = 2 * kPi * rng.next();
+template <class Rng> static inline Vec cosine_hemisphere(Rng &rng, const Vec &n, unsigned slot) { /* :47-62 */
+    const double theta = std::acos(std::sqrt(1 - rng.next(slot)));
+    const double phi = 2 * kPi * rng.next(slot + 1);
     const Vec l = sph(theta, phi);
     return unit(from_local(n, l.x, l.y, l.z));
 }
-template <class Rng> static inline Vec cone_sample(Rng &rng, const Vec &wc, double cos_max) { /* solidAngle, :65-82 */
-    const double e0 = rng.next();
+template <class Rng> static inline Vec cone_sample(Rng &rng, const Vec &wc, double cos_max, unsigned slot) { /* solidAngle, :65-82 */
+    const double e0 = rng.next(slot);
     const double theta = std::acos((1 - e0) + e0 * cos_max);
-    const double phi = 2 * kPi * rng.next();
+    const double phi = 2 * kPi * rng.next(slot + 1);
     const Vec l = sph(theta, phi);
     return unit(from_local(wc, l.x, l.y, l.z));
 }
@@ -263,9 +266,9 @@ static inline double smith_g(const Vec &n, const Vec &wi, const Vec &wo, const V
     const double g2 = smith_g1(n, wo, wh, alpha);
     return g1 * g2;
 }
-template <class Rng> static inline Vec facet_normal(Rng &rng, double alpha) { /* vectorFacet :71-84 */
-    const double theta = std::atan(std::sqrt(-alpha * alpha * std::log(1 - rng.next())));
-    const double phi = 2 * kPi * rng.next();
+template <class Rng> static inline Vec facet_normal(Rng &rng, double alpha, unsigned slot) { /* vectorFacet :71-84 */
+    const double theta = std::atan(std::sqrt(-alpha * alpha * std::log(1 - rng.next(slot))));
+    const double phi = 2 * kPi * rng.next(slot + 1);
     return unit(sph(theta, phi));
 }
 static inline double facet_pdf(const Vec &wo, const Vec &wh, double alpha, const Vec &n) { /* microFacetProb :86-92 */
@@ -293,7 +296,7 @@ static inline double power_heuristic(double f, double g) {
 /* muestreoSA -> solidAngle(L), samplingFunctions.h:238-247 and :163-206 */
 template <class Rng>
 static inline Vec light_sampled_direct(Rng &rng, Scene &sc, int light, const Vec &x, const Sphere &obj, const Vec &n, const Vec &wray,
-                                       Vec &wi_out, double &cos_max_out, double alpha) {
+                                       Vec &wi_out, double &cos_max_out, double alpha, unsigned slot) {
     const Sphere &src = sc.s[light];
     Vec cx = src.p - x;
     const double len = std::sqrt(dot(cx, cx));
@@ -301,7 +304,7 @@ static inline Vec light_sampled_direct(Rng &rng, Scene &sc, int light, const Vec
     const double cos_max = std::sqrt(1 - (src.r / len) * (src.r / len));
     cos_max_out = cos_max;
     /* solidAngle(L) */
-    const Vec wi = cone_sample(rng, cx, cos_max);
+    const Vec wi = cone_sample(rng, cx, cos_max, slot);
     wi_out = wi;
     Vec wil = to_local(n, wi);
     Vec wol = to_local(n, wray * -1);
@@ -322,7 +325,7 @@ static inline Vec light_sampled_direct(Rng &rng, Scene &sc, int light, const Vec
 /* uniform, samplingFunctions.h:250-261 */
 template <class Rng>
 static inline Vec bsdf_sampled_direct_lambert(Rng &rng, Scene &sc, const Vec &n, const Vec &x, const Vec &albedo, Vec &wi_out, int &source) {
-    Vec wi = cosine_hemisphere(rng, n);
+    Vec wi = cosine_hemisphere(rng, n, S_MIS);
     wi = unit(wi);
     int sid = -1;
     const Vec Le = first_hit_radiance(sc, x, wi, sid);
@@ -353,10 +356,11 @@ static inline Vec surface_direct_mis(Rng &rng, Scene &sc, const Sphere &obj, con
     Vec wo = wray * -1;
     double cos_max = 0; /* reference: uninitialised */
     const int count = (int)sc.s.size();
+    unsigned area_index = 0;
     for (int light = 0; light < count; ++light) {
         if (sc.s[light].r > 0 && sc.s[light].radiance.x > 0) {
             Vec wi_light;
-            const Vec f = light_sampled_direct(rng, sc, light, x, obj, n, wray, wi_light, cos_max, alpha) * transmittance(x, sc.s[light].p, sigma_t);
+            const Vec f = light_sampled_direct(rng, sc, light, x, obj, n, wray, wi_light, cos_max, alpha, S_AREA + 2 * area_index++) * transmittance(x, sc.s[light].p, sigma_t);
             const double fpdf = cone_pdf(cos_max);
             double gpdf;
             if (obj.material == 0) gpdf = cosine_pdf(dot(n, wi_light));
@@ -381,7 +385,7 @@ static inline Vec surface_direct_mis(Rng &rng, Scene &sc, const Sphere &obj, con
             wg = power_heuristic(gpdf, fpdf);
         } else wg = 0;
     } else {
-        const Vec wh = facet_normal(rng, alpha);
+        const Vec wh = facet_normal(rng, alpha, S_MIS);
         wo = unit(to_local(n, wo));
         int source = -1;
         g = bsdf_sampled_direct_facet(sc, x, wray, wh, n, obj, alpha, source);
@@ -420,13 +424,13 @@ static inline Vec bsdf_sample(Rng &rng, const Scene &sc, Vec &wi_out, const Vec 
     const Vec wo = wray * -1;
     Vec fs;
     if (obj.material == 0) {
-        const Vec wi = cosine_hemisphere(rng, n);
+        const Vec wi = cosine_hemisphere(rng, n, S_BSDF);
         fs = obj.c * (1 / kPi);
         pdf = cosine_pdf(dot(n, wi));
         wi_out = wi;
     } else {
         const double alpha = obj.alpha;
-        Vec wh = facet_normal(rng, alpha);
+        Vec wh = facet_normal(rng, alpha, S_BSDF);
         wh = from_local(n, wh.x, wh.y, wh.z);
         const Vec wi = wo * (-1) + wh * 2 * dot(wh, wo);
         fs = facet_brdf(obj.eta, obj.kappa, wi, wh, wo, alpha, n);
@@ -457,7 +461,7 @@ static inline Vec medium_direct(Rng &rng, Scene &sc, const Vec &xt, int source, 
     const double len = std::sqrt(dot(wc, wc));
     wc = wc * (1 / len);
     const double cos_max = std::sqrt(1 - src.r / len * (src.r / len));
-    const Vec wl = cone_sample(rng, wc, cos_max);
+    const Vec wl = cone_sample(rng, wc, cos_max, S_NEE);
     const double prob_wl = cone_pdf(cos_max);
     double dist;
     int hit_id = -1;
@@ -490,7 +494,7 @@ static inline Vec radiance(Rng &rng, Scene &sc, Ray ray, const Settings &cfg, Pa
     const int n_spheres = (int)sc.s.size();
     for (int depth = 0; cfg.max_depth <= 0 || depth < cfg.max_depth; ++depth) {
         rng.begin_bounce(depth);
-        if (rng.next() < q) break; /* :1282 / :1022 / :1353 */
+        if (rng.next(S_RR) < q) break; /* :1282 / :1022 / :1353 */
         if (stats) ++stats->events;
 
         double t;
@@ -508,7 +512,7 @@ static inline Vec radiance(Rng &rng, Scene &sc, Ray ray, const Settings &cfg, Pa
             if (sc.s[i].emits()) emitters[count++] = i;
         if (count == 0) break;
         const double prob_source = 1.0 / count;
-        const int source = emitters[static_cast<int>(rng.next() * count)];
+        const int source = emitters[static_cast<int>(rng.next(S_SRC) * count)];
 
         bool surface;
         double dist = 0, pdf_medium = 1;
@@ -520,7 +524,7 @@ static inline Vec radiance(Rng &rng, Scene &sc, Ray ray, const Settings &cfg, Pa
             const EquiAngular e = equiangular_setup(rng, sc, source, t, ray);
             pdf_medium = equiangular_pdf(e.D, e.thetaA, e.thetaB, e.t_local) * (1.0 - Tr); /* :1093 / :1411 */
             dist = e.t_ray;
-            const double xi = rng.next();
+            const double xi = rng.next(S_DECIDE);
             surface = (cfg.method == 1) ? (xi <= Tr) : (xi < Tr); /* :1096 / :1414 */
         }
 
@@ -585,27 +589,32 @@ struct ListRng {
     const double *u; size_t n, i = 0; bool overrun = false;
     ListRng(const double *u_, size_t n_) : u(u_), n(n_) {}
     void begin_bounce(int) {}
-    double next() { if (i >= n) { overrun = true; return 0.0; } /* 0 < q: the next roulette draw ends the path */ return u[i++]; }
+    double next(unsigned = 0) { if (i >= n) { overrun = true; return 0.0; } /* 0 < q: the next roulette draw ends the path */ return u[i++]; }
 };
 /* POSIX erand48, sequential (the reference's generator, Vector.h:38) */
 struct Erand48Rng {
     unsigned short s[3]; uint64_t draws = 0;
     Erand48Rng(unsigned a, unsigned b, unsigned c) { s[0] = (unsigned short)a; s[1] = (unsigned short)b; s[2] = (unsigned short)c; }
     void begin_bounce(int) {}
-    double next() { ++draws; return erand48(s); }
+    double next(unsigned = 0) { ++draws; return erand48(s); }
 };
-/* Philox4x32-10 keyed (pixel, sample, bounce): the product's stream convention (oracle/philox.h).
- * Bounce 0 starts at draw 0 = the two pixel-jitter draws, then the path's own draws. */
+/* Philox4x32-10 keyed (pixel, sample, bounce), one fixed slot per purpose: the product's stream convention (oracle/philox.h). */
 struct PhiloxRng {
-    uint32_t key[2], ctr[4], out[4]; unsigned idx = 0;
+    uint32_t key[2], ctr[4], out[4]; uint32_t loaded = 0xffffffffu;
     PhiloxRng(uint64_t seed, uint32_t pixel, uint32_t sample) {
         key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32);
         ctr[0] = pixel; ctr[1] = sample; ctr[2] = 0; ctr[3] = 0;
     }
-    void begin_bounce(int b) { if (b == 0) return; ctr[2] = (uint32_t)b; idx = 0; }
-    double next() {
-        if ((idx & 3u) == 0) { ctr[3] = idx >> 2; vpt_philox4x32_10(ctr, key, out); }
-        return vpt_u32_to_unit(out[idx++ & 3u]);
+    void begin_bounce(int b) { ctr[2] = (uint32_t)b; loaded = 0xffffffffu; }
+    double next(unsigned slot) {
+        if ((slot >> 2) != loaded) { ctr[3] = slot >> 2; vpt_philox4x32_10(ctr, key, out); loaded = slot >> 2; }
+        return vpt_u32_to_unit(out[slot & 3u]);
+    }
+    void jitter(double &a, double &b) { /* pseudo-bounce 0xffffffff, slots 0 and 1 */
+        const uint32_t c[4] = {ctr[0], ctr[1], 0xffffffffu, 0};
+        uint32_t o[4];
+        vpt_philox4x32_10(c, key, o);
+        a = vpt_u32_to_unit(o[0]); b = vpt_u32_to_unit(o[1]);
     }
 };
 

@@ -79,11 +79,11 @@ void l1_singleScattering(const double *scene, int n, unsigned quirks, const doub
 }
 
 /* ---- surface sampling ----------------------------------------------------------------------------------- */
-void l1_cosineHemispheric(const double *n, const double *u, int nu, double *o) { ListRng r(u, nu); put(o, cosine_hemisphere(r, V(n))); }
-void l1_solidAngleDir(const double *wc, double cmax, const double *u, int nu, double *o) { ListRng r(u, nu); put(o, cone_sample(r, V(wc), cmax)); }
+void l1_cosineHemispheric(const double *n, const double *u, int nu, double *o) { ListRng r(u, nu); put(o, cosine_hemisphere(r, V(n), 0)); }
+void l1_solidAngleDir(const double *wc, double cmax, const double *u, int nu, double *o) { ListRng r(u, nu); put(o, cone_sample(r, V(wc), cmax, 0)); }
 double l1_solidAngleProb(double cmax) { return cone_pdf(cmax); }
 double l1_hemiCosineProb(double c) { return cosine_pdf(c); }
-void l1_vectorFacet(double alpha, const double *u, int nu, double *o) { ListRng r(u, nu); put(o, facet_normal(r, alpha)); }
+void l1_vectorFacet(double alpha, const double *u, int nu, double *o) { ListRng r(u, nu); put(o, facet_normal(r, alpha, 0)); }
 double l1_NDF(double c, double a) { return beckmann(c, a); }
 void l1_fresnel(double c, const double *eta, const double *kappa, double *o) { put(o, fresnel_conductor(c, V(eta), V(kappa))); }
 double l1_G_smith(const double *n, const double *wi, const double *wo, const double *wh, double a) { return smith_g(V(n), V(wi), V(wo), V(wh), a); }
@@ -98,7 +98,7 @@ void l1_muestreoSA(const double *scene, int n, unsigned quirks, int light, const
     Scene sc = make_scene(scene, n, quirks);
     ListRng r(u, nu);
     Vec w;
-    put(L, light_sampled_direct(r, sc, light, V(x), sc.s[obj], V(nrm), V(wray), w, *cmax, alpha));
+    put(L, light_sampled_direct(r, sc, light, V(x), sc.s[obj], V(nrm), V(wray), w, *cmax, alpha, 0));
     put(wi, w);
 }
 void l1_MISv2(const double *scene, int n, unsigned quirks, int obj, const double *x, const double *nrm, const double *wray, double alpha, double st,
@@ -139,8 +139,8 @@ uint64_t l1_radiance_erand48(const double *scene, int n, unsigned quirks, int me
     put(out, radiance(r, sc, Ray{V(o), V(d)}, settings(method, sa, ss, cp, max_depth)));
     return r.draws;
 }
-/* `count` paths with given rays on the product's Philox streams (pixel[i], sample[i]); the two jitter draws of
- * bounce 0 are skipped, exactly as the device's vpt_test_radiance does. */
+/* `count` paths with given rays on the product's Philox streams (pixel[i], sample[i]); (the pixel-jitter slots are simply
+ * not used), exactly as the device's VPT_UNIT_RADIANCE does. */
 void l1_radiance_philox(const double *scene, int n, unsigned quirks, int method, double sa, double ss, double cp, int max_depth, uint64_t seed,
                         int count, const double *o, const double *d, const uint32_t *pixel, const uint32_t *sample, double *out, uint64_t *events) {
     const Settings cfg = settings(method, sa, ss, cp, max_depth);
@@ -150,7 +150,6 @@ void l1_radiance_philox(const double *scene, int n, unsigned quirks, int method,
 #pragma omp for schedule(static)
         for (int i = 0; i < count; ++i) {
             PhiloxRng r(seed, pixel[i], sample[i]);
-            r.next(); r.next();
             PathStats st;
             put(out + 3 * i, radiance(r, sc, Ray{V(o + 3 * i), V(d + 3 * i)}, cfg, &st));
             if (events) events[i] = st.events;
@@ -189,7 +188,8 @@ void l1_render(const double *scene, int n, unsigned quirks, int method, double s
                 double s[3] = {0, 0, 0}, q[3] = {0, 0, 0};
                 for (int k = sample_begin; k < sample_end; ++k) {
                     PhiloxRng r(seed, (uint32_t)pix, (uint32_t)k);
-                    const double xi1 = r.next(), xi2 = r.next();
+                    double xi1, xi2;
+                    r.jitter(xi1, xi2);
                     PathStats st;
                     const Vec v = radiance(r, sc, cam.ray(x, y, xi1, xi2), cfg, &st);
                     events += st.events;

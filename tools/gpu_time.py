@@ -1,0 +1,14 @@
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import minimal_volumetric_path_tracer_b200 as v
+spp = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+for kern, name in ((v.KERNEL_MEGA, "mega"), (v.KERNEL_MEGA_SCAN, "scan")):
+    for method in (0, 1, 2):
+        p = v.default_params(spp=spp, method=method, kernel=kern)
+        v.render(p)
+        best = 0
+        for _ in range(3):
+            hdr, st = v.render(p, stats=True)
+            best = max(best, st.paths / st.kernel_ms / 1e3)
+        print("%s method %d spp %d: %.1f Mpaths/s  (events/path %.3f scans/path %.3f) mean %s" % (name, method, spp, best, st.events / st.paths, st.scene_scans / st.paths, hdr.mean(axis=(0, 1))), flush=True)
