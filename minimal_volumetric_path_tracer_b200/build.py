@@ -23,7 +23,7 @@ UNITS = [
     ("vpt_kernels_f64.cu", ["-fmad=false"]),
     ("vpt_api.cpp", []),
 ]
-DEPS = ["vpt_internal.h", "vpt_philox.cuh", "vpt_f32.cuh", "vpt_f64.cuh", os.path.join("..", "..", "include", "vpt.h")]
+DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))) + [os.path.join("..", "..", "include", "vpt.h")]  # every header: a stale .so is a silent bug
 
 
 def _nvcc():

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include "vpt_f32.cuh"
 #include "vpt_mega_scan.cuh"
+#include "vpt_wavefront.cuh"
 
 namespace vpt {
 
@@ -144,6 +145,36 @@ __global__ void __launch_bounds__(kThreadsPerBlock) render_f32_scan_kernel(const
     atomicAdd(&counters->paths, (unsigned long long)(lp.sample_end - lp.sample_begin));
 }
 
+// ---- warp-local wavefront (vpt_wavefront.cuh) ----------------------------------------------------------------------------------
+template <int METHOD>
+__global__ void __launch_bounds__(kThreadsPerBlock) render_f32_wave_kernel(const __grid_constant__ SceneF sc, const __grid_constant__ LaunchParams lp,
+                                                                            const __grid_constant__ ConstsF cf, float *__restrict__ hdr, Counters *__restrict__ counters) {
+    __shared__ MatF mats[kMaxSpheres];
+    __shared__ WarpPool pools[kWarpsPerBlock];
+    for (int i = threadIdx.x; i < sc.n_spheres * (int)(sizeof(MatF) / 4); i += blockDim.x)
+        reinterpret_cast<uint32_t *>(mats)[i] = reinterpret_cast<const uint32_t *>(sc.mat)[i];
+    __syncthreads();
+    const long long tile = (long long)blockIdx.x * lp.tile_count + lp.tile_rank;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long pixel_base = tile * kTile + warp * 32;
+    const int n_valid = (int)min(32LL, (long long)lp.n_pixels - pixel_base);
+    if (n_valid <= 0) return;
+    const Consts k = make_consts(cf);
+    const CameraF cam = make_camera(cf);
+    WarpPool &P = pools[warp];
+    Wavefront<METHOD> wf(sc, mats, k, cam, P, lp.key0, lp.key1, (uint32_t)pixel_base, n_valid, lp.width, lp.height);
+    wf.run(lp.sample_begin, lp.sample_end);
+    __syncwarp();
+    if (lane < n_valid) {
+        float *out = hdr + (pixel_base + lane) * 3;
+        for (int c = 0; c < 3; ++c) out[c] = (float)((double)(long long)P.acc[lane][c] * kFixInv * lp.out_scale);
+    }
+    if (!counters) return;
+    atomicAdd(&counters->events, (unsigned long long)wf.events); atomicAdd(&counters->scans, (unsigned long long)wf.scans);
+    if (wf.nonfinite) atomicAdd(&counters->nonfinite, (unsigned long long)wf.nonfinite);
+    atomicAdd(&counters->paths, (unsigned long long)wf.paths);
+}
+
 int launch_render_f32(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks, int kernel) {
     cudaStream_t st = (cudaStream_t)stream;
     if (kernel == VPT_KERNEL_MEGA) {
@@ -151,6 +182,12 @@ int launch_render_f32(const SceneF &scene, const LaunchParams &lp, const ConstsF
         case 0: render_f32_kernel<0><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
         case 1: render_f32_kernel<1><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
         default: render_f32_kernel<2><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
+        }
+    } else if (kernel == VPT_KERNEL_WAVEFRONT) {
+        switch (lp.method) {
+        case 0: render_f32_wave_kernel<0><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
+        case 1: render_f32_wave_kernel<1><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
+        default: render_f32_wave_kernel<2><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
         }
     } else {
         switch (lp.method) {

@@ -229,16 +229,20 @@ def test_precision_quirk_contract(gpu):
 # ---- the two FP32 kernel variants compute the same thing -------------------------------------------------------------------
 @pytest.mark.parametrize("method", [0, 1, 2])
 def test_kernel_variants_agree(gpu, l1, method):
-    """MEGA (vertex per iteration) and MEGA_SCAN (scan-converged state machine): same streams, same decisions, sums differ by
+    """MEGA (vertex per iteration), MEGA_SCAN (scan-converged state machine) and WAVEFRONT (warp-local queues): same streams, same decisions, sums differ by
     fp32 re-association only; both against the oracle"""
     w, h, spp = 160, 120, 16
     p = gpu.default_params(width=w, height=h, spp=spp, method=method, seed=12, output=gpu.OUTPUT_SUM)
     a, sa = gpu.render(p.copy(kernel=gpu.KERNEL_MEGA), stats=True)
     b, sb = gpu.render(p.copy(kernel=gpu.KERNEL_MEGA_SCAN), stats=True)
-    assert abs(int(sa.events) - int(sb.events)) <= 3e-4 * sa.events and sa.scene_scans == pytest.approx(sb.scene_scans, rel=2e-3)
-    err = np.abs(a - b) / np.maximum(np.abs(a), 1e-3)
-    assert np.median(err) < 1e-6 and np.mean(err > 1e-3) < 0.01
+    c, sc_ = gpu.render(p.copy(kernel=gpu.KERNEL_WAVEFRONT), stats=True)
+    for other, so in ((b, sb), (c, sc_)):
+        assert abs(int(sa.events) - int(so.events)) <= 3e-4 * sa.events and sa.scene_scans == pytest.approx(so.scene_scans, rel=2e-3)
+        assert so.paths == w * h * spp
+        err = np.abs(a - other) / np.maximum(np.abs(a), 1e-3)
+        assert np.median(err) < 1e-6 and np.mean(err > 1e-3) < 0.01
+    assert np.array_equal(c, gpu.render(p.copy(kernel=gpu.KERNEL_WAVEFRONT)))   # fixed-point accumulation: order-independent, bit-reproducible
     ref, _, rst = l1.render(DEFAULT_SCENE, 0, method, SA, SS, w, h, 12, spp, want_sumsq=False)
-    for img in (a, b):
+    for img in (a, b, c):
         e = np.abs(img - ref) / np.maximum(np.abs(ref), 1e-3)
         assert np.median(e) < 2e-6 and np.mean(e > 1e-3) < 0.02

@@ -3,7 +3,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import minimal_volumetric_path_tracer_b200 as v
 spp = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-for kern, name in ((v.KERNEL_MEGA, "mega"), (v.KERNEL_MEGA_SCAN, "scan")):
+for kern, name in ((v.KERNEL_MEGA, "mega"), (v.KERNEL_MEGA_SCAN, "scan"), (v.KERNEL_WAVEFRONT, "wave")):
     for method in (0, 1, 2):
         p = v.default_params(spp=spp, method=method, kernel=kern)
         v.render(p)
