@@ -49,10 +49,12 @@ typedef struct {
 enum { VPT_METHOD_FREE_FLIGHT = 0, VPT_METHOD_EQUIANGULAR = 1, VPT_METHOD_MIS = 2 };
 enum { VPT_PRECISION_FP32 = 0, VPT_PRECISION_FP64_REF = 1 };
 enum { VPT_OUTPUT_SUM = 0, VPT_OUTPUT_MEAN = 1 };
-/* FP32 kernel variants (DESIGN.md "Kernels"): MEGA = one path vertex per loop iteration (scene scans inside divergent shading code);
- * MEGA_SCAN = scan-converged state machine, exactly one scene scan per loop iteration executed by all lanes (AUTO picks it: faster by
- * measurement, profiles/); WAVEFRONT = queue-based multi-kernel pipeline (not built: VPT_ERR_UNSUPPORTED). Same results to fp32 rounding. */
-enum { VPT_KERNEL_AUTO = 0, VPT_KERNEL_MEGA = 1, VPT_KERNEL_WAVEFRONT = 2, VPT_KERNEL_MEGA_SCAN = 3 };
+/* FP32 kernel variants (DESIGN.md "Kernels"), same results to fp32 rounding, AUTO = the fastest by measurement (profiles/):
+ * MEGA = one thread per pixel, one path vertex per loop iteration (scene scans inside divergent shading code);
+ * MEGA_SCAN = scan-converged state machine, exactly one scene scan per loop iteration executed by all lanes;
+ * WAVEFRONT = on-chip wavefront, one pool of path records and per-stage queues PER WARP in shared memory;
+ * WAVEFRONT_SM = on-chip wavefront, one persistent CTA per SM, one pool per SM, all warps run the same stage in lock step. */
+enum { VPT_KERNEL_AUTO = 0, VPT_KERNEL_MEGA = 1, VPT_KERNEL_WAVEFRONT = 2, VPT_KERNEL_MEGA_SCAN = 3, VPT_KERNEL_WAVEFRONT_SM = 4 };
 /* Two behaviours of the reference are decided by FP64 rounding (DESIGN.md "Parity hazards"):
  *  R0_FALLTHROUGH   the in-medium point-light connection is overwritten with 0 whenever the r == 0 sphere registers as
  *                   hit in the solid-angle block (volumetricBasicFunctions.h:310-337 / :251-278);

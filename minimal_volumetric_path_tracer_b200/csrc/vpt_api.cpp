@@ -75,8 +75,8 @@ int validate_params(const vpt_params *p, bool need_image) {
     if (!finite3(p->cam_o) || !finite3(p->cam_dir) || !(p->fov > 0) || dot(v3(p->cam_dir), v3(p->cam_dir)) == 0) return VPT_ERR_INVALID_ARGUMENT;
     if (p->quirks & ~(uint32_t)VPT_QUIRKS_REFERENCE) return VPT_ERR_INVALID_ARGUMENT;
     if (p->precision == VPT_PRECISION_FP32 && p->quirks != 0) return VPT_ERR_UNSUPPORTED; // rounding-decided behaviours exist in FP64 only
-    if (p->kernel != VPT_KERNEL_AUTO && p->kernel != VPT_KERNEL_MEGA && p->kernel != VPT_KERNEL_MEGA_SCAN && p->kernel != VPT_KERNEL_WAVEFRONT) return VPT_ERR_INVALID_ARGUMENT;
-    if (p->kernel == VPT_KERNEL_WAVEFRONT && p->precision != VPT_PRECISION_FP32) return VPT_ERR_UNSUPPORTED;
+    if (p->kernel < VPT_KERNEL_AUTO || p->kernel > VPT_KERNEL_WAVEFRONT_SM) return VPT_ERR_INVALID_ARGUMENT;
+    if ((p->kernel == VPT_KERNEL_WAVEFRONT || p->kernel == VPT_KERNEL_WAVEFRONT_SM) && p->precision != VPT_PRECISION_FP32) return VPT_ERR_UNSUPPORTED;
     return VPT_OK;
 }
 
@@ -214,7 +214,7 @@ int enqueue_render(const vpt_params *p, const vpt_sphere *spheres, int n_spheres
         build_scene_f32(spheres, n_spheres, sc);
         ConstsF cf;
         build_consts_f32(lp, sc.n_emitters, cf);
-        rc = launch_render_f32(sc, lp, cf, hdr_dev, counters_dev, stream, blocks, p->kernel == VPT_KERNEL_AUTO ? VPT_KERNEL_MEGA_SCAN : p->kernel);
+        rc = launch_render_f32(sc, lp, cf, hdr_dev, counters_dev, stream, blocks, p->kernel == VPT_KERNEL_AUTO ? VPT_KERNEL_WAVEFRONT : p->kernel);
     } else {
         SceneD sc;
         build_scene_f64(spheres, n_spheres, sc);

@@ -11,6 +11,7 @@
 #include "vpt_f32.cuh"
 #include "vpt_mega_scan.cuh"
 #include "vpt_wavefront.cuh"
+#include "vpt_smwave.cuh"
 
 namespace vpt {
 
@@ -175,6 +176,68 @@ __global__ void __launch_bounds__(kThreadsPerBlock) render_f32_wave_kernel(const
     atomicAdd(&counters->paths, (unsigned long long)wf.paths);
 }
 
+
+// ---- SM-wide wavefront (vpt_smwave.cuh) -----------------------------------------------------------------------------------------
+template <int METHOD>
+__global__ void __launch_bounds__(kSmThreads, 1) render_f32_smwave_kernel(const __grid_constant__ SceneF sc, const __grid_constant__ LaunchParams lp,
+                                                                           const __grid_constant__ ConstsF cf, float *__restrict__ hdr, Counters *__restrict__ counters,
+                                                                           int log_p, int n_owned_tiles, int n_items) {
+    SmShared &S = sm_shared();
+    const int tid = (int)threadIdx.x;
+    for (int i = tid; i < sc.n_spheres * (int)(sizeof(MatF) / 4); i += kSmThreads)
+        reinterpret_cast<uint32_t *>(S.mats)[i] = reinterpret_cast<const uint32_t *>(sc.mat)[i];
+    for (int i = tid; i < kSmPool; i += kSmThreads) { S.freelist[i] = (uint16_t)i; S.r1[i] = 0u; S.meta[i] = 0u; }
+    for (int i = tid; i < 2 * kSmMaxItemPixels * 3; i += kSmThreads) (&S.acc[0][0][0])[i] = 0ull;
+    if (tid == 0) {
+        int na = 0, nb = 0;
+        for (int pass = 0; pass < 2; ++pass) // general-form spheres (huge / re-anchored ones and anything with r >= 64) first
+            for (int g = 0; g < sc.n_geom; ++g) {
+                const GeomF &G = sc.geom[g];
+                const bool general = G.big || G.r2 >= kSimpleRootMaxR2;
+                if (general != (pass == 0)) continue;
+                if (general) { S.ga[2 * na] = make_float4(G.qx, G.qy, G.qz, G.c0); S.ga[2 * na + 1] = make_float4(G.mx, G.my, G.mz, 0.0f); S.gid[na++] = G.id; }
+                else { S.gb[nb] = make_float4(G.qx, G.qy, G.qz, G.r2); S.gid[na + nb++] = G.id; }
+            }
+        S.n_ga = na; S.n_gb = nb;
+        for (int q = 0; q < SQ_COUNT; ++q) { S.q_head[q] = 0u; S.q_tail[q] = 0u; S.q_end[q] = 0u; }
+        S.free_head = 0u; S.free_tail = (unsigned)kSmPool;
+        for (int b = 0; b < 2; ++b) {
+            const int item = (int)blockIdx.x + b * (int)gridDim.x;
+            S.t_item[b] = item < n_items ? item : -1; S.t_cursor[b] = 0u; S.t_done[b] = 0u;
+        }
+        S.next_item = (int)blockIdx.x + 2 * (int)gridDim.x;
+    }
+    __syncthreads();
+    SmWave<METHOD> wf(S, sc, cf, lp, log_p, n_owned_tiles);
+    wf.run(hdr, n_items);
+    if (!counters) return;
+    unsigned long long ev = wf.events, scn = wf.scans, nf = wf.nonfinite, np = wf.paths;
+    for (int off = 16; off > 0; off >>= 1) {
+        ev += __shfl_down_sync(0xffffffffu, ev, off); scn += __shfl_down_sync(0xffffffffu, scn, off);
+        nf += __shfl_down_sync(0xffffffffu, nf, off); np += __shfl_down_sync(0xffffffffu, np, off);
+    }
+    if ((tid & 31) == 0) {
+        atomicAdd(&counters->events, ev); atomicAdd(&counters->scans, scn); atomicAdd(&counters->paths, np);
+        if (nf) atomicAdd(&counters->nonfinite, nf);
+    }
+}
+
+template <int METHOD>
+static int launch_smwave(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, cudaStream_t st, int n_owned_tiles) {
+    int dev = 0, n_sm = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
+    if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(render_f32_smwave_kernel<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmShared))) != cudaSuccess) return (int)e;
+    // work item = 256 pixels when that still leaves every SM at least 8 items, else one 128-pixel tile
+    const int log_p = (n_owned_tiles / 2 >= 8 * n_sm) ? 8 : 7;
+    const int tiles_per_item = 1 << (log_p - 7);
+    const int n_items = (n_owned_tiles + tiles_per_item - 1) / tiles_per_item;
+    const int grid = n_items < n_sm ? n_items : n_sm;
+    render_f32_smwave_kernel<METHOD><<<grid, kSmThreads, sizeof(SmShared), st>>>(scene, lp, cf, hdr_dev, counters_dev, log_p, n_owned_tiles, n_items);
+    return (int)cudaGetLastError();
+}
+
 int launch_render_f32(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks, int kernel) {
     cudaStream_t st = (cudaStream_t)stream;
     if (kernel == VPT_KERNEL_MEGA) {
@@ -182,6 +245,12 @@ int launch_render_f32(const SceneF &scene, const LaunchParams &lp, const ConstsF
         case 0: render_f32_kernel<0><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
         case 1: render_f32_kernel<1><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
         default: render_f32_kernel<2><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
+        }
+    } else if (kernel == VPT_KERNEL_WAVEFRONT_SM) {
+        switch (lp.method) {
+        case 0: return launch_smwave<0>(scene, lp, cf, hdr_dev, counters_dev, st, n_blocks);
+        case 1: return launch_smwave<1>(scene, lp, cf, hdr_dev, counters_dev, st, n_blocks);
+        default: return launch_smwave<2>(scene, lp, cf, hdr_dev, counters_dev, st, n_blocks);
         }
     } else if (kernel == VPT_KERNEL_WAVEFRONT) {
         switch (lp.method) {
