@@ -268,7 +268,7 @@ def main():
     per_gpu_paths = W * H * SPP
     achieved = per_gpu_paths / (kernel_ms * 1e-3) * FLOP_PER_PATH / 1e12
     roofline = {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": None,
-                "kernel": "render_f32_wave_kernel<%d>" % cfg["method"] if args.precision == "fp32" else "render_f64_kernel", "kernel_ms_per_launch": kernel_ms,
+                "kernel": "render_f32_smwave_kernel<%d>" % cfg["method"] if args.precision == "fp32" else "render_f64_kernel", "kernel_ms_per_launch": kernel_ms,
                 "flop_per_path": FLOP_PER_PATH, "peak_source": "measured live: vpt_measure_fp32_peak FFMA chains (MEASURED_PEAKS.json has no FP32 entry; nominal 74.4)",
                 "hbm_note": "algorithmic HBM traffic is the %d-byte HDR store per launch; see profiles/ for dram bytes" % d2h}
     extras = {}

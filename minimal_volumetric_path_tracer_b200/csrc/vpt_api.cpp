@@ -19,6 +19,7 @@ using namespace vpt;
 namespace {
 
 thread_local std::string g_last_cuda_error;
+thread_local unsigned long long g_last_debug[kDebugCounters];
 
 int cuda_fail(cudaError_t e, const char *what) {
     g_last_cuda_error = std::string(what) + ": " + cudaGetErrorString(e);
@@ -214,7 +215,7 @@ int enqueue_render(const vpt_params *p, const vpt_sphere *spheres, int n_spheres
         build_scene_f32(spheres, n_spheres, sc);
         ConstsF cf;
         build_consts_f32(lp, sc.n_emitters, cf);
-        rc = launch_render_f32(sc, lp, cf, hdr_dev, counters_dev, stream, blocks, p->kernel == VPT_KERNEL_AUTO ? VPT_KERNEL_WAVEFRONT : p->kernel);
+        rc = launch_render_f32(sc, lp, cf, hdr_dev, counters_dev, stream, blocks, p->kernel == VPT_KERNEL_AUTO ? VPT_KERNEL_WAVEFRONT_SM : p->kernel);
     } else {
         SceneD sc;
         build_scene_f64(spheres, n_spheres, sc);
@@ -315,6 +316,7 @@ int vpt_render_device(const vpt_params *p, const vpt_sphere *spheres, int32_t n_
         stats->kernel_ms = ms;
         stats->events = c.events; stats->scene_scans = c.scans; stats->nonfinite = c.nonfinite;
         stats->paths = c.paths;
+        std::memcpy(g_last_debug, c.dbg, sizeof(g_last_debug));
     } while (0);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
@@ -568,6 +570,13 @@ const char *vpt_strerror(int status) {
     }
 }
 const char *vpt_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
+/* development aid, not part of include/vpt.h: the in-kernel cycle counters of the last render with stats on this thread
+ * (all zero unless the library was built with -DVPT_SMWAVE_PROFILE) */
+int vpt_debug_counters(unsigned long long *out, int32_t cap) {
+    const int n = cap < kDebugCounters ? cap : kDebugCounters;
+    for (int i = 0; i < n; ++i) out[i] = g_last_debug[i];
+    return n;
+}
 const char *vpt_version(void) { return "vpt_b200 0.1 (sm_100a)"; }
 
 } // extern "C"

@@ -85,8 +85,10 @@ struct ConstsF {
     float cam_o[3], cam_d[3], cam_cx[3], cam_cy[3], inv_w, inv_h;
 };
 
+constexpr int kDebugCounters = 32;
 struct Counters { // device-side, accumulated with atomics at thread exit
     unsigned long long events, scans, nonfinite, paths;
+    unsigned long long dbg[kDebugCounters]; // only written by builds with -DVPT_SMWAVE_PROFILE (tools/smwave_timing.py); see vpt_smwave.cuh
 };
 
 // entry points implemented in the .cu files, called from vpt_api.cpp

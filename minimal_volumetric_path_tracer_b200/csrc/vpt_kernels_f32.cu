@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kSmThreads, 1) render_f32_smwave_kernel(const 
                 else { S.gb[nb] = make_float4(G.qx, G.qy, G.qz, G.r2); S.gid[na + nb++] = G.id; }
             }
         S.n_ga = na; S.n_gb = nb;
-        for (int q = 0; q < SQ_COUNT; ++q) { S.q_head[q] = 0u; S.q_tail[q] = 0u; S.q_end[q] = 0u; }
+        for (int q = 0; q < SQ_COUNT; ++q) { S.q_tail[q] = 0u; S.q_end[q] = 0u; }
         S.free_head = 0u; S.free_tail = (unsigned)kSmPool;
         for (int b = 0; b < 2; ++b) {
             const int item = (int)blockIdx.x + b * (int)gridDim.x;
@@ -219,6 +219,9 @@ __global__ void __launch_bounds__(kSmThreads, 1) render_f32_smwave_kernel(const 
     if ((tid & 31) == 0) {
         atomicAdd(&counters->events, ev); atomicAdd(&counters->scans, scn); atomicAdd(&counters->paths, np);
         if (nf) atomicAdd(&counters->nonfinite, nf);
+#ifdef VPT_SMWAVE_PROFILE
+        for (int i = 0; i < 24; ++i) if (wf.prof[i]) atomicAdd(&counters->dbg[i], wf.prof[i]);
+#endif
     }
 }
 

@@ -32,7 +32,10 @@ constexpr float kSmFixScale = 1073741824.0f; // 2^30
 constexpr double kSmFixInv = 1.0 / 1073741824.0;
 constexpr float kSimpleRootMaxR2 = 64.0f * 64.0f;
 
-enum : int { SQ_PRIMARY = 0, SQ_MED_POINT, SQ_MED_AREA, SQ_SURF_P, SQ_SURF_L, SQ_SURF_F, SQ_COUNT, ST_GEN = SQ_COUNT, ST_FLUSH, ST_EXIT };
+enum : int { SQ_PRIMARY = 0, SQ_MED_POINT, SQ_MED_AREA, SQ_SURF_P, SQ_SURF_L, SQ_SURF_F, SQ_COUNT };
+// Claim order of a round's batches (one nibble per rank, SQ_COUNT = generation), longest stage first so that a round ends evenly:
+// SURF_F, SURF_L, PRIMARY, MED_AREA, MED_POINT, SURF_P, generation
+constexpr unsigned kRankStage = 0x6312045u;
 
 struct SmShared {
     // ---- path records (SoA) ----
@@ -55,16 +58,34 @@ struct SmShared {
     int gid[2 * kMaxSpheres];   // scan order -> caller's sphere index (general ones first)
     int n_ga, n_gb;
     // ---- control ----
-    unsigned q_head[SQ_COUNT]; // claim counters: a warp takes entries [old, old + 32) with one atomicAdd
+    // this round's batch table by rank (kRankStage): batch k belongs to the last rank with rb_first[rank] <= k and covers entries
+    // [rb_begin + 32 j, min(rb_end, +32)), j = k - rb_first
+    __align__(16) unsigned rb_first[8]; // [7] = number of batches of the round
+    unsigned rb_begin[8], rb_end[8];
+    unsigned round_claim;      // next unclaimed batch of the round: one atomicAdd per batch
+    unsigned tail_budget, tail_used; // camera samples that warps out of batches may still generate in this round (tail fill)
     unsigned q_tail[SQ_COUNT]; // push counters
-    unsigned q_end[SQ_COUNT];  // this round's snapshot: entries below it may be claimed
+    unsigned q_end[SQ_COUNT];  // entries below it have been handed out
     unsigned free_head, free_tail; // the free-record ring: allocate at the head (only below this round's snapshot), release at the tail
-    unsigned gen_claim, gen_count, gen_begin; // this round's new camera samples: claim counter, how many, first sample index of the item
     int gen_slot, flush_slot, exit_flag;
+#ifdef VPT_SMWAVE_PROFILE
+    long long dbg_arrive[32];
+#endif
     unsigned t_cursor[2], t_done[2];
     int t_item[2]; // -1: slot idle
     int next_item;
 };
+
+// shared-memory atomic add issued by ONE lane (the callers aggregate over the warp themselves): plain ATOMS.ADD, without the
+// compiler's own warp-aggregation wrapper around atomicAdd
+__device__ __forceinline__ unsigned smem_add(unsigned *p, unsigned v) {
+    unsigned old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(p)), "r"(v));
+    return old;
+}
+__device__ __forceinline__ void smem_red(unsigned *p, unsigned v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v));
+}
 
 extern __shared__ __align__(16) unsigned char smwave_smem[]; // the CTA's one SmShared (dynamic shared memory)
 __device__ __forceinline__ SmShared &sm_shared() { return *reinterpret_cast<SmShared *>(smwave_smem); }
@@ -112,6 +133,18 @@ __device__ __forceinline__ bool scan_sm(const SmShared &S, F3 o, F3 d, float &t,
     return h.index >= 0;
 }
 
+// optional in-kernel timing (-DVPT_SMWAVE_PROFILE): per-warp cycle sums, added to Counters::dbg at the end
+//   dbg[0..7]  cycles inside batches of stage q (SQ_* order, 6 = generation, 7 = tail-fill generation)     dbg[8..15]  batches of stage q
+//   dbg[16] cycles waiting at barrier (A)   dbg[17] cycles from (A) to (B) (planning)   dbg[18] cycles in the claim loop outside batches
+//   dbg[19] total cycles of all warps   dbg[20] rounds (per CTA, summed)   dbg[21] cycles flushing
+#ifdef VPT_SMWAVE_PROFILE
+#define SMW_T(var) const long long var = clock64()
+#define SMW_ADD(i, v) prof[i] += (unsigned long long)(v)
+#else
+#define SMW_T(var)
+#define SMW_ADD(i, v)
+#endif
+
 template <int METHOD>
 struct SmWave {
     SmShared &S;
@@ -121,6 +154,9 @@ struct SmWave {
     const int tid, lane;
     const int log_p, item_pixels, n_owned_tiles;
     unsigned events = 0, scans = 0, nonfinite = 0, paths = 0;
+#ifdef VPT_SMWAVE_PROFILE
+    unsigned long long prof[24] = {};
+#endif
 
     __device__ SmWave(SmShared &S_, const SceneF &sc_, const ConstsF &k_, const LaunchParams &lp_, int log_p_, int n_owned_)
         : S(S_), sc(sc_), k(k_), lp(lp_), tid((int)threadIdx.x), lane((int)threadIdx.x & 31), log_p(log_p_), item_pixels(1 << log_p_), n_owned_tiles(n_owned_) {}
@@ -138,7 +174,7 @@ struct SmWave {
         const unsigned m = __ballot_sync(0xffffffffu, flag);
         if (m == 0u) return;
         unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&S.q_tail[q], (unsigned)__popc(m));
+        if (lane == 0) base = smem_add(&S.q_tail[q], (unsigned)__popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
         if (flag) S.queue[q][(base + __popc(m & ((1u << lane) - 1u))) & (kSmPool - 1)] = (uint16_t)slot;
     }
@@ -146,7 +182,7 @@ struct SmWave {
         const unsigned m = __ballot_sync(0xffffffffu, flag);
         if (m == 0u) return -1;
         unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&S.free_head, (unsigned)__popc(m));
+        if (lane == 0) base = smem_add(&S.free_head, (unsigned)__popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
         return flag ? (int)S.freelist[(base + __popc(m & ((1u << lane) - 1u))) & (kSmPool - 1)] : -1;
     }
@@ -154,7 +190,7 @@ struct SmWave {
         const unsigned m = __ballot_sync(0xffffffffu, flag);
         if (m == 0u) return;
         unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&S.free_tail, (unsigned)__popc(m));
+        if (lane == 0) base = smem_add(&S.free_tail, (unsigned)__popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
         if (flag) S.freelist[(base + __popc(m & ((1u << lane) - 1u))) & (kSmPool - 1)] = (uint16_t)slot;
     }
@@ -162,16 +198,26 @@ struct SmWave {
     __device__ __forceinline__ void add_radiance(uint32_t meta, F3 L) {
         if (!isfinite(L.x + L.y + L.z)) { ++nonfinite; return; }
         unsigned long long *a = S.acc[(meta >> 9) & 1u][meta & 0x1ffu];
-        if (L.x != 0.0f) atomicAdd(a + 0, (unsigned long long)__float2ll_rn(L.x * kSmFixScale));
-        if (L.y != 0.0f) atomicAdd(a + 1, (unsigned long long)__float2ll_rn(L.y * kSmFixScale));
-        if (L.z != 0.0f) atomicAdd(a + 2, (unsigned long long)__float2ll_rn(L.z * kSmFixScale));
+        if (L.x != 0.0f) add_fixed(a + 0, __float2ll_rn(L.x * kSmFixScale));
+        if (L.y != 0.0f) add_fixed(a + 1, __float2ll_rn(L.y * kSmFixScale));
+        if (L.z != 0.0f) add_fixed(a + 2, __float2ll_rn(L.z * kSmFixScale));
+    }
+    // 64-bit two's-complement add from native 32-bit shared-memory atomics (a 64-bit atomicAdd on shared memory is a CAS loop):
+    // low word first, its carry goes into the high word; the sum modulo 2^64 does not depend on the order of the adds
+    static __device__ __forceinline__ void add_fixed(unsigned long long *acc, long long v) {
+        unsigned *w = reinterpret_cast<unsigned *>(acc);
+        const unsigned lo = (unsigned)v;
+        unsigned hi = (unsigned)((unsigned long long)v >> 32);
+        const unsigned old = smem_add(w, lo);
+        hi += (old + lo < old) ? 1u : 0u;
+        if (hi) smem_red(w + 1, hi);
     }
     __device__ __forceinline__ void count_done(bool ended, uint32_t meta) {
         const unsigned m0 = __ballot_sync(0xffffffffu, ended && ((meta >> 9) & 1u) == 0u);
         const unsigned m1 = __ballot_sync(0xffffffffu, ended && ((meta >> 9) & 1u) == 1u);
         if (lane == 0) {
-            if (m0) atomicAdd(&S.t_done[0], (unsigned)__popc(m0));
-            if (m1) atomicAdd(&S.t_done[1], (unsigned)__popc(m1));
+            if (m0) smem_red(&S.t_done[0], (unsigned)__popc(m0));
+            if (m1) smem_red(&S.t_done[1], (unsigned)__popc(m1));
         }
     }
     __device__ __forceinline__ uint32_t pixel_of(uint32_t meta) const {
@@ -231,7 +277,7 @@ struct SmWave {
         push(SQ_PRIMARY, alive, slot);
         // samples of pixels outside the image and paths killed by the first roulette are finished already
         const unsigned m = __ballot_sync(0xffffffffu, mine && !alive);
-        if (lane == 0 && m) atomicAdd(&S.t_done[b], (unsigned)__popc(m));
+        if (lane == 0 && m) smem_red(&S.t_done[b], (unsigned)__popc(m));
     }
 
     // ---- PRIMARY: scan of the path ray, light pick, distance sampling, surface-or-medium decision --------------------------------
@@ -474,78 +520,133 @@ struct SmWave {
         }
     }
 
-    // ---- one round: thread 0 snapshots the queues and plans the generation ---------------------------------------------------------
+    // ---- one round: warp 0 snapshots the queues (lane = claim rank) and plans the generation (lane 0) -------------------------------
     __device__ __forceinline__ void plan_round(unsigned item_total) {
         int flush = -1, gen = -1, active = 0;
-        for (int b = 0; b < 2; ++b) {
-            if (S.t_item[b] < 0) continue;
-            ++active;
-            if (S.t_cursor[b] == item_total) { if (S.t_done[b] == item_total && flush < 0) flush = b; }
-            else if (gen < 0 || S.t_item[b] < S.t_item[gen]) gen = b;
+        unsigned left = 0, n_free = 0, gen_begin = 0;
+        if (lane == 0) {
+            for (int b = 0; b < 2; ++b) {
+                if (S.t_item[b] < 0) continue;
+                ++active;
+                if (S.t_cursor[b] >= item_total) { S.t_cursor[b] = item_total; if (S.t_done[b] == item_total && flush < 0) flush = b; } // (tail fill may overshoot)
+                else if (gen < 0 || S.t_item[b] < S.t_item[gen]) gen = b;
+            }
+            if (gen >= 0) { gen_begin = S.t_cursor[gen]; left = item_total - gen_begin; n_free = S.free_tail - S.free_head; }
         }
-        S.flush_slot = flush;
-        unsigned n_gen = 0;
-        if (gen >= 0) {
-            n_gen = min(S.free_tail - S.free_head, item_total - S.t_cursor[gen]);
-            if (n_gen < item_total - S.t_cursor[gen]) n_gen &= ~31u; // full warps only, except for the last samples of an item
-            S.gen_begin = S.t_cursor[gen];
-            S.t_cursor[gen] += n_gen;
-        }
-        S.gen_slot = gen; S.gen_count = n_gen; S.gen_claim = 0u;
+        left = __shfl_sync(0xffffffffu, left, 0);
+        n_free = __shfl_sync(0xffffffffu, n_free, 0);
+        gen_begin = __shfl_sync(0xffffffffu, gen_begin, 0);
         // while new samples keep coming only full 32-record batches are handed out (the remainder waits for the next round);
         // once generation has stopped (an item drains) everything goes
-        unsigned work = n_gen;
-        for (int q = 0; q < SQ_COUNT; ++q) {
-            const unsigned head = S.q_end[q]; // everything below the previous snapshot was consumed
-            unsigned count = S.q_tail[q] - head;
-            if (n_gen != 0u) count &= ~31u;
-            S.q_head[q] = head; S.q_end[q] = head + count;
-            work += count;
+        unsigned begin = 0, end = 0;
+        if (lane < SQ_COUNT) {
+            const int q = (kRankStage >> (4 * lane)) & 0xf;
+            begin = S.q_end[q];
+            unsigned count = S.q_tail[q] - begin;
+            if (left != 0u) count &= ~31u;
+            end = begin + count;
+            S.q_end[q] = end;
         }
-        S.exit_flag = (work == 0u && flush < 0 && active == 0) ? 1 : 0;
-    }
-
-    // claim the next 32 entries of queue q below this round's snapshot; returns the number of entries (0: none left)
-    __device__ __forceinline__ int claim(int q, unsigned end, unsigned &start) {
-        if ((int)(end - *(volatile unsigned *)&S.q_head[q]) <= 0) return 0;
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&S.q_head[q], 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        start = base;
-        const int left = (int)(end - base);
-        return left <= 0 ? 0 : min(left, 32);
+        unsigned queued = end - begin;
+#pragma unroll
+        for (int off = 1; off < 8; off <<= 1) queued += __shfl_xor_sync(0xffffffffu, queued, off);
+        // generation: normally left to the tail fill -- warps that find the round's batches all claimed generate camera samples instead
+        // of idling at the barrier -- and planned as batches of the round only when the queues cannot keep every warp busy
+        unsigned n_gen = 0;
+        if (queued < (unsigned)kSmThreads) {
+            n_gen = min(n_free, left);
+            if (n_gen < left) n_gen &= ~31u; // full warps only, except for the last samples of an item
+        }
+        if (lane == SQ_COUNT) { begin = gen_begin; end = gen_begin + n_gen; }
+        const unsigned nb = (end - begin + 31u) >> 5;
+        unsigned incl = nb;
+#pragma unroll
+        for (int off = 1; off < 8; off <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
+        if (lane < 8) { S.rb_first[lane] = incl - nb; S.rb_begin[lane] = begin; S.rb_end[lane] = end; }
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 7);
+        if (lane == 0) {
+            if (gen >= 0) S.t_cursor[gen] = gen_begin + n_gen;
+            S.flush_slot = flush; S.gen_slot = gen; S.round_claim = 0u; S.tail_budget = n_free - n_gen; S.tail_used = 0u;
+            S.exit_flag = (total == 0u && flush < 0 && gen < 0) ? 1 : 0; // nothing queued, nothing to generate, nothing to write out
+        }
     }
 
     __device__ __forceinline__ void run(float *__restrict__ hdr, int n_items) {
         const unsigned item_total = (unsigned)item_pixels * (unsigned)(lp.sample_end - lp.sample_begin);
+        SMW_T(t_start);
         for (;;) {
+            SMW_T(t0);
+#ifdef VPT_SMWAVE_PROFILE
+            if (lane == 0) S.dbg_arrive[tid >> 5] = t0;
+#endif
             __syncthreads(); // (A) the previous round's pushes / releases / counters are visible
-            if (tid == 0) plan_round(item_total);
+            SMW_T(t1);
+            if (tid < 32) plan_round(item_total);
             __syncthreads(); // (B) the plan is visible
+            SMW_T(t2);
+#ifdef VPT_SMWAVE_PROFILE
+            if (tid == 0) { // arrival spread at (A): last arrival minus mean arrival (x warps = idle warp-cycles), and last arrival -> (B) passed
+                long long last = 0, sum = 0;
+                for (int w = 0; w < kSmThreads / 32; ++w) { const long long a = S.dbg_arrive[w]; last = a > last ? a : last; sum += a; }
+                prof[23] += (unsigned long long)(last * (kSmThreads / 32) - sum);
+                prof[22] += (unsigned long long)((t2 - last) * (kSmThreads / 32));
+            }
+#endif
+            SMW_ADD(16, t1 - t0); SMW_ADD(17, t2 - t1); SMW_ADD(20, tid == 0);
             if (S.exit_flag) break;
             if (S.flush_slot >= 0) flush_item(S.flush_slot, hdr, n_items); // its records are all finished; the round below only touches the other item
-            unsigned end[SQ_COUNT];
-#pragma unroll
-            for (int q = 0; q < SQ_COUNT; ++q) end[q] = S.q_end[q];
-            const unsigned gen_count = S.gen_count, gen_begin = S.gen_begin;
+            SMW_T(t3);
+            SMW_ADD(21, t3 - t2);
+#ifdef VPT_SMWAVE_PROFILE
+            long long in_batches = 0;
+#define SMW_BATCH(q, call) { const long long b0 = clock64(); call; const long long b1 = clock64(); prof[q] += b1 - b0; prof[8 + q] += 1; in_batches += b1 - b0; }
+#else
+#define SMW_BATCH(q, call) { call; }
+#endif
+            const unsigned total = S.rb_first[7];
             const int gen_slot = S.gen_slot;
-            for (;;) { // claim batches, longest stage first, until the snapshot is used up
-                unsigned start; int n;
-                if ((n = claim(SQ_SURF_F, end[SQ_SURF_F], start)) > 0) { stage_surf<true>(lane < n ? (int)S.queue[SQ_SURF_F][(start + lane) & (kSmPool - 1)] : -1); continue; }
-                if ((n = claim(SQ_SURF_L, end[SQ_SURF_L], start)) > 0) { stage_surf<false>(lane < n ? (int)S.queue[SQ_SURF_L][(start + lane) & (kSmPool - 1)] : -1); continue; }
-                if ((n = claim(SQ_PRIMARY, end[SQ_PRIMARY], start)) > 0) { stage_primary(lane < n ? (int)S.queue[SQ_PRIMARY][(start + lane) & (kSmPool - 1)] : -1); continue; }
-                if ((n = claim(SQ_MED_AREA, end[SQ_MED_AREA], start)) > 0) { stage_med<false>(lane < n ? (int)S.queue[SQ_MED_AREA][(start + lane) & (kSmPool - 1)] : -1); continue; }
-                if ((n = claim(SQ_MED_POINT, end[SQ_MED_POINT], start)) > 0) { stage_med<true>(lane < n ? (int)S.queue[SQ_MED_POINT][(start + lane) & (kSmPool - 1)] : -1); continue; }
-                if ((n = claim(SQ_SURF_P, end[SQ_SURF_P], start)) > 0) { stage_surf_p(lane < n ? (int)S.queue[SQ_SURF_P][(start + lane) & (kSmPool - 1)] : -1); continue; }
-                if (*(volatile unsigned *)&S.gen_claim < gen_count) {
-                    unsigned base = 0;
-                    if (lane == 0) base = atomicAdd(&S.gen_claim, 32u);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (base < gen_count) { stage_gen(gen_slot, gen_begin + base, (int)min(32u, gen_count - base)); continue; }
+            unsigned raw = 0;
+            if (lane == 0) raw = smem_add(&S.round_claim, 1u);
+            unsigned kb = __shfl_sync(0xffffffffu, raw, 0);
+            while (kb < total) {
+                const uint4 f0 = *reinterpret_cast<const uint4 *>(&S.rb_first[0]), f1 = *reinterpret_cast<const uint4 *>(&S.rb_first[4]);
+                const int rank = (kb >= f0.y) + (kb >= f0.z) + (kb >= f0.w) + (kb >= f1.x) + (kb >= f1.y) + (kb >= f1.z);
+                const unsigned start = S.rb_begin[rank] + ((kb - S.rb_first[rank]) << 5);
+                const int n = (int)min(32u, S.rb_end[rank] - start);
+                const unsigned e = (start + (unsigned)lane) & (kSmPool - 1);
+                switch (rank) {
+                case 0: SMW_BATCH(SQ_SURF_F, stage_surf<true>(lane < n ? (int)S.queue[SQ_SURF_F][e] : -1)); break;
+                case 1: SMW_BATCH(SQ_SURF_L, stage_surf<false>(lane < n ? (int)S.queue[SQ_SURF_L][e] : -1)); break;
+                case 2: SMW_BATCH(SQ_PRIMARY, stage_primary(lane < n ? (int)S.queue[SQ_PRIMARY][e] : -1)); break;
+                case 3: SMW_BATCH(SQ_MED_AREA, stage_med<false>(lane < n ? (int)S.queue[SQ_MED_AREA][e] : -1)); break;
+                case 4: SMW_BATCH(SQ_MED_POINT, stage_med<true>(lane < n ? (int)S.queue[SQ_MED_POINT][e] : -1)); break;
+                case 5: SMW_BATCH(SQ_SURF_P, stage_surf_p(lane < n ? (int)S.queue[SQ_SURF_P][e] : -1)); break;
+                default: SMW_BATCH(6, stage_gen(gen_slot, start, n)); break;
                 }
-                break;
+                // (claiming the next batch before running this one hides the atomic's latency but commits warps too early: measured slower)
+                if (lane == 0) raw = smem_add(&S.round_claim, 1u);
+                kb = __shfl_sync(0xffffffffu, raw, 0);
             }
+            // tail fill: the round's batches are all claimed; instead of idling at the barrier generate camera samples from the budget
+            // the plan left over (one free record per sample is guaranteed), they are consumed in the next round
+            if (gen_slot >= 0) {
+                const unsigned budget = S.tail_budget;
+                for (;;) {
+                    unsigned base = item_total;
+                    if (lane == 0 && *(volatile unsigned *)&S.tail_used + 32u <= budget && smem_add(&S.tail_used, 32u) + 32u <= budget)
+                        base = smem_add(&S.t_cursor[gen_slot], 32u);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (base >= item_total) break;
+                    SMW_BATCH(7, stage_gen(gen_slot, base, (int)min(32u, item_total - base)));
+                }
+            }
+#ifdef VPT_SMWAVE_PROFILE
+            prof[18] += clock64() - t3 - in_batches;
+#endif
         }
+#ifdef VPT_SMWAVE_PROFILE
+        prof[19] += clock64() - t_start;
+#endif
     }
 };
 
