@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock) render_f32_wave_kernel(const
 template <int METHOD>
 __global__ void __launch_bounds__(kSmThreads, 1) render_f32_smwave_kernel(const __grid_constant__ SceneF sc, const __grid_constant__ LaunchParams lp,
                                                                            const __grid_constant__ ConstsF cf, float *__restrict__ hdr, Counters *__restrict__ counters,
-                                                                           int log_p, int n_owned_tiles, int n_items) {
+                                                                           int log_p, int n_owned_tiles, int n_items, int zero) {
     SmShared &S = sm_shared();
     const int tid = (int)threadIdx.x;
     for (int i = tid; i < sc.n_spheres * (int)(sizeof(MatF) / 4); i += kSmThreads)
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kSmThreads, 1) render_f32_smwave_kernel(const 
         S.next_item = (int)blockIdx.x + 2 * (int)gridDim.x;
     }
     __syncthreads();
-    SmWave<METHOD> wf(S, sc, cf, lp, log_p, n_owned_tiles);
+    SmWave<METHOD> wf(S, sc, cf, lp, log_p, n_owned_tiles, zero);
     wf.run(hdr, n_items);
     if (!counters) return;
     unsigned long long ev = wf.events, scn = wf.scans, nf = wf.nonfinite, np = wf.paths;
@@ -237,7 +237,7 @@ static int launch_smwave(const SceneF &scene, const LaunchParams &lp, const Cons
     const int tiles_per_item = 1 << (log_p - 7);
     const int n_items = (n_owned_tiles + tiles_per_item - 1) / tiles_per_item;
     const int grid = n_items < n_sm ? n_items : n_sm;
-    render_f32_smwave_kernel<METHOD><<<grid, kSmThreads, sizeof(SmShared), st>>>(scene, lp, cf, hdr_dev, counters_dev, log_p, n_owned_tiles, n_items);
+    render_f32_smwave_kernel<METHOD><<<grid, kSmThreads, sizeof(SmShared), st>>>(scene, lp, cf, hdr_dev, counters_dev, log_p, n_owned_tiles, n_items, 0);
     return (int)cudaGetLastError();
 }
 

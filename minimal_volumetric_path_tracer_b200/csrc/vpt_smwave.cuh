@@ -78,13 +78,16 @@ struct SmShared {
 
 // shared-memory atomic add issued by ONE lane (the callers aggregate over the warp themselves): plain ATOMS.ADD, without the
 // compiler's own warp-aggregation wrapper around atomicAdd
-__device__ __forceinline__ unsigned smem_add(unsigned *p, unsigned v) {
+// `lane_zero` = laneid * (a kernel argument that is always 0): ptxas wraps an atomic on a provably warp-uniform address in its own
+// leader election (VOTEU / FLO / POPC / S2R / SHFL, ~13 instructions per site, 7 % of all executed instructions in the first
+// profile); the callers have already elected lane 0, so the address is made formally lane dependent.
+__device__ __forceinline__ unsigned smem_add(unsigned *p, unsigned v, unsigned lane_zero = 0u) {
     unsigned old;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(p)), "r"(v));
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(p) + lane_zero), "r"(v));
     return old;
 }
-__device__ __forceinline__ void smem_red(unsigned *p, unsigned v) {
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v));
+__device__ __forceinline__ void smem_red(unsigned *p, unsigned v, unsigned lane_zero = 0u) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p) + lane_zero), "r"(v));
 }
 
 extern __shared__ __align__(16) unsigned char smwave_smem[]; // the CTA's one SmShared (dynamic shared memory)
@@ -152,14 +155,16 @@ struct SmWave {
     const ConstsF &k;
     const LaunchParams &lp;
     const int tid, lane;
+    const unsigned lz; // lane * 0, opaque to the compiler (see smem_add)
     const int log_p, item_pixels, n_owned_tiles;
     unsigned events = 0, scans = 0, nonfinite = 0, paths = 0;
 #ifdef VPT_SMWAVE_PROFILE
     unsigned long long prof[24] = {};
 #endif
 
-    __device__ SmWave(SmShared &S_, const SceneF &sc_, const ConstsF &k_, const LaunchParams &lp_, int log_p_, int n_owned_)
-        : S(S_), sc(sc_), k(k_), lp(lp_), tid((int)threadIdx.x), lane((int)threadIdx.x & 31), log_p(log_p_), item_pixels(1 << log_p_), n_owned_tiles(n_owned_) {}
+    __device__ SmWave(SmShared &S_, const SceneF &sc_, const ConstsF &k_, const LaunchParams &lp_, int log_p_, int n_owned_, int zero)
+        : S(S_), sc(sc_), k(k_), lp(lp_), tid((int)threadIdx.x), lane((int)threadIdx.x & 31), lz((threadIdx.x & 31u) * (unsigned)zero), log_p(log_p_),
+          item_pixels(1 << log_p_), n_owned_tiles(n_owned_) {}
 
     // ---- work items: item j = owned tiles [j * K, (j + 1) * K), K = item_pixels / kTile -----------------------------------------
     __device__ __forceinline__ long long item_pixel(int item, int pl) const {
@@ -174,7 +179,7 @@ struct SmWave {
         const unsigned m = __ballot_sync(0xffffffffu, flag);
         if (m == 0u) return;
         unsigned base = 0;
-        if (lane == 0) base = smem_add(&S.q_tail[q], (unsigned)__popc(m));
+        if (lane == 0) base = smem_add(&S.q_tail[q], (unsigned)__popc(m), lz);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (flag) S.queue[q][(base + __popc(m & ((1u << lane) - 1u))) & (kSmPool - 1)] = (uint16_t)slot;
     }
@@ -182,7 +187,7 @@ struct SmWave {
         const unsigned m = __ballot_sync(0xffffffffu, flag);
         if (m == 0u) return -1;
         unsigned base = 0;
-        if (lane == 0) base = smem_add(&S.free_head, (unsigned)__popc(m));
+        if (lane == 0) base = smem_add(&S.free_head, (unsigned)__popc(m), lz);
         base = __shfl_sync(0xffffffffu, base, 0);
         return flag ? (int)S.freelist[(base + __popc(m & ((1u << lane) - 1u))) & (kSmPool - 1)] : -1;
     }
@@ -190,7 +195,7 @@ struct SmWave {
         const unsigned m = __ballot_sync(0xffffffffu, flag);
         if (m == 0u) return;
         unsigned base = 0;
-        if (lane == 0) base = smem_add(&S.free_tail, (unsigned)__popc(m));
+        if (lane == 0) base = smem_add(&S.free_tail, (unsigned)__popc(m), lz);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (flag) S.freelist[(base + __popc(m & ((1u << lane) - 1u))) & (kSmPool - 1)] = (uint16_t)slot;
     }
@@ -216,8 +221,8 @@ struct SmWave {
         const unsigned m0 = __ballot_sync(0xffffffffu, ended && ((meta >> 9) & 1u) == 0u);
         const unsigned m1 = __ballot_sync(0xffffffffu, ended && ((meta >> 9) & 1u) == 1u);
         if (lane == 0) {
-            if (m0) smem_red(&S.t_done[0], (unsigned)__popc(m0));
-            if (m1) smem_red(&S.t_done[1], (unsigned)__popc(m1));
+            if (m0) smem_red(&S.t_done[0], (unsigned)__popc(m0), lz);
+            if (m1) smem_red(&S.t_done[1], (unsigned)__popc(m1), lz);
         }
     }
     __device__ __forceinline__ uint32_t pixel_of(uint32_t meta) const {
@@ -277,7 +282,7 @@ struct SmWave {
         push(SQ_PRIMARY, alive, slot);
         // samples of pixels outside the image and paths killed by the first roulette are finished already
         const unsigned m = __ballot_sync(0xffffffffu, mine && !alive);
-        if (lane == 0 && m) smem_red(&S.t_done[b], (unsigned)__popc(m));
+        if (lane == 0 && m) smem_red(&S.t_done[b], (unsigned)__popc(m), lz);
     }
 
     // ---- PRIMARY: scan of the path ray, light pick, distance sampling, surface-or-medium decision --------------------------------
@@ -606,7 +611,7 @@ struct SmWave {
             const unsigned total = S.rb_first[7];
             const int gen_slot = S.gen_slot;
             unsigned raw = 0;
-            if (lane == 0) raw = smem_add(&S.round_claim, 1u);
+            if (lane == 0) raw = smem_add(&S.round_claim, 1u, lz);
             unsigned kb = __shfl_sync(0xffffffffu, raw, 0);
             while (kb < total) {
                 const uint4 f0 = *reinterpret_cast<const uint4 *>(&S.rb_first[0]), f1 = *reinterpret_cast<const uint4 *>(&S.rb_first[4]);
@@ -624,7 +629,7 @@ struct SmWave {
                 default: SMW_BATCH(6, stage_gen(gen_slot, start, n)); break;
                 }
                 // (claiming the next batch before running this one hides the atomic's latency but commits warps too early: measured slower)
-                if (lane == 0) raw = smem_add(&S.round_claim, 1u);
+                if (lane == 0) raw = smem_add(&S.round_claim, 1u, lz);
                 kb = __shfl_sync(0xffffffffu, raw, 0);
             }
             // tail fill: the round's batches are all claimed; instead of idling at the barrier generate camera samples from the budget
@@ -633,8 +638,8 @@ struct SmWave {
                 const unsigned budget = S.tail_budget;
                 for (;;) {
                     unsigned base = item_total;
-                    if (lane == 0 && *(volatile unsigned *)&S.tail_used + 32u <= budget && smem_add(&S.tail_used, 32u) + 32u <= budget)
-                        base = smem_add(&S.t_cursor[gen_slot], 32u);
+                    if (lane == 0 && *(volatile unsigned *)&S.tail_used + 32u <= budget && smem_add(&S.tail_used, 32u, lz) + 32u <= budget)
+                        base = smem_add(&S.t_cursor[gen_slot], 32u, lz);
                     base = __shfl_sync(0xffffffffu, base, 0);
                     if (base >= item_total) break;
                     SMW_BATCH(7, stage_gen(gen_slot, base, (int)min(32u, item_total - base)));
