@@ -167,11 +167,12 @@ struct SmWave {
           item_pixels(1 << log_p_), n_owned_tiles(n_owned_) {}
 
     // ---- work items: item j = owned tiles [j * K, (j + 1) * K), K = item_pixels / kTile -----------------------------------------
-    __device__ __forceinline__ long long item_pixel(int item, int pl) const {
-        const long long owned = ((long long)item << (log_p - 7)) + (pl >> 7);
-        if (owned >= n_owned_tiles) return -1;
-        const long long pixel = (owned * lp.tile_count + lp.tile_rank) * kTile + (pl & (kTile - 1));
-        return pixel < lp.n_pixels ? pixel : -1;
+    // (32-bit arithmetic: n_pixels is an int32, so tile and pixel indices fit; -1 = outside the image / not this rank's tile)
+    __device__ __forceinline__ int item_pixel(int item, int pl) const {
+        const unsigned owned = ((unsigned)item << (log_p - 7)) + ((unsigned)pl >> 7);
+        if (owned >= (unsigned)n_owned_tiles) return -1;
+        const unsigned pixel = (owned * (unsigned)lp.tile_count + (unsigned)lp.tile_rank) * (unsigned)kTile + ((unsigned)pl & (unsigned)(kTile - 1));
+        return pixel < (unsigned)lp.n_pixels ? (int)pixel : -1;
     }
 
     // ---- queue / pool primitives (warp-aggregated shared-memory atomics) ------------------------------------------------------------
@@ -255,7 +256,7 @@ struct SmWave {
         const unsigned g = g0 + (unsigned)lane;
         const int pl = (int)(g & (unsigned)(item_pixels - 1));
         const uint32_t sample = (uint32_t)lp.sample_begin + (g >> log_p);
-        const long long pixel = mine ? item_pixel(S.t_item[b], pl) : -1;
+        const int pixel = mine ? item_pixel(S.t_item[b], pl) : -1;
         bool alive = false;
         uint4 b0 = make_uint4(0, 0, 0, 0);
         if (pixel >= 0) {
@@ -266,7 +267,7 @@ struct SmWave {
         const int slot = alloc(alive);
         if (alive) {
             const uint4 j = philox_block((uint32_t)pixel, sample, kJitterBounce, 0, lp.key0, lp.key1);
-            const int row = (int)(pixel / lp.width), col = (int)(pixel - (long long)row * lp.width);
+            const int row = (int)((unsigned)pixel / (unsigned)lp.width), col = pixel - row * lp.width;
             const float fx = (float)col, fy = (float)(lp.height - 1 - row); // rt.cpp:773
             const float u = (fx + u32_to_unit_f32(j.x) - 0.5f) * k.inv_w - 0.5f, v = (fy + u32_to_unit_f32(j.y) - 0.5f) * k.inv_h - 0.5f;
             const F3 d = unit(mk(fmaf(k.cam_cx[0], u, fmaf(k.cam_cy[0], v, k.cam_d[0])), fmaf(k.cam_cx[1], u, fmaf(k.cam_cy[1], v, k.cam_d[1])),
@@ -311,11 +312,16 @@ struct SmWave {
                 const float proj = dot(dv, d);
                 const F3 perp = fma3(d, -proj, dv);
                 const float D = sqrtf(dot(perp, perp));
-                const float thA = atan2f(-proj, D), thB = atan2f(t - proj, D);
+                // theta_B - theta_A = atan2((b - a) D, D^2 + a b) with a = -proj, b = t - proj (both angles in (-pi/2, pi/2], b > a), and
+                // tan(theta_A + xi (theta_B - theta_A)) by the addition theorem with tan(theta_A) = a / D: one atan2f and one tanf of an
+                // angle in (0, pi) instead of two atan2f and a tanf
+                const float a = -proj, b = fminf(t, 1e18f) - proj; // (a miss has t = MAXFLOAT: keep the products finite, theta_B is pi/2 to 1e-15)
+                const float dth = atan2f((b - a) * D, fmaf(a, b, D * D));
                 const float xi = u32_to_unit_f32(S.r2[s]);
-                const float tl = D * tanf((1.0f - xi) * thA + xi * thB);
+                const float tau = tanf(xi * dth);
+                const float tl = D * fmaf(D, tau, a) / fmaf(-a, tau, D);
                 dist = tl + proj;
-                inv_pdf = fabsf(thB - thA) * (tl * tl + D * D) / (D * (1.0f - Tr));
+                inv_pdf = dth * (tl * tl + D * D) / (D * (1.0f - Tr));
                 const float xs = u32_to_unit_f32(S.r3[s]);
                 surface = (METHOD == 1) ? (xs <= Tr) : (xs < Tr);
             }
@@ -510,9 +516,9 @@ struct SmWave {
     __device__ __forceinline__ void flush_item(int b, float *__restrict__ hdr, int n_items) {
         const int item = S.t_item[b];
         for (int pl = tid; pl < item_pixels; pl += kSmThreads) {
-            const long long pixel = item_pixel(item, pl);
+            const int pixel = item_pixel(item, pl);
             if (pixel >= 0) {
-                float *out = hdr + pixel * 3;
+                float *out = hdr + (size_t)pixel * 3;
                 for (int c = 0; c < 3; ++c) out[c] = (float)((double)(long long)S.acc[b][pl][c] * kSmFixInv * lp.out_scale);
             }
             S.acc[b][pl][0] = 0ull; S.acc[b][pl][1] = 0ull; S.acc[b][pl][2] = 0ull;
