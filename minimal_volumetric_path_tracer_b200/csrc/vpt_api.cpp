@@ -339,18 +339,20 @@ int vpt_render(const vpt_params *p, const vpt_sphere *spheres, int32_t n_spheres
     const size_t bytes = (size_t)p->width * p->height * 3 * sizeof(float);
     float *dev = nullptr;
     cudaStream_t stream = nullptr;
-    CUDA_TRY(cudaMalloc(&dev, bytes));
-    cudaError_t ce = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
-    if (ce != cudaSuccess) { cudaFree(dev); return cuda_fail(ce, "cudaStreamCreate"); }
-    vpt_stats local;
-    rc = vpt_render_device(p, spheres, n_spheres, dev, stream, stats ? stats : &local);
+    CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    // stream-ordered allocation from the device's default memory pool: after the first call no driver allocation and no implicit
+    // device-wide synchronisation (cudaMalloc / cudaFree cost several milliseconds per frame)
+    cudaError_t ce = cudaMallocAsync((void **)&dev, bytes, stream);
+    if (ce != cudaSuccess) { cudaStreamDestroy(stream); return cuda_fail(ce, "cudaMallocAsync"); }
+    rc = vpt_render_device(p, spheres, n_spheres, dev, stream, stats); // with stats == NULL nothing synchronises before the copy below
     if (rc == VPT_OK) {
         ce = cudaMemcpyAsync(hdr_rgb, dev, bytes, cudaMemcpyDeviceToHost, stream);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(stream);
         if (ce != cudaSuccess) rc = cuda_fail(ce, "copy HDR to host");
     }
+    cudaFreeAsync(dev, stream);
+    ce = cudaStreamSynchronize(stream);
+    if (ce != cudaSuccess && rc == VPT_OK) rc = cuda_fail(ce, "vpt_render");
     cudaStreamDestroy(stream);
-    cudaFree(dev);
     if (rc == VPT_OK && stats) stats->total_ms = now_ms() - t0;
     return rc;
 }

@@ -64,17 +64,20 @@ struct SmShared {
     unsigned rb_begin[8], rb_end[8];
     unsigned round_claim;      // next unclaimed batch of the round: one atomicAdd per batch
     unsigned tail_budget, tail_used; // camera samples that warps out of batches may still generate in this round (tail fill)
-    unsigned q_tail[SQ_COUNT]; // push counters
-    unsigned q_end[SQ_COUNT];  // entries below it have been handed out
-    unsigned free_head, free_tail; // the free-record ring: allocate at the head (only below this round's snapshot), release at the tail
+    // the 20 words the round plan reads, contiguous: warp 0 fetches them with ONE load (lane i reads word i, see plan_round)
+    __align__(16) unsigned q_tail[SQ_COUNT]; // [0..5]   push counters
+    unsigned q_end[SQ_COUNT];                // [6..11]  entries below it have been handed out
+    unsigned free_head, free_tail;           // [12,13]  the free-record ring: allocate at the head (only below the round's snapshot), release at the tail
+    int t_item[2];                           // [14,15]  work item of the slot, -1: slot idle
+    unsigned t_cursor[2], t_done[2];         // [16..19] camera samples generated / paths finished
+    unsigned ctl_pad[12];
     int gen_slot, flush_slot, exit_flag;
 #ifdef VPT_SMWAVE_PROFILE
     long long dbg_arrive[32];
 #endif
-    unsigned t_cursor[2], t_done[2];
-    int t_item[2]; // -1: slot idle
     int next_item;
 };
+static_assert(offsetof(SmShared, t_done) - offsetof(SmShared, q_tail) == 18 * sizeof(unsigned), "plan_round reads the control words by index");
 
 // shared-memory atomic add issued by ONE lane (the callers aggregate over the warp themselves): plain ATOMS.ADD, without the
 // compiler's own warp-aggregation wrapper around atomicAdd
@@ -531,31 +534,30 @@ struct SmWave {
         }
     }
 
-    // ---- one round: warp 0 snapshots the queues (lane = claim rank) and plans the generation (lane 0) -------------------------------
+    // ---- one round: warp 0 snapshots the queues (lane = claim rank) and plans the generation --------------------------------------
+    // Every other warp waits for this, so the dependent chain is kept short: ONE shared-memory load fetches all control words (lane i
+    // reads word i), everything else is register shuffles, and every lane computes the few scalar decisions redundantly.
     __device__ __forceinline__ void plan_round(unsigned item_total) {
-        int flush = -1, gen = -1, active = 0;
-        unsigned left = 0, n_free = 0, gen_begin = 0;
-        if (lane == 0) {
-            for (int b = 0; b < 2; ++b) {
-                if (S.t_item[b] < 0) continue;
-                ++active;
-                if (S.t_cursor[b] >= item_total) { S.t_cursor[b] = item_total; if (S.t_done[b] == item_total && flush < 0) flush = b; } // (tail fill may overshoot)
-                else if (gen < 0 || S.t_item[b] < S.t_item[gen]) gen = b;
-            }
-            if (gen >= 0) { gen_begin = S.t_cursor[gen]; left = item_total - gen_begin; n_free = S.free_tail - S.free_head; }
-        }
-        left = __shfl_sync(0xffffffffu, left, 0);
-        n_free = __shfl_sync(0xffffffffu, n_free, 0);
-        gen_begin = __shfl_sync(0xffffffffu, gen_begin, 0);
+        const unsigned v = (&S.q_tail[0])[lane]; // words 0..19 are the control block, the padding behind it is never used
+        const int item0 = (int)__shfl_sync(0xffffffffu, v, 14), item1 = (int)__shfl_sync(0xffffffffu, v, 15);
+        unsigned cur0 = __shfl_sync(0xffffffffu, v, 16), cur1 = __shfl_sync(0xffffffffu, v, 17);
+        const unsigned done0 = __shfl_sync(0xffffffffu, v, 18), done1 = __shfl_sync(0xffffffffu, v, 19);
+        const unsigned n_free = __shfl_sync(0xffffffffu, v, 13) - __shfl_sync(0xffffffffu, v, 12);
+        cur0 = min(cur0, item_total); cur1 = min(cur1, item_total); // (the tail fill may overshoot)
+        int flush = -1, gen = -1;
+        if (item1 >= 0) { if (cur1 == item_total) { if (done1 == item_total) flush = 1; } else gen = 1; }
+        if (item0 >= 0) { if (cur0 == item_total) { if (done0 == item_total) flush = 0; } else if (gen < 0 || item0 < item1) gen = 0; }
+        const unsigned gen_begin = gen == 0 ? cur0 : cur1;
+        const unsigned left = gen >= 0 ? item_total - gen_begin : 0u;
         // while new samples keep coming only full 32-record batches are handed out (the remainder waits for the next round);
         // once generation has stopped (an item drains) everything goes
+        const int q = (kRankStage >> (4 * min(lane, 6))) & 0xf; // lanes 0..5: the queue of that rank
+        const unsigned tail = __shfl_sync(0xffffffffu, v, q & 7), handed = __shfl_sync(0xffffffffu, v, 6 + (q & 7));
         unsigned begin = 0, end = 0;
         if (lane < SQ_COUNT) {
-            const int q = (kRankStage >> (4 * lane)) & 0xf;
-            begin = S.q_end[q];
-            unsigned count = S.q_tail[q] - begin;
+            unsigned count = tail - handed;
             if (left != 0u) count &= ~31u;
-            end = begin + count;
+            begin = handed; end = handed + count;
             S.q_end[q] = end;
         }
         unsigned queued = end - begin;
@@ -572,11 +574,11 @@ struct SmWave {
         const unsigned nb = (end - begin + 31u) >> 5;
         unsigned incl = nb;
 #pragma unroll
-        for (int off = 1; off < 8; off <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
+        for (int off = 1; off < 8; off <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += u; }
         if (lane < 8) { S.rb_first[lane] = incl - nb; S.rb_begin[lane] = begin; S.rb_end[lane] = end; }
         const unsigned total = __shfl_sync(0xffffffffu, incl, 7);
         if (lane == 0) {
-            if (gen >= 0) S.t_cursor[gen] = gen_begin + n_gen;
+            S.t_cursor[0] = cur0 + (gen == 0 ? n_gen : 0u); S.t_cursor[1] = cur1 + (gen == 1 ? n_gen : 0u);
             S.flush_slot = flush; S.gen_slot = gen; S.round_claim = 0u; S.tail_budget = n_free - n_gen; S.tail_used = 0u;
             S.exit_flag = (total == 0u && flush < 0 && gen < 0) ? 1 : 0; // nothing queued, nothing to generate, nothing to write out
         }
