@@ -122,6 +122,23 @@ __device__ __forceinline__ float one_minus_cos_max(float s2) { return s2 / (1.0f
 // powerHeuristics (misSamplingFunctions.h:12-16)
 __device__ __forceinline__ float power_heuristic(float f, float g) { const float f2 = f * f, g2 = g * g; return f2 / (f2 + g2); }
 
+// equiAngularParams2 (volumetricBasicFunctions.h:209-223) + equiAngularSample (vptSamplingFunctions.h:54) without materialising the
+// two angles: with a = -proj, b = tmax - proj (the segment ends relative to the light's projection, b > a) and D the light's distance
+// from the ray,  theta_B - theta_A = atan2((b - a) D, D^2 + a b)  (both angles lie in (-pi/2, pi/2]) and
+// tan(theta_A + xi (theta_B - theta_A)) follows from the addition theorem with tan(theta_A) = a / D: one atan2f and one tanf instead
+// of two atan2f and a tanf.  Returns the sampled distance along the ray; t_local is measured from the projection point.
+__device__ __forceinline__ float equiangular_sample(F3 light, F3 o, F3 d, float tmax, float xi, float &D, float &dtheta, float &t_local) {
+    const F3 dv = light - o;
+    const float proj = dot(dv, d);
+    const F3 perp = fma3(d, -proj, dv);
+    D = sqrtf(dot(perp, perp));
+    const float a = -proj, b = fminf(tmax, 1e18f) - proj; // (a miss has tmax = MAXFLOAT: keep the products finite, theta_B is pi/2 to 1e-15)
+    dtheta = atan2f((b - a) * D, fmaf(a, b, D * D));
+    const float tau = tanf(xi * dtheta);
+    t_local = D * fmaf(D, tau, a) / fmaf(-a, tau, D);
+    return t_local + proj;
+}
+
 // ---- Beckmann conductor microfacet model (microFacetUtilities.h), local frame n = +z ----------------------------------
 __device__ __forceinline__ float fresnel_channel(float c, float s2, float eta, float kappa) { // fresnelSpectre :11-18 (s2 = sin^2)
     const float e2k2 = eta * eta - kappa * kappa - s2;

@@ -184,21 +184,10 @@ __global__ void __launch_bounds__(kSmThreads, 1) render_f32_smwave_kernel(const 
                                                                            int log_p, int n_owned_tiles, int n_items, int zero) {
     SmShared &S = sm_shared();
     const int tid = (int)threadIdx.x;
-    for (int i = tid; i < sc.n_spheres * (int)(sizeof(MatF) / 4); i += kSmThreads)
-        reinterpret_cast<uint32_t *>(S.mats)[i] = reinterpret_cast<const uint32_t *>(sc.mat)[i];
+    stage_scene(S.scene, sc, tid, kSmThreads);
     for (int i = tid; i < kSmPool; i += kSmThreads) { S.freelist[i] = (uint16_t)i; S.r1[i] = 0u; S.meta[i] = 0u; }
     for (int i = tid; i < 2 * kSmMaxItemPixels * 3; i += kSmThreads) (&S.acc[0][0][0])[i] = 0ull;
     if (tid == 0) {
-        int na = 0, nb = 0;
-        for (int pass = 0; pass < 2; ++pass) // general-form spheres (huge / re-anchored ones and anything with r >= 64) first
-            for (int g = 0; g < sc.n_geom; ++g) {
-                const GeomF &G = sc.geom[g];
-                const bool general = G.big || G.r2 >= kSimpleRootMaxR2;
-                if (general != (pass == 0)) continue;
-                if (general) { S.ga[2 * na] = make_float4(G.qx, G.qy, G.qz, G.c0); S.ga[2 * na + 1] = make_float4(G.mx, G.my, G.mz, 0.0f); S.gid[na++] = G.id; }
-                else { S.gb[nb] = make_float4(G.qx, G.qy, G.qz, G.r2); S.gid[na + nb++] = G.id; }
-            }
-        S.n_ga = na; S.n_gb = nb;
         for (int q = 0; q < SQ_COUNT; ++q) { S.q_tail[q] = 0u; S.q_end[q] = 0u; }
         S.free_head = 0u; S.free_tail = (unsigned)kSmPool;
         for (int b = 0; b < 2; ++b) {
@@ -284,10 +273,10 @@ struct ListRng {
 
 __global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const __grid_constant__ LaunchParams lp, const __grid_constant__ ConstsF cf, int n, const double *__restrict__ in,
                                 int in_stride, double *__restrict__ out, int out_stride) {
-    __shared__ MatF mats[kMaxSpheres];
-    for (int i = threadIdx.x; i < sc.n_spheres * (int)(sizeof(MatF) / 4); i += blockDim.x)
-        reinterpret_cast<uint32_t *>(mats)[i] = reinterpret_cast<const uint32_t *>(sc.mat)[i];
+    SmScene &PS = *reinterpret_cast<SmScene *>(smwave_smem); // the product kernel's scene (dynamic shared memory): same staging, same scan
+    stage_scene(PS, sc, (int)threadIdx.x, (int)blockDim.x);
     __syncthreads();
+    const MatF *mats = PS.mats;
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n) return;
     const double *a = in + (size_t)row * in_stride;
@@ -301,12 +290,18 @@ __global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const
         for (int g = 0; g < sc.n_geom; ++g) if (sc.geom[g].id == idx) t = sphere_t(sc.geom[g], ld3(a + 1), ld3(a + 4));
         o[0] = t;
     } break;
-    case VPT_UNIT_INTERSECT: {
+    case VPT_UNIT_INTERSECT: { // the product kernel's scan (vpt_smwave.cuh scan_sm); on a miss the reference leaves id untouched (0)
         float t = 0.0f; int id = 0;
-        const bool h = scan(sc, ld3(a), ld3(a + 3), t, id, scans);
-        o[0] = h; o[1] = h ? t : 0.0; o[2] = id;
+        const bool h = scan_sm(PS, ld3(a), ld3(a + 3), t, id);
+        o[0] = h; o[1] = h ? t : 0.0; o[2] = h ? id : 0;
     } break;
-    case VPT_UNIT_VISIBILITY: o[0] = visible(sc, ld3(a), ld3(a + 3), scans); break;
+    case VPT_UNIT_VISIBILITY: { // as the product kernel's point-light shadow ray: nothing hit before distance * (1 - 1e-4)
+        const F3 light = ld3(a), lx = light - ld3(a + 3);
+        const float d2 = dot(lx, lx), inv = rsqrtf(d2);
+        float t; int id;
+        const bool h = scan_sm(PS, light, lx * (-inv), t, id);
+        o[0] = !h || t > d2 * inv * (1.0f - 1e-4f);
+    } break;
     case VPT_UNIT_TRANSMITTANCE: {
         const F3 v = ld3(a + 3) - ld3(a);
         o[0] = expf(-(float)a[6] * sqrtf(dot(v, v)));
@@ -323,14 +318,12 @@ __global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const
         const float tmax = (float)fmin(a[1], (double)kMaxFloat);
         const F3 org = ld3(a + 2), dir = ld3(a + 5);
         const float xi = (float)a[8];
-        const F3 dv = mk(src.px, src.py, src.pz) - org;
-        const float proj = dot(dv, dir);
-        const F3 perp = fma3(dir, -proj, dv);
-        const float D = sqrtf(dot(perp, perp));
-        const float thA = atan2f(-proj, D), thB = atan2f(tmax - proj, D);
-        const float tl = D * tanf((1.0f - xi) * thA + xi * thB);
-        o[0] = D; o[1] = thA; o[2] = thB; o[3] = tl; o[4] = tl + proj;
-        o[5] = D / (fabsf(thB - thA) * (tl * tl + D * D));
+        const F3 light = mk(src.px, src.py, src.pz);
+        float D, dth, tl; // the product kernel's form (vpt_f32.cuh equiangular_sample): the two angles are reported for the comparison only
+        const float dist = equiangular_sample(light, org, dir, tmax, xi, D, dth, tl);
+        const float thA = atan2f(-dot(light - org, dir), D);
+        o[0] = D; o[1] = thA; o[2] = thA + dth; o[3] = tl; o[4] = dist;
+        o[5] = D / (dth * (tl * tl + D * D));
     } break;
     case VPT_UNIT_POWER_HEURISTIC: o[0] = power_heuristic((float)a[0], (float)a[1]); break;
     case VPT_UNIT_COSINE_HEMISPHERE: {
@@ -430,7 +423,7 @@ __global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const
 
 int launch_unit_f32(int fn, const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, int n, const double *in_dev, int in_stride, double *out_dev, int out_stride, void *stream) {
     const int tpb = 64;
-    unit_f32_kernel<<<(n + tpb - 1) / tpb, tpb, 0, (cudaStream_t)stream>>>(fn, scene, lp, cf, n, in_dev, in_stride, out_dev, out_stride);
+    unit_f32_kernel<<<(n + tpb - 1) / tpb, tpb, sizeof(SmScene), (cudaStream_t)stream>>>(fn, scene, lp, cf, n, in_dev, in_stride, out_dev, out_stride);
     return (int)cudaGetLastError();
 }
 

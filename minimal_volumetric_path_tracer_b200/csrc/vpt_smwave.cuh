@@ -37,7 +37,34 @@ enum : int { SQ_PRIMARY = 0, SQ_MED_POINT, SQ_MED_AREA, SQ_SURF_P, SQ_SURF_L, SQ
 // SURF_F, SURF_L, PRIMARY, MED_AREA, MED_POINT, SURF_P, generation
 constexpr unsigned kRankStage = 0x6312045u;
 
+// the scene as the scan and the shading code read it; first in the CTA's shared memory (the unit kernels stage only this part)
+struct SmScene {
+    MatF mats[kMaxSpheres];
+    float4 ga[2 * kMaxSpheres]; // general-form spheres: (qx qy qz c0) (mx my mz -)
+    float4 gb[kMaxSpheres];     // direct-root spheres: (px py pz r^2)
+    int gid[2 * kMaxSpheres];   // scan order -> caller's sphere index (general ones first)
+    int n_ga, n_gb;
+};
+// cooperative staging by the whole block (call, then __syncthreads)
+__device__ __forceinline__ void stage_scene(SmScene &S, const SceneF &sc, int tid, int n_threads) {
+    for (int i = tid; i < sc.n_spheres * (int)(sizeof(MatF) / 4); i += n_threads)
+        reinterpret_cast<uint32_t *>(S.mats)[i] = reinterpret_cast<const uint32_t *>(sc.mat)[i];
+    if (tid == 0) {
+        int na = 0, nb = 0;
+        for (int pass = 0; pass < 2; ++pass) // general-form spheres (huge / re-anchored ones and anything with r >= 64) first
+            for (int g = 0; g < sc.n_geom; ++g) {
+                const GeomF &G = sc.geom[g];
+                const bool general = G.big || G.r2 >= kSimpleRootMaxR2;
+                if (general != (pass == 0)) continue;
+                if (general) { S.ga[2 * na] = make_float4(G.qx, G.qy, G.qz, G.c0); S.ga[2 * na + 1] = make_float4(G.mx, G.my, G.mz, 0.0f); S.gid[na++] = G.id; }
+                else { S.gb[nb] = make_float4(G.qx, G.qy, G.qz, G.r2); S.gid[na + nb++] = G.id; }
+            }
+        S.n_ga = na; S.n_gb = nb;
+    }
+}
+
 struct SmShared {
+    SmScene scene; // first: scan_sm_call and the unit kernels find it at the start of the dynamic shared memory
     // ---- path records (SoA) ----
     float ox[kSmPool], oy[kSmPool], oz[kSmPool];
     float dx[kSmPool], dy[kSmPool], dz[kSmPool];
@@ -51,12 +78,6 @@ struct SmShared {
     uint16_t queue[SQ_COUNT][kSmPool];
     uint16_t freelist[kSmPool];
     unsigned long long acc[2][kSmMaxItemPixels][3];
-    // ---- scene ----
-    MatF mats[kMaxSpheres];
-    float4 ga[2 * kMaxSpheres]; // general-form spheres: (qx qy qz c0) (mx my mz -)
-    float4 gb[kMaxSpheres];     // direct-root spheres: (px py pz r^2)
-    int gid[2 * kMaxSpheres];   // scan order -> caller's sphere index (general ones first)
-    int n_ga, n_gb;
     // ---- control ----
     // this round's batch table by rank (kRankStage): batch k belongs to the last rank with rb_first[rank] <= k and covers entries
     // [rb_begin + 32 j, min(rb_end, +32)), j = k - rb_first
@@ -100,7 +121,7 @@ __device__ __forceinline__ SmShared &sm_shared() { return *reinterpret_cast<SmSh
 // One out-of-line copy: it is called from seven places and must stay resident in the instruction cache.
 struct ScanHit { float t; int index; };
 static __device__ __noinline__ ScanHit scan_sm_call(float ox, float oy, float oz, float dx, float dy, float dz) {
-    const SmShared &S = sm_shared();
+    const SmScene &S = *reinterpret_cast<const SmScene *>(smwave_smem);
     const F3 o = mk(ox, oy, oz), d = mk(dx, dy, dz);
     float best = CUDART_INF_F;
     int bi = -1;
@@ -132,7 +153,7 @@ static __device__ __noinline__ ScanHit scan_sm_call(float ox, float oy, float oz
     }
     return ScanHit{best, bi};
 }
-__device__ __forceinline__ bool scan_sm(const SmShared &S, F3 o, F3 d, float &t, int &id) {
+__device__ __forceinline__ bool scan_sm(const SmScene &S, F3 o, F3 d, float &t, int &id) {
     const ScanHit h = scan_sm_call(o.x, o.y, o.z, d.x, d.y, d.z);
     t = h.t;
     id = h.index >= 0 ? S.gid[h.index] : -1;
@@ -296,7 +317,7 @@ struct SmWave {
         F3 o = mk(S.ox[s], S.oy[s], S.oz[s]);
         const F3 d = mk(S.dx[s], S.dy[s], S.dz[s]);
         float t; int hid;
-        const bool hit = scan_sm(S, o, d, t, hid);
+        const bool hit = scan_sm(S.scene, o, d, t, hid);
         bool to_mp = false, to_ma = false, to_sp = false, to_sl = false, to_sf = false, ended = false;
         const uint32_t meta = S.meta[s];
         if (act) {
@@ -304,31 +325,20 @@ struct SmWave {
             if (!hit) { t = kMaxFloat; hid = 0; }
             const int pick = min((int)(u32_to_unit_f32(S.r1[s]) * k.n_emitters), sc.n_emitters - 1);
             const int src = sc.emitters[pick];
-            const MatF &sm = S.mats[src];
+            const MatF &sm = S.scene.mats[src];
             bool surface; float dist, inv_pdf = 1.0f;
             if (METHOD == 0) {
                 dist = -logf(1.0f - u32_to_unit_f32(S.r2[s])) * k.inv_sigma_t; // freeFlightSample, vptSamplingFunctions.h:11
                 surface = dist > t;
             } else { // equiAngularParams2 (volumetricBasicFunctions.h:209-223) + equiAngularProb (vptSamplingFunctions.h:60)
                 const float Tr = expf(-k.sigma_t * t);
-                const F3 dv = mk(sm.px, sm.py, sm.pz) - o;
-                const float proj = dot(dv, d);
-                const F3 perp = fma3(d, -proj, dv);
-                const float D = sqrtf(dot(perp, perp));
-                // theta_B - theta_A = atan2((b - a) D, D^2 + a b) with a = -proj, b = t - proj (both angles in (-pi/2, pi/2], b > a), and
-                // tan(theta_A + xi (theta_B - theta_A)) by the addition theorem with tan(theta_A) = a / D: one atan2f and one tanf of an
-                // angle in (0, pi) instead of two atan2f and a tanf
-                const float a = -proj, b = fminf(t, 1e18f) - proj; // (a miss has t = MAXFLOAT: keep the products finite, theta_B is pi/2 to 1e-15)
-                const float dth = atan2f((b - a) * D, fmaf(a, b, D * D));
-                const float xi = u32_to_unit_f32(S.r2[s]);
-                const float tau = tanf(xi * dth);
-                const float tl = D * fmaf(D, tau, a) / fmaf(-a, tau, D);
-                dist = tl + proj;
+                float D, dth, tl;
+                dist = equiangular_sample(mk(sm.px, sm.py, sm.pz), o, d, t, u32_to_unit_f32(S.r2[s]), D, dth, tl);
                 inv_pdf = dth * (tl * tl + D * D) / (D * (1.0f - Tr));
                 const float xs = u32_to_unit_f32(S.r3[s]);
                 surface = (METHOD == 1) ? (xs <= Tr) : (xs < Tr);
             }
-            const MatF &obj = S.mats[hid];
+            const MatF &obj = S.scene.mats[hid];
             if (surface && obj.emits) { // :1308-1313: a directly seen emitter ends the path
                 const F3 L = (meta >> 10) == 0 ? had(mk(obj.lr, obj.lg, obj.lb), mk(S.br[s], S.bg[s], S.bb[s])) : mk(S.lr[s], S.lg[s], S.lb[s]);
                 add_radiance(meta, L);
@@ -371,7 +381,7 @@ struct SmWave {
         const uint32_t sample = S.sample[s], meta = S.meta[s];
         const uint32_t pixel = pixel_of(meta);
         const uint4 b1 = philox_block(pixel, sample, meta >> 10, 1, lp.key0, lp.key1);
-        const MatF &sm = S.mats[src];
+        const MatF &sm = S.scene.mats[src];
         const F3 light = mk(sm.px, sm.py, sm.pz);
         const F3 lx = light - o;
         const float d2 = dot(lx, lx), inv = rsqrtf(d2);
@@ -387,7 +397,7 @@ struct SmWave {
             C = had(mk(sm.lr, sm.lg, sm.lb), beta) * (kInv4Pi * kTwoPi * omc_max * k.n_emitters * w);
         }
         float t; int hid;
-        const bool hit = scan_sm(S, qo, qd, t, hid);
+        const bool hit = scan_sm(S.scene, qo, qd, t, hid);
         if (act) {
             ++scans;
             if (POINT) { if (!hit || t > lim) L = L + C; }
@@ -406,8 +416,8 @@ struct SmWave {
         const F3 d = mk(S.dx[s], S.dy[s], S.dz[s]);
         const F3 beta = mk(S.br[s], S.bg[s], S.bb[s]);
         const uint32_t ids = act ? S.r1[s] : 0u;
-        const MatF &sm = S.mats[ids & 0xffu];
-        const MatF &obj = S.mats[ids >> 8];
+        const MatF &sm = S.scene.mats[ids & 0xffu];
+        const MatF &obj = S.scene.mats[ids >> 8];
         const F3 light = mk(sm.px, sm.py, sm.pz);
         const F3 lx = light - o;
         const float d2 = dot(lx, lx), inv = rsqrtf(d2), dist = d2 * inv;
@@ -419,7 +429,7 @@ struct SmWave {
         const F3 C = had(had(mk(sm.lr, sm.lg, sm.lb), f), beta) * (dot(n_, wi) * expf(-k.sigma_t * dist) / d2 * k.n_emitters * k.inv_cp);
         const F3 qd = lx * (-inv);
         float t; int hid;
-        const bool hit = scan_sm(S, light, qd, t, hid);
+        const bool hit = scan_sm(S.scene, light, qd, t, hid);
         if (act) {
             ++scans;
             if (!hit || t > dist * (1.0f - 1e-4f)) { S.lr[s] += C.x; S.lg[s] += C.y; S.lb[s] += C.z; }
@@ -446,7 +456,7 @@ struct SmWave {
         const uint32_t sample = S.sample[s], meta = S.meta[s];
         const uint32_t depth = meta >> 10;
         const uint32_t pixel = pixel_of(meta);
-        const MatF &obj = S.mats[id];
+        const MatF &obj = S.scene.mats[id];
         const F3 n_ = unit(o - mk(obj.px, obj.py, obj.pz));
         const Frame fr = make_frame(n_);
         const F3 wo_l = FACET ? unit(to_local(fr, -d)) : mk(0, 0, 1);
@@ -457,14 +467,14 @@ struct SmWave {
             if ((a & 1) == 0) ra = philox_block(pixel, sample, depth, 2 + (a >> 1), lp.key0, lp.key1);
             const float xi1 = u32_to_unit_f32((a & 1) ? ra.z : ra.x), xi2 = u32_to_unit_f32((a & 1) ? ra.w : ra.y);
             const int lid = sc.area[a];
-            const MatF &sm = S.mats[lid];
+            const MatF &sm = S.scene.mats[lid];
             const F3 cx = mk(sm.px, sm.py, sm.pz) - o;
             const float len2 = dot(cx, cx), inv_len = rsqrtf(len2);
             const float omc_max = one_minus_cos_max(sm.r * sm.r / len2);
             omc_last = omc_max;
             const F3 wi = cone_sample(cx * inv_len, omc_max, xi1, xi2);
             float t; int hid;
-            const bool hit = scan_sm(S, o, wi, t, hid);
+            const bool hit = scan_sm(S.scene, o, wi, t, hid);
             if (act) {
                 ++scans;
                 if ((hit ? hid : 0) == lid) { // id stays 0 on a miss, samplingFunctions.h:196
@@ -486,11 +496,11 @@ struct SmWave {
             else wi_l = cosine_local(xi1, xi2);
             const F3 wi = unit(to_world(fr, wi_l));
             float t; int hid;
-            const bool hit = scan_sm(S, o, wi, t, hid);
+            const bool hit = scan_sm(S.scene, o, wi, t, hid);
             if (act) {
                 ++scans;
-                if (hit && S.mats[hid].emits) {
-                    const MatF &em = S.mats[hid];
+                if (hit && S.scene.mats[hid].emits) {
+                    const MatF &em = S.scene.mats[hid];
                     const F3 cx = mk(em.px, em.py, em.pz) - o;
                     float omc = one_minus_cos_max(em.r * em.r / dot(cx, cx));
                     if (FACET) {
