@@ -99,6 +99,7 @@ struct SmShared {
     int next_item;
 };
 static_assert(offsetof(SmShared, t_done) - offsetof(SmShared, q_tail) == 18 * sizeof(unsigned), "plan_round reads the control words by index");
+static_assert(offsetof(SmShared, free_tail) - offsetof(SmShared, q_tail) == 13 * sizeof(unsigned) && offsetof(SmShared, freelist) - offsetof(SmShared, queue) == SQ_COUNT * kSmPool * sizeof(uint16_t), "route() addresses the free ring as queue number SQ_COUNT");
 
 // shared-memory atomic add issued by ONE lane (the callers aggregate over the warp themselves): plain ATOMS.ADD, without the
 // compiler's own warp-aggregation wrapper around atomicAdd
@@ -215,6 +216,21 @@ struct SmWave {
         base = __shfl_sync(0xffffffffu, base, 0);
         if (flag) S.queue[q][(base + __popc(m & ((1u << lane) - 1u))) & (kSmPool - 1)] = (uint16_t)slot;
     }
+    // Route every lane's record in ONE step: dest = a stage queue (SQ_*), kFree (the record goes back to the free ring) or -1 (nothing).
+    // Lanes with the same destination find each other with match.any; the lowest lane of each group reserves the group's entries
+    // with one atomic (all group leaders in the same instruction), the others take their rank behind it.  Replaces up to six
+    // ballot / atomic / store sequences per stage (PRIMARY feeds five queues and the free ring).
+    static constexpr int kFree = SQ_COUNT;
+    __device__ __forceinline__ void route(int dest, int slot) {
+        const unsigned grp = __match_any_sync(0xffffffffu, dest);
+        if (dest < 0) return;
+        const int leader = __ffs(grp) - 1;
+        unsigned base = 0;
+        // counters: q_tail[0..5] are words 0..5 of the control block, free_tail is word 13; rings: queue[0..5] and, right behind them, freelist
+        if (lane == leader) base = smem_add(&S.q_tail[0] + (dest == kFree ? 13 : dest), (unsigned)__popc(grp), lz);
+        base = __shfl_sync(grp, base, leader);
+        (&S.queue[0][0])[dest * kSmPool + ((base + __popc(grp & ((1u << lane) - 1u))) & (kSmPool - 1))] = (uint16_t)slot;
+    }
     __device__ __forceinline__ int alloc(bool flag) { // the round's snapshot guarantees enough free records below free_tail
         const unsigned m = __ballot_sync(0xffffffffu, flag);
         if (m == 0u) return -1;
@@ -276,8 +292,7 @@ struct SmWave {
                 S.meta[slot] = meta;
             } else add_radiance(meta, L);
         }
-        push(SQ_PRIMARY, alive, slot);
-        release(act && !alive, slot);
+        route(alive ? SQ_PRIMARY : (act ? kFree : -1), slot);
         count_done(act && !alive, meta);
     }
 
@@ -366,12 +381,7 @@ struct SmWave {
             }
             if (!ended) { S.ox[s] = o.x; S.oy[s] = o.y; S.oz[s] = o.z; }
         }
-        push(SQ_MED_POINT, to_mp, slot);
-        push(SQ_MED_AREA, to_ma, slot);
-        push(SQ_SURF_P, to_sp, slot);
-        push(SQ_SURF_L, to_sl, slot);
-        push(SQ_SURF_F, to_sf, slot);
-        release(ended, slot);
+        route(to_mp ? SQ_MED_POINT : to_ma ? SQ_MED_AREA : to_sp ? SQ_SURF_P : to_sl ? SQ_SURF_L : to_sf ? SQ_SURF_F : ended ? kFree : -1, slot);
         count_done(ended, meta);
     }
 
@@ -441,8 +451,7 @@ struct SmWave {
             ++scans;
             if (!hit || t > dist * (1.0f - 1e-4f)) { S.lr[s] += C.x; S.lg[s] += C.y; S.lb[s] += C.z; }
         }
-        push(SQ_SURF_L, act && !facet, slot);
-        push(SQ_SURF_F, act && facet, slot);
+        route(act ? (facet ? SQ_SURF_F : SQ_SURF_L) : -1, slot);
     }
     // microfacet BRDF for world-space directions (rare: kept out of line so that the Lambert stages stay small)
     static __device__ __noinline__ F3 facet_eval_world(const MatF &obj, F3 n_, F3 wi, F3 d) {
