@@ -35,7 +35,8 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1
 static __device__ __noinline__ uint4 philox_block(uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t block, uint32_t k0, uint32_t k1) {
     return philox4x32_10(make_uint4(pixel, sample, bounce, block), k0, k1);
 }
-__device__ __forceinline__ float u32_to_unit_f32(uint32_t w) { return (float)(2u * (w >> 9) + 1u) * 5.9604644775390625e-8f; }
+// (2k + 1) 2^-24 with k = w >> 9, without the integer-to-float conversion: 1.k (k in the mantissa) minus (1 - 2^-24) is exactly that value
+__device__ __forceinline__ float u32_to_unit_f32(uint32_t w) { return __uint_as_float(0x3f800000u | (w >> 9)) - 0.99999994039535522461f; }
 __device__ __forceinline__ double u32_to_unit_f64(uint32_t w) { return (double)(2u * (w >> 9) + 1u) * 5.9604644775390625e-8; }
 __device__ __forceinline__ uint32_t pick_lane(const uint4 &b, uint32_t lane) { return lane == 0 ? b.x : lane == 1 ? b.y : lane == 2 ? b.z : b.w; }
 
