@@ -10,8 +10,9 @@
  * (rt.cpp:744-762) and the tonemap / PPM write (rt.cpp:808-829).  INTEGRATION.md shows the call site.
  *
  * Conventions: plain C types only; every function returns 0 (VPT_OK) or a negative vpt_status and never throws;
- * the library keeps no mutable global state; the caller owns every buffer; there is NO CPU fallback -- without a
- * usable CUDA device every compute entry point returns VPT_ERR_NO_DEVICE / VPT_ERR_CUDA.
+ * the caller owns every buffer; the only state the library keeps is a per-device scratch-memory pool for the host-buffer entry
+ * points (released by vpt_trim()); there is NO CPU fallback -- without a usable CUDA device every compute entry point returns
+ * VPT_ERR_NO_DEVICE / VPT_ERR_CUDA.
  */
 #ifndef VPT_H
 #define VPT_H
@@ -158,6 +159,7 @@ int vpt_device_count(void);
 const char *vpt_strerror(int status);
 const char *vpt_last_cuda_error(void); /* thread-local text of the last CUDA failure seen by this thread */
 const char *vpt_version(void);
+void vpt_trim(void); /* give the per-device scratch pools (frame buffers of vpt_render between calls) back to the driver */
 
 #ifdef __cplusplus
 }

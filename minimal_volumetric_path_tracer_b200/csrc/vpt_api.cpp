@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -228,6 +229,36 @@ int enqueue_render(const vpt_params *p, const vpt_sphere *spheres, int n_spheres
 
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
+// Per-device scratch pool for the frame buffer / counters of the host-buffer entry points: a private stream-ordered memory pool
+// whose release threshold keeps the memory between calls (cudaMalloc + cudaFree, or the default pool that trims at every
+// synchronisation, cost 5-10 ms per frame -- as much as a 64-spp render).  The only state the library keeps; vpt_trim() releases it.
+constexpr int kMaxDevices = 64;
+std::mutex g_pool_mutex;
+cudaMemPool_t g_pools[kMaxDevices] = {};
+cudaError_t scratch_pool(int device, cudaMemPool_t *out) {
+    if (device < 0 || device >= kMaxDevices) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (!g_pools[device]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaError_t e = cudaMemPoolCreate(&g_pools[device], &props);
+        if (e != cudaSuccess) { g_pools[device] = nullptr; return e; }
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(g_pools[device], cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    *out = g_pools[device];
+    return cudaSuccess;
+}
+cudaError_t scratch_alloc(int device, void **ptr, size_t bytes, cudaStream_t stream) {
+    cudaMemPool_t pool;
+    cudaError_t e = scratch_pool(device, &pool);
+    if (e != cudaSuccess) return e;
+    return cudaMallocFromPoolAsync(ptr, bytes, pool, stream);
+}
+
 } // namespace
 
 #pragma GCC visibility push(default)
@@ -297,7 +328,7 @@ int vpt_render_device(const vpt_params *p, const vpt_sphere *spheres, int32_t n_
     std::memset(stats, 0, sizeof(*stats));
     Counters *counters_dev = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    CUDA_TRY(cudaMalloc(&counters_dev, sizeof(Counters)));
+    CUDA_TRY(scratch_alloc(p->device, (void **)&counters_dev, sizeof(Counters), stream));
     rc = VPT_OK;
     cudaError_t ce;
     do {
@@ -320,7 +351,7 @@ int vpt_render_device(const vpt_params *p, const vpt_sphere *spheres, int32_t n_
     } while (0);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
-    cudaFree(counters_dev);
+    cudaFreeAsync(counters_dev, stream);
     if (rc) return rc;
     if (ce != cudaSuccess) return cuda_fail(ce, "vpt_render_device");
     stats->total_ms = now_ms() - t0;
@@ -340,9 +371,7 @@ int vpt_render(const vpt_params *p, const vpt_sphere *spheres, int32_t n_spheres
     float *dev = nullptr;
     cudaStream_t stream = nullptr;
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    // stream-ordered allocation from the device's default memory pool: after the first call no driver allocation and no implicit
-    // device-wide synchronisation (cudaMalloc / cudaFree cost several milliseconds per frame)
-    cudaError_t ce = cudaMallocAsync((void **)&dev, bytes, stream);
+    cudaError_t ce = scratch_alloc(p->device, (void **)&dev, bytes, stream); // stream-ordered, from the library's per-device pool
     if (ce != cudaSuccess) { cudaStreamDestroy(stream); return cuda_fail(ce, "cudaMallocAsync"); }
     rc = vpt_render_device(p, spheres, n_spheres, dev, stream, stats); // with stats == NULL nothing synchronises before the copy below
     if (rc == VPT_OK) {
@@ -572,6 +601,11 @@ const char *vpt_strerror(int status) {
     }
 }
 const char *vpt_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
+void vpt_trim(void) {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    for (int d = 0; d < kMaxDevices; ++d)
+        if (g_pools[d]) { cudaMemPoolDestroy(g_pools[d]); g_pools[d] = nullptr; }
+}
 /* development aid, not part of include/vpt.h: the in-kernel cycle counters of the last render with stats on this thread
  * (all zero unless the library was built with -DVPT_SMWAVE_PROFILE) */
 int vpt_debug_counters(unsigned long long *out, int32_t cap) {
