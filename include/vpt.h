@@ -47,7 +47,10 @@ typedef struct {
     double alpha; /* Beckmann roughness */
 } vpt_sphere;
 
-enum { VPT_METHOD_FREE_FLIGHT = 0, VPT_METHOD_EQUIANGULAR = 1, VPT_METHOD_MIS = 2 };
+/* RAYMARCH = rayMarching3 (rayMarchingMethods.h:330-384, the commented line rt.cpp:791): deterministic constant-step Riemann sum of
+ * the single scattering from ONE source (vpt_params.march_source, treated as a point at its centre) along the camera ray up to the
+ * first surface; only the pixel jitter is random.  A noise-free check of the medium next-event term. */
+enum { VPT_METHOD_FREE_FLIGHT = 0, VPT_METHOD_EQUIANGULAR = 1, VPT_METHOD_MIS = 2, VPT_METHOD_RAYMARCH = 3 };
 enum { VPT_PRECISION_FP32 = 0, VPT_PRECISION_FP64_REF = 1 };
 enum { VPT_OUTPUT_SUM = 0, VPT_OUTPUT_MEAN = 1 };
 /* FP32 kernel variants (DESIGN.md "Kernels"), same results to fp32 rounding, AUTO = the fastest by measurement (profiles/):
@@ -80,7 +83,9 @@ typedef struct {
     int32_t output;                   /* VPT_OUTPUT_SUM: per-pixel sum over the rendered samples; MEAN: sum / spp (rt.cpp:800) */
     int32_t kernel;                   /* VPT_KERNEL_* */
     int32_t device;                   /* CUDA ordinal */
-    int32_t _pad;
+    int32_t march_source;             /* VPT_METHOD_RAYMARCH: sphere index of the source; 7 in the commented call rt.cpp:791 (an area light: its own
+                                         sphere blocks the centre-origin shadow ray, the image is black outside it); 8 is the point light */
+    double march_step;                /* VPT_METHOD_RAYMARCH: step length, 0.1 in rt.cpp:791 */
 } vpt_params;
 
 typedef struct {
@@ -143,6 +148,7 @@ typedef enum {
     VPT_UNIT_CAMERA_RAY = 17,      /* rt.cpp:787                 in: x, y, xi1, xi2 (width, height, camera from `p`)   out: d[3] */
     VPT_UNIT_RADIANCE_LIST = 18,   /* the three shade methods on an EXPLICIT list of uniforms (e.g. the reference's erand48 sequence)
                                       in: o[3], d[3], n_u, u[120]                                      out: L[3], draws used (-1: list too short) */
+    VPT_UNIT_RAYMARCH = 19,        /* rayMarchingMethods.h:330   in: o[3], d[3], step, source_index (sigma_* from `p`)            out: L[3], steps */
     VPT_UNIT_COUNT_
 } vpt_unit_fn;
 int vpt_unit(int32_t fn, const vpt_params *p, const vpt_sphere *spheres, int32_t n_spheres, int32_t n, const double *in, int32_t in_stride,

@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvpt_b200.so")
 
-METHOD_FREE_FLIGHT, METHOD_EQUIANGULAR, METHOD_MIS = 0, 1, 2
+METHOD_FREE_FLIGHT, METHOD_EQUIANGULAR, METHOD_MIS, METHOD_RAYMARCH = 0, 1, 2, 3
 PRECISION_FP32, PRECISION_FP64_REF = 0, 1
 OUTPUT_SUM, OUTPUT_MEAN = 0, 1
 KERNEL_AUTO, KERNEL_MEGA, KERNEL_WAVEFRONT, KERNEL_MEGA_SCAN, KERNEL_WAVEFRONT_SM = 0, 1, 2, 3, 4
@@ -17,7 +17,7 @@ QUIRK_R0_FALLTHROUGH, QUIRK_EXACT_VISIBILITY, QUIRKS_REFERENCE, QUIRKS_NONE = 1,
 
 class UNIT:
     SPHERE_INTERSECT, INTERSECT, VISIBILITY, TRANSMITTANCE, FREE_FLIGHT, PHASE_SAMPLE, EQUIANGULAR, POWER_HEURISTIC = range(8)
-    COSINE_HEMISPHERE, CONE_SAMPLE, MICROFACET, FACET_NORMAL, MEDIUM_NEE, POINT_LIGHT, SURFACE_MIS, BSDF_SAMPLE, RADIANCE, CAMERA_RAY, RADIANCE_LIST = range(8, 19)
+    COSINE_HEMISPHERE, CONE_SAMPLE, MICROFACET, FACET_NORMAL, MEDIUM_NEE, POINT_LIGHT, SURFACE_MIS, BSDF_SAMPLE, RADIANCE, CAMERA_RAY, RADIANCE_LIST, RAYMARCH = range(8, 20)
 
 
 class Sphere(C.Structure):  # vpt_sphere
@@ -31,7 +31,7 @@ class Params(C.Structure):  # vpt_params
                 ("sigma_a", C.c_double), ("sigma_s", C.c_double), ("continue_prob", C.c_double),
                 ("cam_o", C.c_double * 3), ("cam_dir", C.c_double * 3), ("fov", C.c_double), ("seed", C.c_uint64),
                 ("quirks", C.c_uint32), ("precision", C.c_int32), ("output", C.c_int32), ("kernel", C.c_int32), ("device", C.c_int32),
-                ("_pad", C.c_int32)]
+                ("march_source", C.c_int32), ("march_step", C.c_double)]
 
     def copy(self, **kw):
         q = Params.from_buffer_copy(bytes(self))

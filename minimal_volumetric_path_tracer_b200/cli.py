@@ -6,7 +6,7 @@ import time
 
 from . import api
 
-METHODS = {"free": api.METHOD_FREE_FLIGHT, "equi": api.METHOD_EQUIANGULAR, "mis": api.METHOD_MIS}
+METHODS = {"free": api.METHOD_FREE_FLIGHT, "equi": api.METHOD_EQUIANGULAR, "mis": api.METHOD_MIS, "march": api.METHOD_RAYMARCH}
 
 
 def parse_args(argv):
@@ -16,6 +16,8 @@ def parse_args(argv):
     ap.add_argument("--size", default="1024x768", help="WxH (rt.cpp:752)")
     ap.add_argument("--sigma-a", type=float, default=0.001)
     ap.add_argument("--sigma-s", type=float, default=0.009)
+    ap.add_argument("--march-step", type=float, default=0.1, help="--method march: step length (rt.cpp:791)")
+    ap.add_argument("--march-source", type=int, default=7, help="--method march: source sphere (rt.cpp:791 passes 7; 8 is the point light)")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--max-depth", type=int, default=0)
     ap.add_argument("--continue-prob", type=float, default=0.6)
@@ -35,7 +37,7 @@ def parse_args(argv):
 
 def params_from_args(a):
     p = api.default_params(width=a.width, height=a.height, spp=a.spp, method=METHODS[a.method], sigma_a=a.sigma_a, sigma_s=a.sigma_s,
-                           seed=a.seed, max_depth=a.max_depth, continue_prob=a.continue_prob)
+                           seed=a.seed, max_depth=a.max_depth, continue_prob=a.continue_prob, march_step=a.march_step, march_source=a.march_source)
     if a.ref:
         p.precision = api.PRECISION_FP64_REF
         p.quirks = api.QUIRKS_REFERENCE

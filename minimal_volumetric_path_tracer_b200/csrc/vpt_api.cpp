@@ -70,7 +70,8 @@ int validate_params(const vpt_params *p, bool need_image) {
         if (!all_tiles && (p->tile_count <= 0 || p->tile_rank < 0 || p->tile_rank >= p->tile_count)) return VPT_ERR_INVALID_ARGUMENT;
         if (p->output != VPT_OUTPUT_SUM && p->output != VPT_OUTPUT_MEAN) return VPT_ERR_INVALID_ARGUMENT;
     }
-    if (p->method < 0 || p->method > 2) return VPT_ERR_INVALID_ARGUMENT;
+    if (p->method < 0 || p->method > VPT_METHOD_RAYMARCH) return VPT_ERR_INVALID_ARGUMENT;
+    if (p->method == VPT_METHOD_RAYMARCH && (!(p->march_step > 0) || !std::isfinite(p->march_step) || p->march_source < 0 || p->march_source >= kMaxSpheres)) return VPT_ERR_INVALID_ARGUMENT;
     if (p->precision != VPT_PRECISION_FP32 && p->precision != VPT_PRECISION_FP64_REF) return VPT_ERR_INVALID_ARGUMENT;
     if (!(p->sigma_a >= 0) || !(p->sigma_s >= 0) || !(p->sigma_a + p->sigma_s > 0) || !std::isfinite(p->sigma_a + p->sigma_s)) return VPT_ERR_INVALID_ARGUMENT;
     if (!(p->continue_prob > 0) || !(p->continue_prob <= 1)) return VPT_ERR_INVALID_ARGUMENT;
@@ -165,6 +166,7 @@ void build_launch(const vpt_params *p, LaunchParams &lp) {
     lp.quirks = p->quirks;
     lp.out_scale = p->output == VPT_OUTPUT_MEAN ? 1.0 / (double)p->spp : 1.0;
     lp.sigma_a = p->sigma_a; lp.sigma_s = p->sigma_s; lp.continue_prob = p->continue_prob;
+    lp.march_step = p->march_step; lp.march_source = p->march_source;
     // camera basis, rt.cpp:755-759
     const V3 d = unit(v3(p->cam_dir));
     const V3 cx{p->width * p->fov / p->height, 0., 0.};
@@ -188,6 +190,7 @@ void build_consts_f32(const LaunchParams &lp, int n_emitters, ConstsF &k) {
     k.method = lp.method; k.max_depth = lp.max_depth;
     for (int i = 0; i < 3; ++i) { k.cam_o[i] = (float)lp.cam_o[i]; k.cam_d[i] = (float)lp.cam_d[i]; k.cam_cx[i] = (float)lp.cam_cx[i]; k.cam_cy[i] = (float)lp.cam_cy[i]; }
     k.inv_w = (float)(1.0 / lp.width); k.inv_h = (float)(1.0 / lp.height);
+    k.march_step = (float)lp.march_step; k.march_source = lp.march_source;
 }
 
 int owned_tiles(const LaunchParams &lp) { return (lp.n_tiles_total - lp.tile_rank + lp.tile_count - 1) / lp.tile_count; }
@@ -208,15 +211,17 @@ int enqueue_render(const vpt_params *p, const vpt_sphere *spheres, int n_spheres
     const int blocks = owned_tiles(lp);
     int n_emit = 0;
     for (int i = 0; i < n_spheres; ++i) n_emit += emits(spheres[i]);
-    if (lp.tile_count > 1 || n_emit == 0 || blocks == 0) CUDA_TRY(cudaMemsetAsync(hdr_dev, 0, bytes, stream));
-    if (n_emit == 0 || blocks == 0) return VPT_OK; // no emitter: every path returns black (vptShadeMethods.h:1301)
+    if (lp.tile_count > 1 || (n_emit == 0 && lp.method != VPT_METHOD_RAYMARCH) || blocks == 0) CUDA_TRY(cudaMemsetAsync(hdr_dev, 0, bytes, stream));
+    if (lp.method == VPT_METHOD_RAYMARCH && lp.march_source >= n_spheres) return VPT_ERR_INVALID_ARGUMENT;
+    if ((n_emit == 0 && lp.method != VPT_METHOD_RAYMARCH) || blocks == 0) return VPT_OK; // no emitter: every path returns black (vptShadeMethods.h:1301)
     int rc;
     if (p->precision == VPT_PRECISION_FP32) {
         SceneF sc;
         build_scene_f32(spheres, n_spheres, sc);
         ConstsF cf;
         build_consts_f32(lp, sc.n_emitters, cf);
-        rc = launch_render_f32(sc, lp, cf, hdr_dev, counters_dev, stream, blocks, p->kernel == VPT_KERNEL_AUTO ? VPT_KERNEL_WAVEFRONT_SM : p->kernel);
+        if (lp.method == VPT_METHOD_RAYMARCH) rc = launch_march_f32(sc, lp, cf, hdr_dev, counters_dev, stream, blocks);
+        else rc = launch_render_f32(sc, lp, cf, hdr_dev, counters_dev, stream, blocks, p->kernel == VPT_KERNEL_AUTO ? VPT_KERNEL_WAVEFRONT_SM : p->kernel);
     } else {
         SceneD sc;
         build_scene_f64(spheres, n_spheres, sc);
@@ -282,6 +287,7 @@ void vpt_default_params(vpt_params *p) {
     p->output = VPT_OUTPUT_MEAN;
     p->kernel = VPT_KERNEL_AUTO;
     p->device = 0;
+    p->march_source = 7; p->march_step = 0.1; // rt.cpp:791
 }
 
 int vpt_default_scene(vpt_sphere *out, int32_t cap) {
@@ -473,7 +479,7 @@ int vpt_write_ppm(const float *hdr_rgb, int32_t width, int32_t height, const cha
 
 // ---- unit kernels -----------------------------------------------------------------------------------------------------------------
 static const int kUnitStrides[VPT_UNIT_COUNT_][2] = {
-    {7, 1}, {6, 3}, {6, 1}, {7, 1}, {2, 4}, {2, 3}, {9, 6}, {2, 1}, {5, 4}, {7, 4}, {13, 6}, {3, 3}, {10, 3}, {11, 3}, {19, 3}, {9, 6}, {8, 4}, {4, 3}, {127, 4},
+    {7, 1}, {6, 3}, {6, 1}, {7, 1}, {2, 4}, {2, 3}, {9, 6}, {2, 1}, {5, 4}, {7, 4}, {13, 6}, {3, 3}, {10, 3}, {11, 3}, {19, 3}, {9, 6}, {8, 4}, {4, 3}, {127, 4}, {8, 4},
 };
 int vpt_unit_strides(int32_t fn, int32_t *in_stride, int32_t *out_stride) {
     if (fn < 0 || fn >= VPT_UNIT_COUNT_) return VPT_ERR_INVALID_ARGUMENT;

@@ -137,6 +137,34 @@ __device__ __forceinline__ double transmittance(D3 a, D3 b, double sigma_t) {   
     const D3 v = b - a;
     return exp(sigma_t * sqrt(dot(v, v)) * -1.0);
 }
+// rayMarching3, rayMarchingMethods.h:330-384: constant-step Riemann sum of the single scattering from the source's centre.
+// (The reference attenuates each sample by the transmittance from the SURFACE point x to the sample, :350, not from the ray origin;
+// reproduced as written.)  n_steps (nullable) receives the number of loop iterations.
+__device__ __forceinline__ D3 ray_march3(const Ctx &c, D3 o, D3 d, double step, int source, Tally &tl, double *n_steps = nullptr) {
+    double t;
+    int id = 0;
+    if (n_steps) *n_steps = 0;
+    if (!scan(c, o, d, t, id, tl)) return mk(0, 0, 0);
+    const D3 x = o + d * t;
+    D3 Li = mk(0, 0, 0);
+    const double steps = t / step;
+    const D3 light = pos(c.s[source]);
+    int i = 0;
+    for (; i < steps; i++) {
+        const D3 xt = o + d * step * i;
+        const double T = transmittance(x, xt, c.sigma_a + c.sigma_s);
+        const double phase = phase_value();
+        const D3 wc = light - xt;
+        const double normwc = dot(wc, wc);
+        if (visible(c, light, xt, tl)) {
+            const D3 Le = rad(c.s[source]) * (1 / normwc);
+            const D3 Ls = Le * (phase * transmittance(xt, light, c.sigma_a + c.sigma_s));
+            Li = Li + Ls * (T) * c.sigma_s * step;
+        }
+    }
+    if (n_steps) *n_steps = i;
+    return Li;
+}
 __device__ __forceinline__ double power_heuristic(double f, double g) { const double f2 = f * f, g2 = g * g; return f2 / (f2 + g2); }
 
 // microFacetUtilities.h

@@ -75,6 +75,9 @@ struct LaunchParams {
     double sigma_a, sigma_s, continue_prob;
     // camera (rt.cpp:755-759), prepared on the host in double
     double cam_o[3], cam_d[3], cam_cx[3], cam_cy[3];
+    // VPT_METHOD_RAYMARCH
+    double march_step;
+    int32_t march_source, pad_;
 };
 
 // fp32 constants derived from LaunchParams on the host (double arithmetic), so that no kernel converts doubles in its hot loop
@@ -83,6 +86,7 @@ struct ConstsF {
     float n_emitters; // 1 / probSource
     int32_t method, max_depth;
     float cam_o[3], cam_d[3], cam_cx[3], cam_cy[3], inv_w, inv_h;
+    float march_step; int32_t march_source;
 };
 
 constexpr int kDebugCounters = 32;
@@ -92,6 +96,7 @@ struct Counters { // device-side, accumulated with atomics at thread exit
 };
 
 // entry points implemented in the .cu files, called from vpt_api.cpp
+int launch_march_f32(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks);
 int launch_render_f32(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks, int kernel);
 int launch_render_f64(const SceneD &scene, const LaunchParams &lp, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks);
 int launch_unit_f32(int fn, const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, int n, const double *in_dev, int in_stride, double *out_dev, int out_stride, void *stream);

@@ -12,6 +12,7 @@
 #include "vpt_mega_scan.cuh"
 #include "vpt_wavefront.cuh"
 #include "vpt_smwave.cuh"
+#include "vpt_march.cuh"
 
 namespace vpt {
 
@@ -230,6 +231,38 @@ static int launch_smwave(const SceneF &scene, const LaunchParams &lp, const Cons
     return (int)cudaGetLastError();
 }
 
+// ---- ray-marching reference solver (vpt_march.cuh): one thread per pixel ---------------------------------------------------------
+__global__ void __launch_bounds__(kThreadsPerBlock) render_f32_march_kernel(const __grid_constant__ SceneF sc, const __grid_constant__ LaunchParams lp,
+                                                                             const __grid_constant__ ConstsF cf, float *__restrict__ hdr, Counters *__restrict__ counters) {
+    SmScene &S = *reinterpret_cast<SmScene *>(smwave_smem);
+    stage_scene(S, sc, (int)threadIdx.x, (int)blockDim.x);
+    __syncthreads();
+    const long long tile = (long long)blockIdx.x * lp.tile_count + lp.tile_rank;
+    const long long pixel = tile * kTile + threadIdx.x;
+    if (pixel >= lp.n_pixels) return;
+    const CameraF cam = make_camera(cf);
+    const int row = (int)(pixel / lp.width), col = (int)(pixel - (long long)row * lp.width);
+    double acc[3] = {0, 0, 0};
+    unsigned scans = 0, nonfinite = 0;
+    for (int s = lp.sample_begin; s < lp.sample_end; ++s) {
+        const uint4 j = philox_block((uint32_t)pixel, (uint32_t)s, kJitterBounce, 0, lp.key0, lp.key1);
+        const F3 d = camera_dir(cam, (float)col, (float)(lp.height - 1 - row), u32_to_unit_f32(j.x), u32_to_unit_f32(j.y));
+        double L[3]; unsigned n_steps;
+        ray_march3(S, cam.o, d, lp.march_step, cf.march_source, cf.sigma_t, cf.sigma_s, L, n_steps, scans);
+        if (isfinite(L[0] + L[1] + L[2])) { acc[0] += L[0]; acc[1] += L[1]; acc[2] += L[2]; } else ++nonfinite;
+    }
+    float *out = hdr + pixel * 3;
+    out[0] = (float)(acc[0] * lp.out_scale); out[1] = (float)(acc[1] * lp.out_scale); out[2] = (float)(acc[2] * lp.out_scale);
+    if (!counters) return;
+    atomicAdd(&counters->events, (unsigned long long)(lp.sample_end - lp.sample_begin)); atomicAdd(&counters->scans, (unsigned long long)scans);
+    if (nonfinite) atomicAdd(&counters->nonfinite, (unsigned long long)nonfinite);
+    atomicAdd(&counters->paths, (unsigned long long)(lp.sample_end - lp.sample_begin));
+}
+int launch_march_f32(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks) {
+    render_f32_march_kernel<<<n_blocks, kThreadsPerBlock, sizeof(SmScene), (cudaStream_t)stream>>>(scene, lp, cf, hdr_dev, counters_dev);
+    return (int)cudaGetLastError();
+}
+
 int launch_render_f32(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks, int kernel) {
     cudaStream_t st = (cudaStream_t)stream;
     if (kernel == VPT_KERNEL_MEGA) {
@@ -416,6 +449,11 @@ __global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const
     case VPT_UNIT_CAMERA_RAY: {
         const CameraF cam = make_camera(cf);
         st3(o, camera_dir(cam, (float)a[0], (float)a[1], (float)a[2], (float)a[3]));
+    } break;
+    case VPT_UNIT_RAYMARCH: {
+        double L[3]; unsigned n_steps;
+        ray_march3(PS, ld3(a), ld3(a + 3), a[6], (int)a[7], k.sigma_t, k.sigma_s, L, n_steps, scans);
+        o[0] = L[0]; o[1] = L[1]; o[2] = L[2]; o[3] = n_steps;
     } break;
     default: break;
     }

@@ -50,6 +50,16 @@ __global__ void __launch_bounds__(kThreadsPerBlock) render_f64_kernel(const __gr
     int s = lp.sample_begin;
     bool active = false;
     p.depth = 0;
+    if (c.method == VPT_METHOD_RAYMARCH) { // rt.cpp:791: one deterministic march per jittered camera ray
+        for (; s < lp.sample_end; ++s) {
+            rng.start((uint32_t)pixel, (uint32_t)s, lp.key0, lp.key1);
+            double j1, j2;
+            rng.jitter_f64(j1, j2);
+            const D3 L = ray_march3(c, v3(lp.cam_o), camera_dir(lp, col, cam_y, j1, j2), lp.march_step, lp.march_source, tally);
+            ++tally.events;
+            if (isfinite(L.x + L.y + L.z)) { acc_r += L.x; acc_g += L.y; acc_b += L.z; } else ++nonfinite;
+        }
+    }
     for (;;) {
         bool have = false;
         for (;;) {
@@ -203,6 +213,7 @@ __global__ void unit_f64_kernel(int fn, const __grid_constant__ SceneD sc, const
         st3(o, p.L); o[3] = rng.overrun ? -1.0 : (double)rng.i;
     } break;
     case VPT_UNIT_CAMERA_RAY: st3(o, camera_dir(lp, (int)a[0], (int)a[1], a[2], a[3])); break;
+    case VPT_UNIT_RAYMARCH: st3(o, ray_march3(c, v3(a), v3(a + 3), a[6], (int)a[7], tl, o + 3)); break;
     default: break;
     }
 }

@@ -476,6 +476,34 @@ static inline Vec medium_direct(Rng &rng, Scene &sc, const Vec &xt, int source, 
 }
 
 /* ---- estimators ------------------------------------------------------------------------------------ */
+/* rayMarching3, rayMarchingMethods.h:330-384 (the commented call src/rt.cpp:791): constant-step Riemann sum of the single scattering
+ * from the centre of sphere `source`.  As written in the reference: each sample is attenuated by the transmittance from the SURFACE
+ * point x to the sample (:350), not from the ray origin.  n_steps (nullable) = loop iterations. */
+static inline Vec ray_march3(Scene &sc, const Ray &r, double sigma_a, double sigma_s, double step, int source, uint64_t *n_steps = nullptr) {
+    double t;
+    int id = 0;
+    if (n_steps) *n_steps = 0;
+    if (!scan(sc, r, t, id)) return Vec();
+    const Vec x = r.o + r.d * t;
+    Vec Li;
+    const double steps = t / step;
+    int i = 0;
+    for (; i < steps; i++) {
+        const Vec xt = r.o + r.d * step * i;
+        const double T = transmittance(x, xt, sigma_a + sigma_s);
+        const double phase = phase_value();
+        const Vec wc = sc.s[source].p - xt;
+        const double normwc = dot(wc, wc);
+        if (visible(sc, sc.s[source].p, xt)) {
+            const Vec Le = sc.s[source].radiance * (1 / normwc);
+            const Vec Ls = Le * (phase * transmittance(xt, sc.s[source].p, sigma_a + sigma_s));
+            Li = Li + Ls * (T) * sigma_s * step;
+        }
+    }
+    if (n_steps) *n_steps = (uint64_t)i;
+    return Li;
+}
+
 struct Settings {
     int method = 0;              /* 0 free-flight (vptShadeMethods.h:1263), 1 equi-angular (:1014), 2 "MIS" (:1345) */
     double sigma_a = 0.001, sigma_s = 0.009; /* src/rt.cpp:794 */

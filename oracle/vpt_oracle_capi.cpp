@@ -157,6 +157,46 @@ void l1_radiance_philox(const double *scene, int n, unsigned quirks, int method,
     }
 }
 
+/* rayMarching3 on `count` rays; out: count x 4 (L[3], steps) */
+void l1_ray_march3(const double *scene, int n, unsigned quirks, double sa, double ss, double step, int source, int count, const double *o, const double *d, double *out) {
+#pragma omp parallel
+    {
+        Scene sc = make_scene(scene, n, quirks);
+#pragma omp for schedule(dynamic, 1)
+        for (int i = 0; i < count; ++i) {
+            uint64_t steps = 0;
+            put(out + 4 * i, ray_march3(sc, Ray{V(o + 3 * i), V(d + 3 * i)}, sa, ss, step, source, &steps));
+            out[4 * i + 3] = (double)steps;
+        }
+    }
+}
+/* whole frame with rayMarching3 per jittered camera ray (rt.cpp:791), Philox jitter as l1_render */
+void l1_render_march(const double *scene, int n, unsigned quirks, double sa, double ss, double step, int source,
+                     int w, int h, const double *cam_o, const double *cam_dir, double fov, uint64_t seed, int sample_begin, int sample_end, int nthreads, double *sum) {
+    const Camera cam(w, h, V(cam_o), V(cam_dir), fov);
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel
+    {
+        Scene sc = make_scene(scene, n, quirks);
+#pragma omp for schedule(dynamic, 1)
+        for (int row = 0; row < h; ++row) {
+            const int y = h - 1 - row;
+            for (int x = 0; x < w; ++x) {
+                const size_t pix = (size_t)row * w + x;
+                double s[3] = {0, 0, 0};
+                for (int k = sample_begin; k < sample_end; ++k) {
+                    PhiloxRng r(seed, (uint32_t)pix, (uint32_t)k);
+                    double xi1, xi2;
+                    r.jitter(xi1, xi2);
+                    const Vec v = ray_march3(sc, cam.ray(x, y, xi1, xi2), sa, ss, step, source);
+                    s[0] += v.x; s[1] += v.y; s[2] += v.z;
+                }
+                for (int c = 0; c < 3; ++c) sum[pix * 3 + c] = s[c];
+            }
+        }
+    }
+}
+
 /* camera, src/rt.cpp:752-759,787 */
 void l1_camera(int w, int h, const double *cam_o, const double *cam_dir, double fov, double *o, double *d, double *cx, double *cy) {
     const Camera c(w, h, V(cam_o), V(cam_dir), fov);

@@ -237,6 +237,19 @@ class L1:
                            _p(total), _p(sq) if want_sumsq else None, st.ctypes.data_as(PU64))
         return total, sq, dict(paths=int(st[0]), events=int(st[1]), scans=int(st[2]))
 
+    def ray_march3(self, scene, quirks, sa, ss, step, source, o, d):
+        """rayMarching3 on n rays -> n x 4 (L[3], steps)"""
+        s = _v(scene); o = _v(o).reshape(-1, 3); d = _v(d).reshape(-1, 3); out = np.zeros((len(o), 4))
+        self.lib.l1_ray_march3(_p(s), C.c_int(len(s)), C.c_uint(quirks), D(sa), D(ss), D(step), C.c_int(source), C.c_int(len(o)), _p(o), _p(d), _p(out))
+        return out
+
+    def render_march(self, scene, quirks, sa, ss, step, source, w, h, seed, spp, sample_begin=0, cam_o=CAM_O, cam_dir=CAM_DIR, fov=CAM_FOV, nthreads=0):
+        s, co, cd = _v(scene), _v(cam_o), _v(cam_dir)
+        total = np.zeros((h, w, 3))
+        self.lib.l1_render_march(_p(s), C.c_int(len(s)), C.c_uint(quirks), D(sa), D(ss), D(step), C.c_int(source), C.c_int(w), C.c_int(h), _p(co), _p(cd), D(fov),
+                                 C.c_uint64(seed), C.c_int(sample_begin), C.c_int(sample_begin + spp), C.c_int(nthreads), _p(total))
+        return total
+
     def toDisplayValue(self, x): return self.lib.l1_toDisplayValue(D(x))
 
 

@@ -4,6 +4,7 @@ oracle/Makefile).  Run in the build container only (the reference tree does not 
   python tools/gen_golden.py units     -> tests/golden/units.npz      unit-function vectors (inputs, explicit uniforms, outputs)
   python tools/gen_golden.py paths     -> tests/golden/paths.npz      per-path radiance on seeded erand48 streams
   python tools/gen_golden.py images    -> tests/golden/image_*.npz    16x16-block statistics of whole renders
+  python tools/gen_golden.py march     -> tests/golden/march.npz      rayMarching3 (rayMarchingMethods.h:330) on fixed rays
 """
 import os
 import sys
@@ -212,6 +213,24 @@ def block_stats(total, sq, spp, block=16):
     return m.astype(np.float32), v.astype(np.float32)
 
 
+def gen_march():
+    """rayMarching3 of the UNMODIFIED reference (as shipped: quirks 3) and with the robust hooks (quirks 0) on 96 rays: the literals of the
+    commented call rt.cpp:791 (sigma 0.001 / 0.0125, step 0.1, source 7), the point light (source 8) and a coarser step"""
+    l0 = L0(); l1 = L1(); rng = np.random.default_rng(4242)
+    l0.reset_scene()
+    o, d = rand_rays(rng, l1, 96)
+    out = {"o": o, "d": d}
+    cases = [("src7_step01", 0.001, 0.0125, 0.1, 7), ("src8_step01", 0.001, 0.0125, 0.1, 8), ("src8_step05", 0.001, 0.009, 0.5, 8), ("src9_step1", 0.002, 0.02, 1.0, 9)]
+    out["cases"] = np.array([[sa, ss, step, src] for _, sa, ss, step, src in cases])
+    for q in (3, 0):
+        l0.set_quirks(q)
+        for name, sa, ss, step, src in cases:
+            out["q%d_%s" % (q, name)] = np.array([l0.rayMarching3(o[i], d[i], sa, ss, step, src) for i in range(len(o))])
+    l0.set_quirks(3)
+    np.savez_compressed(os.path.join(GOLD, "march.npz"), **out)
+    print("march.npz:", {k: v.shape for k, v in out.items()})
+
+
 def gen_images(which=None):
     l0 = L0()
     jobs = [  # name, scene, quirks, method, spp
@@ -247,5 +266,7 @@ if __name__ == "__main__":
         gen_units()
     if what in ("paths", "all"):
         gen_paths()
+    if what in ("march", "all"):
+        gen_march()
     if what in ("images", "all"):
         gen_images(sys.argv[2:] or None)
