@@ -266,3 +266,37 @@ def test_auto_kernel_per_path_parity(gpu, l1, method):
     assert np.median(err) < 1e-6
     assert np.mean(err < 1e-5) > 0.99, float(np.mean(err < 1e-5))
     assert np.array_equal((img == 0).all(axis=2) & (ref == 0).all(axis=2), (ref == 0).all(axis=2)) or np.mean((img == 0).all(axis=2) != (ref == 0).all(axis=2)) < 2e-3
+
+
+def _stress_scene():
+    """Not in the reference: exercises what the default scene does not -- an ODD number of area lights (the cone-sample uniforms come in pairs
+    per Philox block), two point lights, a mid-size sphere (r = 90: general root form without re-anchoring), a second microfacet object, an
+    emitter with a zero red channel (MISv2 only samples lights with radiance.x > 0, misSamplingFunctions.h:106), 15 spheres."""
+    rows = [r.copy() for r in DEFAULT_SCENE]
+    z = [0.0] * 7
+    rows.append(np.array([90, 60, -125, -30, .6, .4, .3, 0, 0, 0, 0, *z]))                    # r = 90 Lambert boulder poking through the floor
+    rows.append(np.array([1.5, -20, 10, 40, 0, 0, 0, 40, 60, 90, 0, *z]))                      # third area light
+    rows.append(np.array([0, 30, -10, 60, 0, 0, 0, 0, 900, 900, 0, *z]))                       # second point light
+    rows.append(np.array([6, -5, -34.8, 60, 0, 0, 0, 0, 0, 0, 1, 0.2, 0.92, 1.1, 3.9, 2.45, 2.14, 0.2]))  # rough gold-ish microfacet ball
+    rows.append(np.array([1.0, 10, 0, 90, 0, 0, 0, 0, 20, 20, 0, *z]))                         # emitter with radiance.x == 0
+    return np.array(rows)
+
+
+@pytest.mark.parametrize("method", [0, 1, 2])
+def test_auto_kernel_per_path_parity_on_a_scene_not_in_the_reference(gpu, l1, method):
+    """the product kernel against the FP64 oracle, one path per pixel, on the stress scene"""
+    sc = _stress_scene()
+    w, h = 192, 144
+    p = gpu.default_params(width=w, height=h, spp=1, method=method, seed=31, output=gpu.OUTPUT_SUM)
+    img, st = gpu.render(p, gpu.scene_from_rows(sc), stats=True)
+    ref, _, rst = l1.render(sc, 0, method, SA, SS, w, h, 31, 1, want_sumsq=False)
+    assert st.paths == w * h and st.nonfinite == 0
+    assert abs(int(st.events) - int(rst["events"])) <= 3e-4 * rst["events"]
+    err = np.abs(img - ref).max(axis=2) / np.maximum(np.abs(ref).max(axis=2), 1e-4)
+    assert np.median(err) < 1e-6 and np.mean(err < 1e-5) > 0.985, (float(np.median(err)), float(np.mean(err < 1e-5)))
+    # and with more samples the two images agree pixel by pixel (sums of 8 paths)
+    p8 = p.copy(spp=8)
+    img8 = gpu.render(p8, gpu.scene_from_rows(sc))
+    ref8, _, _ = l1.render(sc, 0, method, SA, SS, w, h, 31, 8, want_sumsq=False)
+    e8 = np.abs(img8 - ref8) / np.maximum(np.abs(ref8), 1e-3)
+    assert np.median(e8) < 2e-6 and np.mean(e8 > 1e-3) < 0.03
