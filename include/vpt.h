@@ -103,6 +103,12 @@ void vpt_default_params(vpt_params *p);
 /* Sphere.cpp:11-22 restated as data; returns the sphere count (10) or VPT_ERR_INVALID_ARGUMENT if cap is too small. */
 int vpt_default_scene(vpt_sphere *out, int32_t cap);
 
+/* Scene files (scenes without recompiling; the reference edits Sphere.cpp:7-106): text, one sphere per line, 18 numbers in the
+ * argument order of the Sphere constructor (Sphere.h:23) -- radius, centre[3], albedo[3], radiance[3], material, eta[3], kappa[3], alpha --
+ * separated by blanks or commas; `#` starts a comment.  Returns the sphere count, VPT_ERR_IO (cannot read), VPT_ERR_SCENE (malformed line,
+ * more than `cap` spheres).  scenes/ holds the reference's active scene and its five commented alternates. */
+int vpt_load_scene(const char *path, vpt_sphere *out, int32_t cap);
+
 /* Replaces the pixel loop rt.cpp:767-805.  hdr_rgb: HOST buffer, width*height*3 floats, pixel index (h-y-1)*w+x as
  * rt.cpp:773 (row 0 = top of the image), UNCLAMPED linear radiance; pixels outside this call's tiles are written as 0. */
 int vpt_render(const vpt_params *p, const vpt_sphere *spheres, int32_t n_spheres, float *hdr_rgb, vpt_stats *stats /* nullable */);

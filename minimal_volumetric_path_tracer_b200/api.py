@@ -72,6 +72,7 @@ def load_library(path=None):
     PD, PU32 = C.POINTER(C.c_double), C.POINTER(C.c_uint32)
     lib.vpt_default_params.argtypes = [PP]; lib.vpt_default_params.restype = None
     lib.vpt_default_scene.argtypes = [PS, C.c_int32]
+    lib.vpt_load_scene.argtypes = [C.c_char_p, PS, C.c_int32]
     lib.vpt_render.argtypes = [PP, PS, C.c_int32, PF, PST]
     lib.vpt_render_device.argtypes = [PP, PS, C.c_int32, C.c_void_p, C.c_void_p, PST]
     lib.vpt_render_multi.argtypes = [PP, PS, C.c_int32, C.POINTER(C.c_int32), C.c_int32, PF, PST]
@@ -111,6 +112,16 @@ def default_scene():
     n = load_library().vpt_default_scene(arr, 10)
     assert n == 10
     return arr
+
+
+def load_scene(path):
+    """a scene file (scenes/*.txt; format: include/vpt.h vpt_load_scene) -> Sphere array"""
+    arr = (Sphere * 32)()
+    lib = load_library()
+    n = lib.vpt_load_scene(os.fsencode(path), arr, 32)
+    if n < 0:
+        _check(lib, n)
+    return (Sphere * n).from_buffer_copy(bytes(arr)[: n * C.sizeof(Sphere)])
 
 
 def scene_from_rows(rows):

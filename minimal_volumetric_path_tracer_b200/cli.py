@@ -18,6 +18,7 @@ def parse_args(argv):
     ap.add_argument("--sigma-s", type=float, default=0.009)
     ap.add_argument("--march-step", type=float, default=0.1, help="--method march: step length (rt.cpp:791)")
     ap.add_argument("--march-source", type=int, default=7, help="--method march: source sphere (rt.cpp:791 passes 7; 8 is the point light)")
+    ap.add_argument("--scene", default=None, help="scene file (scenes/*.txt); default: the reference's active scene, Sphere.cpp:11-22")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--max-depth", type=int, default=0)
     ap.add_argument("--continue-prob", type=float, default=0.6)
@@ -48,7 +49,7 @@ def main(argv=None):
     a = parse_args(sys.argv[1:] if argv is None else argv)
     start = time.time()
     p = params_from_args(a)
-    scene = api.default_scene()
+    scene = api.load_scene(a.scene) if a.scene else api.default_scene()
     if a.gpus > 1:
         hdr, st = api.render_multi(p, scene, list(range(a.gpus)), stats=True)
     else:

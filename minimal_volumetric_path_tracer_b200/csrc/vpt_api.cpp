@@ -317,6 +317,39 @@ int vpt_default_scene(vpt_sphere *out, int32_t cap) {
     return 10;
 }
 
+int vpt_load_scene(const char *path, vpt_sphere *out, int32_t cap) {
+    if (!path || !out || cap <= 0) return VPT_ERR_INVALID_ARGUMENT;
+    std::FILE *f = std::fopen(path, "r");
+    if (!f) return VPT_ERR_IO;
+    int n = 0, rc = VPT_OK;
+    char line[2048];
+    while (rc == VPT_OK && std::fgets(line, sizeof(line), f)) {
+        if (char *hash = std::strchr(line, '#')) *hash = 0;
+        double v[18];
+        int k = 0;
+        char *s = line;
+        for (;;) {
+            while (*s == ' ' || *s == '\t' || *s == ',' || *s == '\r' || *s == '\n') ++s;
+            if (!*s) break;
+            char *end = nullptr;
+            const double x = std::strtod(s, &end);
+            if (end == s || k >= 18) { k = -1; break; }
+            v[k++] = x; s = end;
+        }
+        if (k == 0) continue; // blank or comment line
+        if (k != 18 || n >= cap || v[10] != std::floor(v[10])) { rc = VPT_ERR_SCENE; break; }
+        vpt_sphere &d = out[n++];
+        std::memset(&d, 0, sizeof(d));
+        d.r = v[0];
+        for (int c = 0; c < 3; ++c) { d.p[c] = v[1 + c]; d.c[c] = v[4 + c]; d.radiance[c] = v[7 + c]; d.eta[c] = v[11 + c]; d.kappa[c] = v[14 + c]; }
+        d.material = (int32_t)v[10];
+        d.alpha = v[17];
+    }
+    std::fclose(f);
+    if (rc != VPT_OK) return rc;
+    return n > 0 ? n : VPT_ERR_SCENE;
+}
+
 int vpt_render_device(const vpt_params *p, const vpt_sphere *spheres, int32_t n_spheres, float *hdr_dev, void *cuda_stream, vpt_stats *stats) {
     const double t0 = now_ms();
     int rc = validate_params(p, true);

@@ -2,7 +2,7 @@
 // stderr, "elapsed time: Ns" on stdout; src/rt.cpp:744-830) and replaces its OpenMP pixel loop (rt.cpp:767-805) with one
 // call through the C-ABI of include/vpt.h.  Everything the reference hard-codes is an optional flag here.
 //
-//   rt <spp> [--method free|equi|mis|march] [--march-step x] [--march-source i] [--size WxH] [--sigma-a x] [--sigma-s x] [--seed n] [--ref] [--gpus n]
+//   rt <spp> [--method free|equi|mis|march] [--march-step x] [--march-source i] [--scene file] [--size WxH] [--sigma-a x] [--sigma-s x] [--seed n] [--ref] [--gpus n]
 //            [--max-depth n] [--continue-prob x] [-o image.ppm]
 #include <chrono>
 #include <cstdio>
@@ -14,7 +14,7 @@
 #include "vpt.h"
 
 static int usage() {
-    std::fprintf(stderr, "usage: rt <spp> [--method free|equi|mis|march] [--march-step x] [--march-source i] [--size WxH] [--sigma-a x] [--sigma-s x] [--seed n] [--ref] [--gpus n] "
+    std::fprintf(stderr, "usage: rt <spp> [--method free|equi|mis|march] [--march-step x] [--march-source i] [--scene file] [--size WxH] [--sigma-a x] [--sigma-s x] [--seed n] [--ref] [--gpus n] "
                          "[--max-depth n] [--continue-prob x] [-o image.ppm]\n");
     return 2;
 }
@@ -25,7 +25,7 @@ int main(int argc, char **argv) {
     vpt_params p;
     vpt_default_params(&p);
     p.spp = std::atoi(argv[1]);
-    std::string out = "image.ppm";
+    std::string out = "image.ppm", scene_path;
     int gpus = 1;
     for (int i = 2; i < argc; ++i) {
         const std::string a = argv[i];
@@ -38,6 +38,7 @@ int main(int argc, char **argv) {
         else if (a == "--sigma-s") p.sigma_s = std::atof(val("--sigma-s"));
         else if (a == "--march-step") p.march_step = std::atof(val("--march-step"));   // rt.cpp:791: 0.1
         else if (a == "--march-source") p.march_source = std::atoi(val("--march-source")); // rt.cpp:791: 7
+        else if (a == "--scene") scene_path = val("--scene");   // instead of editing Sphere.cpp and recompiling
         else if (a == "--seed") p.seed = std::strtoull(val("--seed"), nullptr, 10);
         else if (a == "--max-depth") p.max_depth = std::atoi(val("--max-depth"));
         else if (a == "--continue-prob") p.continue_prob = std::atof(val("--continue-prob"));
@@ -47,7 +48,8 @@ int main(int argc, char **argv) {
         else return usage();
     }
     vpt_sphere scene[VPT_MAX_SPHERES];
-    const int n = vpt_default_scene(scene, VPT_MAX_SPHERES); // Sphere.cpp:11-22
+    const int n = scene_path.empty() ? vpt_default_scene(scene, VPT_MAX_SPHERES) /* Sphere.cpp:11-22 */ : vpt_load_scene(scene_path.c_str(), scene, VPT_MAX_SPHERES);
+    if (n < 0) { std::fprintf(stderr, "rt: %s: %s\n", scene_path.c_str(), vpt_strerror(n)); return 1; }
     std::vector<float> hdr((size_t)p.width * p.height * 3);
     vpt_stats st;
     int rc;

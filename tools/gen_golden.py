@@ -4,6 +4,7 @@ oracle/Makefile).  Run in the build container only (the reference tree does not 
   python tools/gen_golden.py units     -> tests/golden/units.npz      unit-function vectors (inputs, explicit uniforms, outputs)
   python tools/gen_golden.py paths     -> tests/golden/paths.npz      per-path radiance on seeded erand48 streams
   python tools/gen_golden.py images    -> tests/golden/image_*.npz    16x16-block statistics of whole renders
+  python tools/gen_golden.py scenes    -> tests/golden/scenes.npz     per-path radiance on the reference's commented alternate scenes (scenes/*.txt)
   python tools/gen_golden.py march     -> tests/golden/march.npz      rayMarching3 (rayMarchingMethods.h:330) on fixed rays
 """
 import os
@@ -213,6 +214,34 @@ def block_stats(total, sq, spp, block=16):
     return m.astype(np.float32), v.astype(np.float32)
 
 
+ALT_SCENES = ["scene2_sigma", "scene3_near_camera", "scene4_area_light", "scene5_infinite", "scene6_two_points"]
+
+
+def gen_scenes():
+    """the UNMODIFIED reference on its five commented alternate scenes (include/Sphere.cpp:27-106, as data in scenes/*.txt): 120 seeded paths per
+    scene and method, as shipped (quirks 3) and with the robust hooks (quirks 0)"""
+    l0 = L0(); l1 = L1(); rng = np.random.default_rng(909)
+    N = 120
+    o, d = rand_rays(rng, l1, N)
+    seeds = rng.integers(0, 65536, (N, 3))
+    out = {"o": o, "d": d, "seeds": seeds}
+    for name in ALT_SCENES:
+        rows = np.loadtxt(os.path.join(ROOT, "scenes", name + ".txt"), comments="#")
+        out["rows_" + name] = rows
+        l0.set_scene(rows)
+        for quirks in (3, 0):
+            l0.set_quirks(quirks)
+            for method in (0, 1, 2):
+                res = np.zeros((N, 4))
+                for i in range(N):
+                    L, nd = l0.radiance(method, o[i], d[i], SA, SS, seed3=tuple(int(s) for s in seeds[i]))
+                    res[i, :3] = L; res[i, 3] = nd
+                out["%s_q%d_m%d" % (name, quirks, method)] = res
+    l0.reset_scene(); l0.set_quirks(3)
+    np.savez_compressed(os.path.join(GOLD, "scenes.npz"), **out)
+    print("scenes.npz written:", len(out), "arrays")
+
+
 def gen_march():
     """rayMarching3 of the UNMODIFIED reference (as shipped: quirks 3) and with the robust hooks (quirks 0) on 96 rays: the literals of the
     commented call rt.cpp:791 (sigma 0.001 / 0.0125, step 0.1, source 7), the point light (source 8) and a coarser step"""
@@ -266,6 +295,8 @@ if __name__ == "__main__":
         gen_units()
     if what in ("paths", "all"):
         gen_paths()
+    if what in ("scenes", "all"):
+        gen_scenes()
     if what in ("march", "all"):
         gen_march()
     if what in ("images", "all"):
