@@ -267,10 +267,12 @@ def main():
     peak_tflops, max_clk = v.measure_fp32_peak(local)
     per_gpu_paths = W * H * SPP
     achieved = per_gpu_paths / (kernel_ms * 1e-3) * FLOP_PER_PATH / 1e12
-    roofline = {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": None,
+    roofline = {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+                "traffic": d2h + 107264,  # bytes per launch: the HDR store + the 107 KB DRAM read of the ncu capture (profiles/r1_smwave_v8_ncu.txt)
+               
                 "kernel": "render_f32_smwave_kernel<%d>" % cfg["method"] if args.precision == "fp32" else "render_f64_kernel", "kernel_ms_per_launch": kernel_ms,
                 "flop_per_path": FLOP_PER_PATH, "peak_source": "measured live: vpt_measure_fp32_peak FFMA chains (MEASURED_PEAKS.json has no FP32 entry; nominal 74.4)",
-                "hbm_note": "algorithmic HBM traffic is the %d-byte HDR store per launch; see profiles/ for dram bytes" % d2h}
+                "hbm_note": "the kernel is FP32-issue bound, not HBM bound: path state lives in shared memory; algorithmic HBM traffic is the %d-byte HDR store per launch (ncu: dram read 107 KB, DRAM throughput 0.00 %%)" % d2h}
     extras = {}
     if args.config == "c2" and args.precision == "fp32":  # short secondary measurements: the other two methods and the FP64 REF mode
         for name, kw, spp in (("free_flight_mpaths_s", dict(method=0), 256), ("mis_mpaths_s", dict(method=2), 256),
