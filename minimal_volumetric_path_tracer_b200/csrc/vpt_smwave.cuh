@@ -1,24 +1,26 @@
-// vpt_smwave.cuh -- SM-wide wavefront FP32 kernel (VPT_KERNEL_WAVEFRONT_SM): one persistent CTA per SM, lock-step stages.
+// vpt_smwave.cuh -- SM-wide wavefront FP32 kernel (VPT_KERNEL_WAVEFRONT_SM, the AUTO kernel): one persistent CTA per SM, path state on chip.
 //
-// Why (profiles/r1_summary.md, "wave v2"): the warp-local wavefront (vpt_wavefront.cuh) fixed SIMT efficiency (28 of 32 lanes
-// active) but only 40 % of the issue slots were used -- 42 % of all stall samples were `no_inst`: sixteen warps per SM, each in a
-// different stage of a 62 KB kernel, thrash the 32 KB L1.5 / 6 KB L0 instruction caches.  Here ALL warps of an SM run the SAME stage
-// at the same time on one shared pool of path records:
-//   * one CTA of kSmThreads threads per SM, grid = number of SMs (persistent); work items = groups of pixel tiles, handed out
-//     statically (item j -> CTA j % gridDim.x), two items in flight per CTA so that a draining item overlaps the next one;
-//   * kSmPool path records in shared memory (SoA, 68 B each), one index queue (ring) per stage;
-//   * work proceeds in ROUNDS: at a barrier thread 0 snapshots every queue's tail and decides how many new camera samples to
-//     generate into the free records; then every warp claims 32-record batches from the snapshot with one shared-memory atomic per
-//     batch -- longest stages first, so the round ends evenly -- runs them and pushes the survivors to the next stage's queue
-//     (warp ballot + one atomic per warp); what is pushed during a round is consumed in the next one.  Batches are full warps
-//     except while a work item drains, so the lanes stay busy, and one round costs two barriers for about 2000 records;
+// Why (profiles/r1_summary.md): the warp-local wavefront (vpt_wavefront.cuh) fixed SIMT efficiency (28 of 32 lanes active) but used only
+// 40 % of the issue slots -- 42 % of all stall samples were `no_inst`: sixteen warps per SM, each in a different stage of a 62 KB
+// kernel, thrash the 32 KB L1.5 / 6 KB L0 instruction caches.  Here the warps of an SM share ONE pool of path records and move through
+// the stages together:
+//   * one CTA of kSmThreads threads per SM, grid = number of SMs (persistent); work items = groups of pixel tiles x all samples, handed
+//     out statically (item j -> CTA j % gridDim.x), two items in flight per CTA so that a draining item overlaps the next one;
+//   * kSmPool path records in shared memory (SoA, 68 B each), one index queue (ring) per stage, one ring of free records;
+//   * work proceeds in ROUNDS: at a barrier warp 0 snapshots every queue's tail (one load of the 20 control words, then shuffles) into a
+//     table of 32-record batches ordered longest stage first; every warp claims batches with ONE shared-memory atomic each, runs them
+//     and routes the survivors to the next stage's ring (match.any groups the lanes by destination: one atomic per group); what is
+//     pushed during a round is consumed in the next one.  Only full batches are handed out while samples remain.  A warp that finds
+//     the table used up generates new camera samples into the free records instead of idling at the barrier (tail fill).  The rank order
+//     also keeps the 24 warps inside two or three stages at a time -- a barrier-free variant lost 40 % to instruction-cache misses;
 //   * queues are split by what diverges: medium vertex with a point / an area source, surface vertex needing the pLight shadow ray,
 //     Lambert / microfacet surface vertex;
-//   * the scene's scan records are staged in shared memory as float4 (broadcast LDS.128); ordinary spheres (r < 64) use the
-//     direct roots -b -+ sqrt(det) with det = r^2 - |op - (op.d)d|^2 (21 instructions per test), huge ones the re-anchored
-//     cancellation-free form of vpt_f32.cuh.
-// Random-number slots, formulas and semantics are exactly those of vpt_f32.cuh (file:line citations there); per-pixel sums use
-// the order-independent 2^-30 fixed-point accumulators of vpt_wavefront.cuh, so images are bit-reproducible.
+//   * the scene's scan records are staged in shared memory as float4 (broadcast LDS.128); ordinary spheres (r < 64) use the direct
+//     roots -b -+ sqrt(det) with det = r^2 - |op - (op.d)d|^2, huge ones the re-anchored cancellation-free form of vpt_f32.cuh; the
+//     nearest accepted root is selected with one three-input unsigned minimum per sphere (see scan_sm_call).
+// Random-number slots, formulas and semantics are exactly those of vpt_f32.cuh (file:line citations there); per-pixel sums are 64-bit
+// fixed-point (2^-30) accumulators in shared memory, built from native 32-bit atomics: integer adds are order independent, so images
+// are bit-reproducible although the order in which paths finish is data dependent.
 #pragma once
 #include "vpt_mega_scan.cuh"
 
@@ -238,14 +240,6 @@ struct SmWave {
         if (lane == 0) base = smem_add(&S.free_head, (unsigned)__popc(m), lz);
         base = __shfl_sync(0xffffffffu, base, 0);
         return flag ? (int)S.freelist[(base + __popc(m & ((1u << lane) - 1u))) & (kSmPool - 1)] : -1;
-    }
-    __device__ __forceinline__ void release(bool flag, int slot) {
-        const unsigned m = __ballot_sync(0xffffffffu, flag);
-        if (m == 0u) return;
-        unsigned base = 0;
-        if (lane == 0) base = smem_add(&S.free_tail, (unsigned)__popc(m), lz);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (flag) S.freelist[(base + __popc(m & ((1u << lane) - 1u))) & (kSmPool - 1)] = (uint16_t)slot;
     }
     // a path ended: add its radiance to the pixel (rt.cpp:794) -- the caller reports it to count_done()
     __device__ __forceinline__ void add_radiance(uint32_t meta, F3 L) {
