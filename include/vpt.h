@@ -57,8 +57,9 @@ enum { VPT_OUTPUT_SUM = 0, VPT_OUTPUT_MEAN = 1 };
  * MEGA = one thread per pixel, one path vertex per loop iteration (scene scans inside divergent shading code);
  * MEGA_SCAN = scan-converged state machine, exactly one scene scan per loop iteration executed by all lanes;
  * WAVEFRONT = on-chip wavefront, one pool of path records and per-stage queues PER WARP in shared memory;
- * WAVEFRONT_SM = on-chip wavefront, one persistent CTA per SM, one pool per SM, all warps run the same stage in lock step. */
-enum { VPT_KERNEL_AUTO = 0, VPT_KERNEL_MEGA = 1, VPT_KERNEL_WAVEFRONT = 2, VPT_KERNEL_MEGA_SCAN = 3, VPT_KERNEL_WAVEFRONT_SM = 4 };
+ * WAVEFRONT_SM = on-chip wavefront, one persistent CTA per SM, one pool per SM, the warps move through the stages together;
+ * WAVEFRONT_HBM = the classic multi-kernel wavefront: SoA path-state queues in HBM, one kernel per stage (synchronises the stream). */
+enum { VPT_KERNEL_AUTO = 0, VPT_KERNEL_MEGA = 1, VPT_KERNEL_WAVEFRONT = 2, VPT_KERNEL_MEGA_SCAN = 3, VPT_KERNEL_WAVEFRONT_SM = 4, VPT_KERNEL_WAVEFRONT_HBM = 5 };
 /* Two behaviours of the reference are decided by FP64 rounding (DESIGN.md "Parity hazards"):
  *  R0_FALLTHROUGH   the in-medium point-light connection is overwritten with 0 whenever the r == 0 sphere registers as
  *                   hit in the solid-angle block (volumetricBasicFunctions.h:310-337 / :251-278);

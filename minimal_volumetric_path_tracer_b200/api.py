@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "libvpt_b200.so")
 METHOD_FREE_FLIGHT, METHOD_EQUIANGULAR, METHOD_MIS, METHOD_RAYMARCH = 0, 1, 2, 3
 PRECISION_FP32, PRECISION_FP64_REF = 0, 1
 OUTPUT_SUM, OUTPUT_MEAN = 0, 1
-KERNEL_AUTO, KERNEL_MEGA, KERNEL_WAVEFRONT, KERNEL_MEGA_SCAN, KERNEL_WAVEFRONT_SM = 0, 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_MEGA, KERNEL_WAVEFRONT, KERNEL_MEGA_SCAN, KERNEL_WAVEFRONT_SM, KERNEL_WAVEFRONT_HBM = 0, 1, 2, 3, 4, 5
 QUIRK_R0_FALLTHROUGH, QUIRK_EXACT_VISIBILITY, QUIRKS_REFERENCE, QUIRKS_NONE = 1, 2, 3, 0
 
 

@@ -20,6 +20,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 UNITS = [
     ("vpt_kernels_f32.cu", ["-prec-div=false", "-prec-sqrt=false", "-ftz=true"]),
+    ("vpt_kernels_hbm.cu", ["-prec-div=false", "-prec-sqrt=false", "-ftz=true"]),
     ("vpt_kernels_f64.cu", ["-fmad=false"]),
     ("vpt_api.cpp", []),
 ]

@@ -78,8 +78,8 @@ int validate_params(const vpt_params *p, bool need_image) {
     if (!finite3(p->cam_o) || !finite3(p->cam_dir) || !(p->fov > 0) || dot(v3(p->cam_dir), v3(p->cam_dir)) == 0) return VPT_ERR_INVALID_ARGUMENT;
     if (p->quirks & ~(uint32_t)VPT_QUIRKS_REFERENCE) return VPT_ERR_INVALID_ARGUMENT;
     if (p->precision == VPT_PRECISION_FP32 && p->quirks != 0) return VPT_ERR_UNSUPPORTED; // rounding-decided behaviours exist in FP64 only
-    if (p->kernel < VPT_KERNEL_AUTO || p->kernel > VPT_KERNEL_WAVEFRONT_SM) return VPT_ERR_INVALID_ARGUMENT;
-    if ((p->kernel == VPT_KERNEL_WAVEFRONT || p->kernel == VPT_KERNEL_WAVEFRONT_SM) && p->precision != VPT_PRECISION_FP32) return VPT_ERR_UNSUPPORTED;
+    if (p->kernel < VPT_KERNEL_AUTO || p->kernel > VPT_KERNEL_WAVEFRONT_HBM) return VPT_ERR_INVALID_ARGUMENT;
+    if ((p->kernel == VPT_KERNEL_WAVEFRONT || p->kernel == VPT_KERNEL_WAVEFRONT_SM || p->kernel == VPT_KERNEL_WAVEFRONT_HBM) && p->precision != VPT_PRECISION_FP32) return VPT_ERR_UNSUPPORTED;
     return VPT_OK;
 }
 
@@ -221,6 +221,7 @@ int enqueue_render(const vpt_params *p, const vpt_sphere *spheres, int n_spheres
         ConstsF cf;
         build_consts_f32(lp, sc.n_emitters, cf);
         if (lp.method == VPT_METHOD_RAYMARCH) rc = launch_march_f32(sc, lp, cf, hdr_dev, counters_dev, stream, blocks);
+        else if (p->kernel == VPT_KERNEL_WAVEFRONT_HBM) { rc = launch_hbmwave_f32(sc, lp, cf, hdr_dev, counters_dev, stream, blocks, launches); if (launches && rc == 0) --*launches; }
         else rc = launch_render_f32(sc, lp, cf, hdr_dev, counters_dev, stream, blocks, p->kernel == VPT_KERNEL_AUTO ? VPT_KERNEL_WAVEFRONT_SM : p->kernel);
     } else {
         SceneD sc;
@@ -265,6 +266,8 @@ cudaError_t scratch_alloc(int device, void **ptr, size_t bytes, cudaStream_t str
 }
 
 } // namespace
+
+int vpt::scratch_alloc_(int device, void **ptr, size_t bytes, void *stream) { return (int)scratch_alloc(device, ptr, bytes, (cudaStream_t)stream); }
 
 #pragma GCC visibility push(default)
 extern "C" {

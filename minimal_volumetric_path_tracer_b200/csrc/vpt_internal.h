@@ -96,6 +96,10 @@ struct Counters { // device-side, accumulated with atomics at thread exit
 };
 
 // entry points implemented in the .cu files, called from vpt_api.cpp
+// multi-kernel HBM wavefront (vpt_kernels_hbm.cu); synchronises the stream internally (it polls a device flag between batches of rounds)
+int launch_hbmwave_f32(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, void *stream, int n_owned_tiles, uint64_t *launches);
+// stream-ordered allocation from the library's per-device scratch pool (vpt_api.cpp); free with cudaFreeAsync
+int scratch_alloc_(int device, void **ptr, size_t bytes, void *stream);
 int launch_march_f32(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks);
 int launch_render_f32(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks, int kernel);
 int launch_render_f64(const SceneD &scene, const LaunchParams &lp, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks);

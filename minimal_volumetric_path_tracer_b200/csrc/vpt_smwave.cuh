@@ -47,21 +47,23 @@ struct SmScene {
     int gid[2 * kMaxSpheres];   // scan order -> caller's sphere index (general ones first)
     int n_ga, n_gb;
 };
-// cooperative staging by the whole block (call, then __syncthreads)
+// cooperative staging by the whole block (call, then __syncthreads).  Scan order: general-form spheres (huge / re-anchored ones and anything
+// with r >= 64) first, in scene order, then the direct-root ones; every scan record finds its place with one pass over its predecessors.
 __device__ __forceinline__ void stage_scene(SmScene &S, const SceneF &sc, int tid, int n_threads) {
     for (int i = tid; i < sc.n_spheres * (int)(sizeof(MatF) / 4); i += n_threads)
         reinterpret_cast<uint32_t *>(S.mats)[i] = reinterpret_cast<const uint32_t *>(sc.mat)[i];
-    if (tid == 0) {
-        int na = 0, nb = 0;
-        for (int pass = 0; pass < 2; ++pass) // general-form spheres (huge / re-anchored ones and anything with r >= 64) first
-            for (int g = 0; g < sc.n_geom; ++g) {
-                const GeomF &G = sc.geom[g];
-                const bool general = G.big || G.r2 >= kSimpleRootMaxR2;
-                if (general != (pass == 0)) continue;
-                if (general) { S.ga[2 * na] = make_float4(G.qx, G.qy, G.qz, G.c0); S.ga[2 * na + 1] = make_float4(G.mx, G.my, G.mz, 0.0f); S.gid[na++] = G.id; }
-                else { S.gb[nb] = make_float4(G.qx, G.qy, G.qz, G.r2); S.gid[na + nb++] = G.id; }
-            }
-        S.n_ga = na; S.n_gb = nb;
+    if (tid < sc.n_geom) {
+        const GeomF &G = sc.geom[tid];
+        const bool general = G.big || G.r2 >= kSimpleRootMaxR2;
+        int before_same = 0, n_general = 0;
+        for (int g = 0; g < sc.n_geom; ++g) {
+            const bool gg = sc.geom[g].big || sc.geom[g].r2 >= kSimpleRootMaxR2;
+            n_general += gg;
+            before_same += (g < tid && gg == general);
+        }
+        if (general) { S.ga[2 * before_same] = make_float4(G.qx, G.qy, G.qz, G.c0); S.ga[2 * before_same + 1] = make_float4(G.mx, G.my, G.mz, 0.0f); S.gid[before_same] = G.id; }
+        else { S.gb[before_same] = make_float4(G.qx, G.qy, G.qz, G.r2); S.gid[n_general + before_same] = G.id; }
+        if (tid == 0) { S.n_ga = n_general; S.n_gb = sc.n_geom - n_general; }
     }
 }
 

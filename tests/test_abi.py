@@ -73,7 +73,7 @@ def test_argument_validation_precedes_device_work(vpt):
     assert _rc(vpt, P(), hdr=False) == INVALID
     assert _rc(vpt, P(quirks=vpt.QUIRKS_REFERENCE)) == UNSUPPORTED          # rounding-decided behaviours are FP64-only
     assert _rc(vpt, P(kernel=9)) == INVALID
-    for wave in (vpt.KERNEL_WAVEFRONT, vpt.KERNEL_WAVEFRONT_SM):      # the on-chip wavefront kernels are FP32 only
+    for wave in (vpt.KERNEL_WAVEFRONT, vpt.KERNEL_WAVEFRONT_SM, vpt.KERNEL_WAVEFRONT_HBM):      # the on-chip wavefront kernels are FP32 only
         assert _rc(vpt, P(kernel=wave, precision=vpt.PRECISION_FP64_REF)) == UNSUPPORTED
     rows = DEFAULT_SCENE.copy(); rows[6, 10] = 2                             # dielectric: outside the hot-path scope
     assert _rc(vpt, P(), vpt.scene_from_rows(rows)) == UNSUPPORTED

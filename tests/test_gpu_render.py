@@ -229,8 +229,8 @@ def test_precision_quirk_contract(gpu):
 # ---- the two FP32 kernel variants compute the same thing -------------------------------------------------------------------
 @pytest.mark.parametrize("method", [0, 1, 2])
 def test_kernel_variants_agree(gpu, l1, method):
-    """MEGA (vertex per iteration), MEGA_SCAN (scan-converged state machine), WAVEFRONT (warp-local queues) and WAVEFRONT_SM (one pool per SM,
-    AUTO): same streams, same decisions up to fp32 rounding (the SM kernel uses the direct roots for small spheres, so a few more near-tie
+    """MEGA (vertex per iteration), MEGA_SCAN (scan-converged state machine), WAVEFRONT (warp-local queues), WAVEFRONT_SM (one pool per SM,
+    AUTO) and WAVEFRONT_HBM (multi-kernel, queues in HBM): same streams, same decisions up to fp32 rounding (the SM kernel uses the direct roots for small spheres, so a few more near-tie
     decisions differ), sums differ by fp32 re-association; all against the oracle"""
     w, h, spp = 160, 120, 16
     p = gpu.default_params(width=w, height=h, spp=spp, method=method, seed=12, output=gpu.OUTPUT_SUM)
@@ -238,15 +238,18 @@ def test_kernel_variants_agree(gpu, l1, method):
     b, sb = gpu.render(p.copy(kernel=gpu.KERNEL_MEGA_SCAN), stats=True)
     c, sc_ = gpu.render(p.copy(kernel=gpu.KERNEL_WAVEFRONT), stats=True)
     d, sd = gpu.render(p.copy(kernel=gpu.KERNEL_WAVEFRONT_SM), stats=True)
-    for other, so in ((b, sb), (c, sc_), (d, sd)):
+    e_, se = gpu.render(p.copy(kernel=gpu.KERNEL_WAVEFRONT_HBM), stats=True)
+    assert se.events == sd.events and se.scene_scans == sd.scene_scans      # the two wavefronts share the stage arithmetic: identical decisions
+    for other, so in ((b, sb), (c, sc_), (d, sd), (e_, se)):
         assert abs(int(sa.events) - int(so.events)) <= 3e-4 * sa.events and sa.scene_scans == pytest.approx(so.scene_scans, rel=2e-3)
         assert so.paths == w * h * spp
         err = np.abs(a - other) / np.maximum(np.abs(a), 1e-3)
         assert np.median(err) < 1e-6 and np.mean(err > 1e-3) < 0.015
-    for kern, img in ((gpu.KERNEL_WAVEFRONT, c), (gpu.KERNEL_WAVEFRONT_SM, d)):  # fixed-point accumulation: order-independent, bit-reproducible
+    for kern, img in ((gpu.KERNEL_WAVEFRONT, c), (gpu.KERNEL_WAVEFRONT_SM, d), (gpu.KERNEL_WAVEFRONT_HBM, e_)):  # fixed-point accumulation: order-independent, bit-reproducible
         assert np.array_equal(img, gpu.render(p.copy(kernel=kern)))
     ref, _, rst = l1.render(DEFAULT_SCENE, 0, method, SA, SS, w, h, 12, spp, want_sumsq=False)
-    for img in (a, b, c, d):
+    assert np.array_equal(d, e_)   # same paths, same fixed-point sums: the HBM wavefront reproduces the on-chip one bit for bit
+    for img in (a, b, c, d, e_):
         e = np.abs(img - ref) / np.maximum(np.abs(ref), 1e-3)
         assert np.median(e) < 2e-6 and np.mean(e > 1e-3) < 0.02
 

@@ -13,7 +13,7 @@ ap.add_argument("--width", type=int, default=1024); ap.add_argument("--height", 
 ap.add_argument("--config", default="default"); ap.add_argument("--kernel", default="auto")
 a = ap.parse_args()
 kw = dict(sigma_a=0.0005, sigma_s=0.0495, continue_prob=0.95, max_depth=64) if a.config == "c4" else {}
-p = v.default_params(width=a.width, height=a.height, spp=a.spp, method=a.method, seed=1, kernel={"auto": v.KERNEL_AUTO, "mega": v.KERNEL_MEGA, "scan": v.KERNEL_MEGA_SCAN, "wave": v.KERNEL_WAVEFRONT, "smwave": v.KERNEL_WAVEFRONT_SM}[a.kernel], **kw)
+p = v.default_params(width=a.width, height=a.height, spp=a.spp, method=a.method, seed=1, kernel={"auto": v.KERNEL_AUTO, "mega": v.KERNEL_MEGA, "scan": v.KERNEL_MEGA_SCAN, "wave": v.KERNEL_WAVEFRONT, "smwave": v.KERNEL_WAVEFRONT_SM, "hbm": v.KERNEL_WAVEFRONT_HBM}[a.kernel], **kw)
 if a.precision != "fp32":
     p.precision = v.PRECISION_FP64_REF; p.quirks = v.QUIRKS_REFERENCE
 for _ in range(a.reps):

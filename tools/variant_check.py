@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT)
 import minimal_volumetric_path_tracer_b200 as v
 if os.environ.get("VPT_LIB"):  # development only: time an experimental build of the library
     v.api.LIB_PATH = os.path.abspath(os.environ["VPT_LIB"])
-kern = {"mega": v.KERNEL_MEGA, "scan": v.KERNEL_MEGA_SCAN, "wave": v.KERNEL_WAVEFRONT, "smwave": v.KERNEL_WAVEFRONT_SM}[sys.argv[1]]
+kern = {"mega": v.KERNEL_MEGA, "scan": v.KERNEL_MEGA_SCAN, "wave": v.KERNEL_WAVEFRONT, "smwave": v.KERNEL_WAVEFRONT_SM, "hbm": v.KERNEL_WAVEFRONT_HBM}[sys.argv[1]]
 w, h, spp = (int(x) for x in sys.argv[2:5]) if len(sys.argv) > 4 else (160, 120, 16)
 ok = True
 for method in (0, 1, 2):
