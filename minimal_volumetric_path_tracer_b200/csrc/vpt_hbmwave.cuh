@@ -105,7 +105,7 @@ struct HbmCtx { // what every stage needs
                 dist = -logf(1.0f - u32_to_unit_f32(r.r2)) * k.inv_sigma_t;
                 surface = dist > t;
             } else {
-                const float Tr = expf(-k.sigma_t * t);
+                const float Tr = __expf(-k.sigma_t * t);
                 float D, dth, tl;
                 dist = equiangular_sample(mk(sm.px, sm.py, sm.pz), r.o, r.d, t, u32_to_unit_f32(r.r2), D, dth, tl);
                 inv_pdf = dth * (tl * tl + D * D) / (D * (1.0f - Tr));
@@ -124,7 +124,7 @@ struct HbmCtx { // what every stage needs
                 r.r1 = (uint32_t)src | ((uint32_t)hid << 8);
             } else {
                 r.o = fma3(r.d, dist, r.o);
-                const float w = (METHOD == 0) ? k.albedo_over_cp : k.sigma_s * expf(-k.sigma_t * fabsf(dist)) * inv_pdf * k.inv_cp;
+                const float w = (METHOD == 0) ? k.albedo_over_cp : k.sigma_s * __expf(-k.sigma_t * fabsf(dist)) * inv_pdf * k.inv_cp;
                 r.r2 = __float_as_uint(w);
                 r.r1 = (uint32_t)src;
                 dest = sm.r == 0.0f ? SQ_MED_POINT : SQ_MED_AREA;
@@ -145,7 +145,7 @@ struct HbmCtx { // what every stage needs
         F3 qo, qd, C; float lim = 0.0f;
         if (POINT) {
             const float dist = d2 * inv;
-            C = had(mk(sm.lr, sm.lg, sm.lb), r.beta) * (expf(-k.sigma_t * dist) / d2 * k.n_emitters * kInv4Pi * w);
+            C = had(mk(sm.lr, sm.lg, sm.lb), r.beta) * (__expf(-k.sigma_t * dist) / d2 * k.n_emitters * kInv4Pi * w);
             qo = light; qd = lx * (-inv); lim = dist * (1.0f - 1e-4f);
         } else {
             const float omc_max = one_minus_cos_max(sm.r * sm.r / d2);
@@ -158,7 +158,7 @@ struct HbmCtx { // what every stage needs
         if (act) {
             ++scans;
             if (POINT) { if (!hit || t > lim) r.L = r.L + C; }
-            else if (hit && hid == src) r.L = r.L + C * expf(-k.sigma_t * t);
+            else if (hit && hid == src) r.L = r.L + C * __expf(-k.sigma_t * t);
         }
         r.d = phase_sample(u32_to_unit_f32(b1.z), u32_to_unit_f32(b1.w));
         r.beta = r.beta * w;
@@ -179,7 +179,7 @@ struct HbmCtx { // what every stage needs
         const bool facet = obj.material == 1;
         F3 f = mk(obj.cr, obj.cg, obj.cb) * kInvPi;
         if (facet) { const Frame fr = make_frame(n_); f = brdf_eval(obj, unit(to_local(fr, wi)), unit(to_local(fr, -r.d))); }
-        const F3 C = had(had(mk(sm.lr, sm.lg, sm.lb), f), r.beta) * (dot(n_, wi) * expf(-k.sigma_t * dist) / d2 * k.n_emitters * k.inv_cp);
+        const F3 C = had(had(mk(sm.lr, sm.lg, sm.lb), f), r.beta) * (dot(n_, wi) * __expf(-k.sigma_t * dist) / d2 * k.n_emitters * k.inv_cp);
         float t; int hid;
         const bool hit = scan_sm(S, light, lx * (-inv), t, hid);
         if (act) {
@@ -223,7 +223,7 @@ struct HbmCtx { // what every stage needs
                     if (FACET) { const F3 wi_l = unit(to_local(fr, wi)); const F3 wh = unit(wi_l + wo_l); f = facet_brdf(obj, wi_l, wh, wo_l); gpdf = facet_pdf(wo_l, wh, obj.alpha); }
                     const float inv_fpdf = kTwoPi * omc_max;
                     const float wmis = power_heuristic(1.0f / inv_fpdf, gpdf);
-                    L = L + had(had(mk(sm.lr, sm.lg, sm.lb), f), beta) * (cos_i * inv_fpdf * expf(-k.sigma_t * len2 * inv_len) * wmis * k.inv_cp);
+                    L = L + had(had(mk(sm.lr, sm.lg, sm.lb), f), beta) * (cos_i * inv_fpdf * __expf(-k.sigma_t * len2 * inv_len) * wmis * k.inv_cp);
                 }
             }
         }

@@ -349,7 +349,7 @@ struct SmWave {
                 dist = -logf(1.0f - u32_to_unit_f32(S.r2[s])) * k.inv_sigma_t; // freeFlightSample, vptSamplingFunctions.h:11
                 surface = dist > t;
             } else { // equiAngularParams2 (volumetricBasicFunctions.h:209-223) + equiAngularProb (vptSamplingFunctions.h:60)
-                const float Tr = expf(-k.sigma_t * t);
+                const float Tr = __expf(-k.sigma_t * t);
                 float D, dth, tl;
                 dist = equiangular_sample(mk(sm.px, sm.py, sm.pz), o, d, t, u32_to_unit_f32(S.r2[s]), D, dth, tl);
                 inv_pdf = dth * (tl * tl + D * D) / (D * (1.0f - Tr));
@@ -370,7 +370,7 @@ struct SmWave {
                 S.r1[s] = (uint32_t)src | ((uint32_t)hid << 8);
             } else {
                 o = fma3(d, dist, o);
-                const float w = (METHOD == 0) ? k.albedo_over_cp : k.sigma_s * expf(-k.sigma_t * fabsf(dist)) * inv_pdf * k.inv_cp;
+                const float w = (METHOD == 0) ? k.albedo_over_cp : k.sigma_s * __expf(-k.sigma_t * fabsf(dist)) * inv_pdf * k.inv_cp;
                 S.r2[s] = __float_as_uint(w);
                 S.r1[s] = (uint32_t)src;
                 to_mp = sm.r == 0.0f; to_ma = !to_mp;
@@ -401,7 +401,7 @@ struct SmWave {
         F3 qo, qd, C; float lim = 0.0f;
         if (POINT) {
             const float dist = d2 * inv;
-            C = had(mk(sm.lr, sm.lg, sm.lb), beta) * (expf(-k.sigma_t * dist) / d2 * k.n_emitters * kInv4Pi * w);
+            C = had(mk(sm.lr, sm.lg, sm.lb), beta) * (__expf(-k.sigma_t * dist) / d2 * k.n_emitters * kInv4Pi * w);
             qo = light; qd = lx * (-inv); lim = dist * (1.0f - 1e-4f);
         } else {
             const float omc_max = one_minus_cos_max(sm.r * sm.r / d2);
@@ -414,7 +414,7 @@ struct SmWave {
         if (act) {
             ++scans;
             if (POINT) { if (!hit || t > lim) L = L + C; }
-            else if (hit && hid == src) L = L + C * expf(-k.sigma_t * t);
+            else if (hit && hid == src) L = L + C * __expf(-k.sigma_t * t);
         }
         const F3 d = phase_sample(u32_to_unit_f32(b1.z), u32_to_unit_f32(b1.w));
         beta = beta * w;
@@ -439,7 +439,7 @@ struct SmWave {
         const bool facet = obj.material == 1;
         F3 f = mk(obj.cr, obj.cg, obj.cb) * kInvPi;
         if (facet) f = facet_eval_world(obj, n_, wi, d);
-        const F3 C = had(had(mk(sm.lr, sm.lg, sm.lb), f), beta) * (dot(n_, wi) * expf(-k.sigma_t * dist) / d2 * k.n_emitters * k.inv_cp);
+        const F3 C = had(had(mk(sm.lr, sm.lg, sm.lb), f), beta) * (dot(n_, wi) * __expf(-k.sigma_t * dist) / d2 * k.n_emitters * k.inv_cp);
         const F3 qd = lx * (-inv);
         float t; int hid;
         const bool hit = scan_sm(S.scene, light, qd, t, hid);
@@ -496,7 +496,7 @@ struct SmWave {
                     if (FACET) { const F3 wi_l = unit(to_local(fr, wi)); const F3 wh = unit(wi_l + wo_l); f = facet_brdf(obj, wi_l, wh, wo_l); gpdf = facet_pdf(wo_l, wh, obj.alpha); }
                     const float inv_fpdf = kTwoPi * omc_max;
                     const float wmis = power_heuristic(1.0f / inv_fpdf, gpdf);
-                    L = L + had(had(mk(sm.lr, sm.lg, sm.lb), f), beta) * (cos_i * inv_fpdf * expf(-k.sigma_t * len2 * inv_len) * wmis * k.inv_cp);
+                    L = L + had(had(mk(sm.lr, sm.lg, sm.lb), f), beta) * (cos_i * inv_fpdf * __expf(-k.sigma_t * len2 * inv_len) * wmis * k.inv_cp);
                 }
             }
         }
