@@ -95,17 +95,23 @@ __device__ __forceinline__ Frame make_frame(F3 n) {
 __device__ __forceinline__ F3 to_local(const Frame &f, F3 w) { return mk(dot(f.s, w), dot(f.t, w), dot(f.n, w)); } // coordinateTraspose :21-30
 __device__ __forceinline__ F3 to_world(const Frame &f, F3 l) { return fma3(f.s, l.x, fma3(f.t, l.y, f.n * l.z)); }
 
+// sin / cos of 2 pi x for x in (0, 1): MUFU.SIN / MUFU.COS after an exact range reduction to (-pi, pi] (absolute error ~5e-7)
+__device__ __forceinline__ void fast_sincos2pi(float x, float &s, float &c) {
+    const float a = (x - rintf(x)) * kTwoPi; // x - round(x) is exact
+    s = __sinf(a); c = __cosf(a);
+}
+
 // ---- sampling ------------------------------------------------------------------------------------------------------
 // isotropicPhaseSample (vptSamplingFunctions.h:34-46): cos = 1 - 2 xi1, sin = 2 sqrt(xi1 (1 - xi1)), phi = 2 pi xi2
 __device__ __forceinline__ F3 phase_sample(float xi1, float xi2) {
     const float c = 1.0f - 2.0f * xi1, s = 2.0f * sqrtf(xi1 * (1.0f - xi1));
-    float sp, cp; sincospif(2.0f * xi2, &sp, &cp);
+    float sp, cp; fast_sincos2pi(xi2, sp, cp);
     return mk(s * cp, s * sp, c);
 }
 // cosineHemispheric (samplingFunctions.h:47-62): cos = sqrt(1 - xi1), sin = sqrt(xi1); local direction
 __device__ __forceinline__ F3 cosine_local(float xi1, float xi2) {
     const float c = sqrtf(1.0f - xi1), s = sqrtf(xi1);
-    float sp, cp; sincospif(2.0f * xi2, &sp, &cp);
+    float sp, cp; fast_sincos2pi(xi2, sp, cp);
     return mk(s * cp, s * sp, c);
 }
 // uniform cone: solidAngle (samplingFunctions.h:65-82) with 1 - cos(theta_max) given exactly (omc_max), so that the
@@ -113,7 +119,7 @@ __device__ __forceinline__ F3 cosine_local(float xi1, float xi2) {
 __device__ __forceinline__ F3 cone_sample(F3 axis, float omc_max, float xi1, float xi2) {
     const float omc = xi1 * omc_max;
     const float c = 1.0f - omc, s = sqrtf(omc * (2.0f - omc));
-    float sp, cp; sincospif(2.0f * xi2, &sp, &cp);
+    float sp, cp; fast_sincos2pi(xi2, sp, cp);
     const Frame f = make_frame(axis);
     return unit(to_world(f, mk(s * cp, s * sp, c)));
 }
@@ -181,7 +187,7 @@ __device__ __forceinline__ F3 facet_brdf(const MatF &m, F3 wi, F3 wh, F3 wo) { /
 __device__ __forceinline__ F3 facet_normal(float alpha, float xi1, float xi2) {
     const float t2 = -alpha * alpha * logf(1.0f - xi1);
     const float c = rsqrtf(1.0f + t2), s = sqrtf(t2) * c;
-    float sp, cp; sincospif(2.0f * xi2, &sp, &cp);
+    float sp, cp; fast_sincos2pi(xi2, sp, cp);
     return mk(s * cp, s * sp, c);
 }
 
