@@ -35,7 +35,7 @@ CONFIGS = {  # BASELINE.json configs, SURVEY.md section 8d
                sigma_a=0.0005, sigma_s=0.0495, continue_prob=0.95, max_depth=64),
     "c5": dict(name="C5 default scene, MIS, 3840x2160 @ 16384 spp", method=2, width=3840, height=2160, spp=16384),
 }
-METHOD_NAMES = {0: "free-flight", 1: "equi-angular", 2: "mis"}
+METHOD_NAMES = {0: "free-flight", 1: "equi-angular", 2: "mis", 4: "mis-distance"}
 
 
 def env_int(name, default):
@@ -275,7 +275,7 @@ def main():
                 "hbm_note": "the kernel is FP32-issue bound, not HBM bound: path state lives in shared memory; algorithmic HBM traffic is the %d-byte HDR store per launch (ncu: dram read 107 KB, DRAM throughput 0.00 %%)" % d2h}
     extras = {}
     if args.config == "c2" and args.precision == "fp32":  # short secondary measurements: the other two methods and the FP64 REF mode
-        for name, kw, spp in (("free_flight_mpaths_s", dict(method=0), 256), ("mis_mpaths_s", dict(method=2), 256),
+        for name, kw, spp in (("free_flight_mpaths_s", dict(method=0), 256), ("mis_mpaths_s", dict(method=2), 256), ("mis_distance_mpaths_s", dict(method=4), 256),
                               ("fp64_ref_mode_equi_mpaths_s", dict(method=1, precision=v.PRECISION_FP64_REF, quirks=v.QUIRKS_REFERENCE), 64)):
             q = v.default_params(width=W, height=H, spp=spp, seed=1, device=local, **kw)
             st = v.Stats()

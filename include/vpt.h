@@ -49,8 +49,14 @@ typedef struct {
 
 /* RAYMARCH = rayMarching3 (rayMarchingMethods.h:330-384, the commented line rt.cpp:791): deterministic constant-step Riemann sum of
  * the single scattering from ONE source (vpt_params.march_source, treated as a point at its centre) along the camera ray up to the
- * first surface; only the pixel jitter is random.  A noise-free check of the medium next-event term. */
-enum { VPT_METHOD_FREE_FLIGHT = 0, VPT_METHOD_EQUIANGULAR = 1, VPT_METHOD_MIS = 2, VPT_METHOD_RAYMARCH = 3 };
+ * first surface; only the pixel jitter is random.  A noise-free check of the medium next-event term.
+ * MIS_DISTANCE is NOT in the reference: the reference's "MIS" method (vptShadeMethods.h:1345) is numerically its equi-angular
+ * estimator again.  MIS_DISTANCE is the combination its name promises: per vertex ONE of the two distance techniques -- free flight
+ * (freeFlightSample, vptSamplingFunctions.h:11) or equi-angular towards the picked source (equiAngularParams2, volumetricBasicFunctions.h:209) --
+ * is chosen with probability 1/2 and weighted with the balance heuristic (the sample is divided by the mean of the two densities); everything
+ * else (roulette, surface shading, next-event estimation, random-number slots) is method 1's.  Same expectation as methods 0-2, lower variance
+ * than either. */
+enum { VPT_METHOD_FREE_FLIGHT = 0, VPT_METHOD_EQUIANGULAR = 1, VPT_METHOD_MIS = 2, VPT_METHOD_RAYMARCH = 3, VPT_METHOD_MIS_DISTANCE = 4 };
 enum { VPT_PRECISION_FP32 = 0, VPT_PRECISION_FP64_REF = 1 };
 enum { VPT_OUTPUT_SUM = 0, VPT_OUTPUT_MEAN = 1 };
 /* FP32 kernel variants (DESIGN.md "Kernels"), same results to fp32 rounding, AUTO = the fastest by measurement (profiles/):
@@ -156,6 +162,9 @@ typedef enum {
     VPT_UNIT_RADIANCE_LIST = 18,   /* the three shade methods on an EXPLICIT list of uniforms (e.g. the reference's erand48 sequence)
                                       in: o[3], d[3], n_u, u[120]                                      out: L[3], draws used (-1: list too short) */
     VPT_UNIT_RAYMARCH = 19,        /* rayMarchingMethods.h:330   in: o[3], d[3], step, source_index (sigma_* from `p`)            out: L[3], steps */
+    VPT_UNIT_MIS_DISTANCE = 20,    /* VPT_METHOD_MIS_DISTANCE's distance decision (not in the reference; free-flight vptSamplingFunctions.h:11-20 and
+                                      equi-angular volumetricBasicFunctions.h:209 + vptSamplingFunctions.h:60 under the balance heuristic)
+                                      in: source_index, tMax, o[3], d[3], sigma_t, xi, xd                out: surface (0/1), distance, mixture pdf */
     VPT_UNIT_COUNT_
 } vpt_unit_fn;
 int vpt_unit(int32_t fn, const vpt_params *p, const vpt_sphere *spheres, int32_t n_spheres, int32_t n, const double *in, int32_t in_stride,

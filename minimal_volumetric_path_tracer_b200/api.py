@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvpt_b200.so")
 
-METHOD_FREE_FLIGHT, METHOD_EQUIANGULAR, METHOD_MIS, METHOD_RAYMARCH = 0, 1, 2, 3
+METHOD_FREE_FLIGHT, METHOD_EQUIANGULAR, METHOD_MIS, METHOD_RAYMARCH, METHOD_MIS_DISTANCE = 0, 1, 2, 3, 4
 PRECISION_FP32, PRECISION_FP64_REF = 0, 1
 OUTPUT_SUM, OUTPUT_MEAN = 0, 1
 KERNEL_AUTO, KERNEL_MEGA, KERNEL_WAVEFRONT, KERNEL_MEGA_SCAN, KERNEL_WAVEFRONT_SM, KERNEL_WAVEFRONT_HBM = 0, 1, 2, 3, 4, 5
@@ -17,7 +17,7 @@ QUIRK_R0_FALLTHROUGH, QUIRK_EXACT_VISIBILITY, QUIRKS_REFERENCE, QUIRKS_NONE = 1,
 
 class UNIT:
     SPHERE_INTERSECT, INTERSECT, VISIBILITY, TRANSMITTANCE, FREE_FLIGHT, PHASE_SAMPLE, EQUIANGULAR, POWER_HEURISTIC = range(8)
-    COSINE_HEMISPHERE, CONE_SAMPLE, MICROFACET, FACET_NORMAL, MEDIUM_NEE, POINT_LIGHT, SURFACE_MIS, BSDF_SAMPLE, RADIANCE, CAMERA_RAY, RADIANCE_LIST, RAYMARCH = range(8, 20)
+    COSINE_HEMISPHERE, CONE_SAMPLE, MICROFACET, FACET_NORMAL, MEDIUM_NEE, POINT_LIGHT, SURFACE_MIS, BSDF_SAMPLE, RADIANCE, CAMERA_RAY, RADIANCE_LIST, RAYMARCH, MIS_DISTANCE = range(8, 21)
 
 
 class Sphere(C.Structure):  # vpt_sphere

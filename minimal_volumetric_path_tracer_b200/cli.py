@@ -6,7 +6,8 @@ import time
 
 from . import api
 
-METHODS = {"free": api.METHOD_FREE_FLIGHT, "equi": api.METHOD_EQUIANGULAR, "mis": api.METHOD_MIS, "march": api.METHOD_RAYMARCH}
+METHODS = {"free": api.METHOD_FREE_FLIGHT, "equi": api.METHOD_EQUIANGULAR, "mis": api.METHOD_MIS, "march": api.METHOD_RAYMARCH,
+           "mis-distance": api.METHOD_MIS_DISTANCE}  # not in the reference: one-sample MIS of the free-flight and equi-angular distance techniques
 
 
 def parse_args(argv):

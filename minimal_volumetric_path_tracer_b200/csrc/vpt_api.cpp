@@ -70,7 +70,7 @@ int validate_params(const vpt_params *p, bool need_image) {
         if (!all_tiles && (p->tile_count <= 0 || p->tile_rank < 0 || p->tile_rank >= p->tile_count)) return VPT_ERR_INVALID_ARGUMENT;
         if (p->output != VPT_OUTPUT_SUM && p->output != VPT_OUTPUT_MEAN) return VPT_ERR_INVALID_ARGUMENT;
     }
-    if (p->method < 0 || p->method > VPT_METHOD_RAYMARCH) return VPT_ERR_INVALID_ARGUMENT;
+    if (p->method < 0 || p->method > VPT_METHOD_MIS_DISTANCE) return VPT_ERR_INVALID_ARGUMENT;
     if (p->method == VPT_METHOD_RAYMARCH && (!(p->march_step > 0) || !std::isfinite(p->march_step) || p->march_source < 0 || p->march_source >= kMaxSpheres)) return VPT_ERR_INVALID_ARGUMENT;
     if (p->precision != VPT_PRECISION_FP32 && p->precision != VPT_PRECISION_FP64_REF) return VPT_ERR_INVALID_ARGUMENT;
     if (!(p->sigma_a >= 0) || !(p->sigma_s >= 0) || !(p->sigma_a + p->sigma_s > 0) || !std::isfinite(p->sigma_a + p->sigma_s)) return VPT_ERR_INVALID_ARGUMENT;
@@ -515,7 +515,7 @@ int vpt_write_ppm(const float *hdr_rgb, int32_t width, int32_t height, const cha
 
 // ---- unit kernels -----------------------------------------------------------------------------------------------------------------
 static const int kUnitStrides[VPT_UNIT_COUNT_][2] = {
-    {7, 1}, {6, 3}, {6, 1}, {7, 1}, {2, 4}, {2, 3}, {9, 6}, {2, 1}, {5, 4}, {7, 4}, {13, 6}, {3, 3}, {10, 3}, {11, 3}, {19, 3}, {9, 6}, {8, 4}, {4, 3}, {127, 4}, {8, 4},
+    {7, 1}, {6, 3}, {6, 1}, {7, 1}, {2, 4}, {2, 3}, {9, 6}, {2, 1}, {5, 4}, {7, 4}, {13, 6}, {3, 3}, {10, 3}, {11, 3}, {19, 3}, {9, 6}, {8, 4}, {4, 3}, {127, 4}, {8, 4}, {11, 3},
 };
 int vpt_unit_strides(int32_t fn, int32_t *in_stride, int32_t *out_stride) {
     if (fn < 0 || fn >= VPT_UNIT_COUNT_) return VPT_ERR_INVALID_ARGUMENT;

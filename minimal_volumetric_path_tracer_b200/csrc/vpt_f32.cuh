@@ -145,6 +145,36 @@ __device__ __forceinline__ float equiangular_sample(F3 light, F3 o, F3 d, float 
     return t_local + proj;
 }
 
+// VPT_METHOD_MIS_DISTANCE (not in the reference, whose "MIS" method :1345 is the equi-angular estimator again):
+// one-sample MIS of the reference's two distance techniques with the balance heuristic.  Both end at the surface with probability
+// Tr = exp(-sigma_t t) and otherwise place a medium vertex on [0, t): free flight with density sigma_t exp(-sigma_t s)
+// (freeFlightProb, vptSamplingFunctions.h:20), equi-angular with equiAngularProb(s) (1 - Tr) (:60, vptShadeMethods.h:1093).  xd < Tr: surface
+// (returns true); xd < (1 + Tr) / 2: free flight restricted to [0, t), s = -log(1 - xi (1 - Tr)) / sigma_t; else the equi-angular sample.
+// inv_pdf = 1 / mixture density = 2 / (sigma_t exp(-sigma_t s) + equiAngularProb(s) (1 - Tr)); the medium vertex then goes through method
+// 1's code.  Restated in FP64 in oracle/vpt_oracle.hpp::mis_distance.
+__device__ __forceinline__ bool mis_distance(F3 light, F3 o, F3 d, float tmax, float Tr, float sigma_t, float inv_sigma_t, float xi, float xd, float &dist, float &inv_pdf) {
+    dist = 0.0f; inv_pdf = 1.0f;
+    if (xd < Tr) return true;
+    const F3 dv = light - o;
+    const float proj = dot(dv, d);
+    const F3 perp = fma3(d, -proj, dv);
+    const float D2 = dot(perp, perp), D = sqrtf(D2);
+    const float a = -proj, b = fminf(tmax, 1e18f) - proj; // as equiangular_sample
+    const float dtheta = atan2f((b - a) * D, fmaf(a, b, D2));
+    float tl;
+    if (xd < fmaf(0.5f, Tr, 0.5f)) {
+        dist = -logf(1.0f - xi * (1.0f - Tr)) * inv_sigma_t;
+        tl = dist - proj;
+    } else {
+        const float tau = tanf(xi * dtheta);
+        tl = D * fmaf(D, tau, a) / fmaf(-a, tau, D);
+        dist = tl + proj;
+    }
+    const float p_free = sigma_t * expf(-sigma_t * dist), p_equi = D * (1.0f - Tr) / (dtheta * fmaf(tl, tl, D2));
+    inv_pdf = 2.0f / (p_free + p_equi);
+    return false;
+}
+
 // ---- Beckmann conductor microfacet model (microFacetUtilities.h), local frame n = +z ----------------------------------
 __device__ __forceinline__ float fresnel_channel(float c, float s2, float eta, float kappa) { // fresnelSpectre :11-18 (s2 = sin^2)
     const float e2k2 = eta * eta - kappa * kappa - s2;
@@ -348,6 +378,9 @@ __device__ __forceinline__ bool vertex(const SceneF &sc, const MatF *mats, const
     if (METHOD == 0) {
         dist = -logf(1.0f - rng.next_f32(S_DIST)) * k.inv_sigma_t; // freeFlightSample, vptSamplingFunctions.h:11
         surface = dist > t;
+    } else if (METHOD == 4) {
+        const float xi = rng.next_f32(S_DIST);
+        surface = mis_distance(mk(src.px, src.py, src.pz), p.o, p.d, t, expf(-k.sigma_t * t), k.sigma_t, k.inv_sigma_t, xi, rng.next_f32(S_DECIDE), dist, inv_pdf);
     } else {
         // equiAngularParams2 (volumetricBasicFunctions.h:209-223) + equiAngularProb (vptSamplingFunctions.h:60)
         const float Tr = expf(-k.sigma_t * t); // TrActual :1046 / psurf :1407 (0 on a miss)

@@ -353,6 +353,25 @@ __device__ __forceinline__ D3 medium_direct(const Ctx &c, D3 xt, int source, dou
     return Ld;
 }
 
+// VPT_METHOD_MIS_DISTANCE: one-sample MIS (balance heuristic) of the free-flight and equi-angular distance techniques -- not in the
+// reference; the FP64 form of vpt_f32.cuh::mis_distance, statement by statement oracle/vpt_oracle.hpp::mis_distance.  Returns true for a
+// surface vertex; otherwise the distance and the mixture density.
+__device__ __forceinline__ bool mis_distance(D3 light, D3 o, D3 d, double t, double sigma_t, double xi, double xd, double &dist, double &pdf) {
+    dist = 0; pdf = 1;
+    const double Tr = exp(sigma_t * t * -1.0);
+    if (xd < Tr) return true;
+    const D3 dv = light - o;
+    const double len = sqrt(dot(dv, dv));
+    const double proj = dot(dv, d) / dot(d, d);
+    const double D = sqrt(len * len - proj * proj);
+    const double thA = atan2(0.0 - proj, D), thB = atan2(t - proj, D);
+    double t_local;
+    if (xd < 0.5 + 0.5 * Tr) { dist = -log(1 - xi * (1 - Tr)) / sigma_t; t_local = dist - proj; }
+    else { t_local = D * tan((1 - xi) * thA + xi * thB); dist = t_local + proj; }
+    pdf = 0.5 * (sigma_t * exp(sigma_t * dist * -1.0) + D / fabs(thB - thA) / (t_local * t_local + D * D) * (1.0 - Tr));
+    return false;
+}
+
 struct Path { D3 o, d, beta, L; int depth; };
 
 // one vertex after a successful roulette draw; vptShadeMethods.h:1263-1340 / :1014-1149 / :1345-1481 in throughput form
@@ -376,6 +395,9 @@ __device__ __forceinline__ bool vertex(const Ctx &c, Path &p, RngT &rng, Tally &
     if (c.method == 0) {
         dist = -log(1 - rng.next_f64(S_DIST)) / c.sigma_t;
         surface = dist > t;
+    } else if (c.method == 4) {
+        const double xi = rng.next_f64(S_DIST);
+        surface = mis_distance(pos(c.s[source]), p.o, p.d, t, c.sigma_t, xi, rng.next_f64(S_DECIDE), dist, pdf_medium);
     } else {
         if (c.method == 2) Tr = exp(c.sigma_t * t * -1.0);
         // equiAngularParams2, volumetricBasicFunctions.h:209-223

@@ -104,6 +104,8 @@ struct HbmCtx { // what every stage needs
             if (METHOD == 0) {
                 dist = -logf(1.0f - u32_to_unit_f32(r.r2)) * k.inv_sigma_t;
                 surface = dist > t;
+            } else if (METHOD == 4) { // distance-sampling MIS (vpt_f32.cuh mis_distance)
+                surface = mis_distance(mk(sm.px, sm.py, sm.pz), r.o, r.d, t, __expf(-k.sigma_t * t), k.sigma_t, k.inv_sigma_t, u32_to_unit_f32(r.r2), u32_to_unit_f32(r.r3), dist, inv_pdf);
             } else {
                 const float Tr = __expf(-k.sigma_t * t);
                 float D, dth, tl;

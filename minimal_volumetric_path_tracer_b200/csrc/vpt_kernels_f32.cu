@@ -269,24 +269,28 @@ int launch_render_f32(const SceneF &scene, const LaunchParams &lp, const ConstsF
         switch (lp.method) {
         case 0: render_f32_kernel<0><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
         case 1: render_f32_kernel<1><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
+        case 4: render_f32_kernel<4><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
         default: render_f32_kernel<2><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
         }
     } else if (kernel == VPT_KERNEL_WAVEFRONT_SM) {
         switch (lp.method) {
         case 0: return launch_smwave<0>(scene, lp, cf, hdr_dev, counters_dev, st, n_blocks);
         case 1: return launch_smwave<1>(scene, lp, cf, hdr_dev, counters_dev, st, n_blocks);
+        case 4: return launch_smwave<4>(scene, lp, cf, hdr_dev, counters_dev, st, n_blocks);
         default: return launch_smwave<2>(scene, lp, cf, hdr_dev, counters_dev, st, n_blocks);
         }
     } else if (kernel == VPT_KERNEL_WAVEFRONT) {
         switch (lp.method) {
         case 0: render_f32_wave_kernel<0><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
         case 1: render_f32_wave_kernel<1><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
+        case 4: render_f32_wave_kernel<4><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
         default: render_f32_wave_kernel<2><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
         }
     } else {
         switch (lp.method) {
         case 0: render_f32_scan_kernel<0><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
         case 1: render_f32_scan_kernel<1><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
+        case 4: render_f32_scan_kernel<4><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
         default: render_f32_scan_kernel<2><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
         }
     }
@@ -358,6 +362,13 @@ __global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const
         o[0] = D; o[1] = thA; o[2] = thA + dth; o[3] = tl; o[4] = dist;
         o[5] = D / (dth * (tl * tl + D * D));
     } break;
+    case VPT_UNIT_MIS_DISTANCE: {
+        const MatF &src = mats[(int)a[0]];
+        const float tmax = (float)fmin(a[1], (double)kMaxFloat), st = (float)a[8];
+        float dist, inv_pdf;
+        const bool surface = mis_distance(mk(src.px, src.py, src.pz), ld3(a + 2), ld3(a + 5), tmax, expf(-st * tmax), st, 1.0f / st, (float)a[9], (float)a[10], dist, inv_pdf);
+        o[0] = surface; o[1] = dist; o[2] = surface ? 1.0f : 1.0f / inv_pdf;
+    } break;
     case VPT_UNIT_POWER_HEURISTIC: o[0] = power_heuristic((float)a[0], (float)a[1]); break;
     case VPT_UNIT_COSINE_HEMISPHERE: {
         const F3 nrm = ld3(a);
@@ -425,6 +436,7 @@ __global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const
             bool alive;
             if (lp.method == 0) alive = vertex<0>(sc, mats, k, p, rng, tally);
             else if (lp.method == 1) alive = vertex<1>(sc, mats, k, p, rng, tally);
+            else if (lp.method == 4) alive = vertex<4>(sc, mats, k, p, rng, tally);
             else alive = vertex<2>(sc, mats, k, p, rng, tally);
             if (!alive) break;
             ++p.depth;
@@ -440,6 +452,7 @@ __global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const
             bool alive;
             if (lp.method == 0) alive = vertex<0>(sc, mats, k, p, rng, tally);
             else if (lp.method == 1) alive = vertex<1>(sc, mats, k, p, rng, tally);
+            else if (lp.method == 4) alive = vertex<4>(sc, mats, k, p, rng, tally);
             else alive = vertex<2>(sc, mats, k, p, rng, tally);
             if (!alive) break;
             ++p.depth;

@@ -149,6 +149,11 @@ __global__ void unit_f64_kernel(int fn, const __grid_constant__ SceneD sc, const
         const double tl_ = D * tan((1 - a[8]) * thA + a[8] * thB);
         o[0] = D; o[1] = thA; o[2] = thB; o[3] = tl_; o[4] = tl_ + proj; o[5] = D / fabs(thB - thA) / (tl_ * tl_ + D * D);
     } break;
+    case VPT_UNIT_MIS_DISTANCE: {
+        double dist, pdf;
+        const bool surface = mis_distance(pos(c.s[(int)a[0]]), v3(a + 2), v3(a + 5), a[1], a[8], a[9], a[10], dist, pdf);
+        o[0] = surface; o[1] = dist; o[2] = pdf;
+    } break;
     case VPT_UNIT_POWER_HEURISTIC: o[0] = power_heuristic(a[0], a[1]); break;
     case VPT_UNIT_COSINE_HEMISPHERE: {
         const D3 w = cosine_hemisphere(v3(a), a[3], a[4]);

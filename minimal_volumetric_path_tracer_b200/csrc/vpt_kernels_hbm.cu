@@ -166,6 +166,7 @@ int launch_hbmwave_f32(const SceneF &scene, const LaunchParams &lp, const Consts
     switch (lp.method) {
     case 0: return run_hbmwave<0>(scene, lp, cf, hdr_dev, counters_dev, st, n_owned_tiles, launches);
     case 1: return run_hbmwave<1>(scene, lp, cf, hdr_dev, counters_dev, st, n_owned_tiles, launches);
+    case 4: return run_hbmwave<4>(scene, lp, cf, hdr_dev, counters_dev, st, n_owned_tiles, launches);
     default: return run_hbmwave<2>(scene, lp, cf, hdr_dev, counters_dev, st, n_owned_tiles, launches);
     }
 }

@@ -113,6 +113,9 @@ __device__ __forceinline__ void render_pixel_scan(const SceneF &sc, const MatF *
             if (METHOD == 0) {
                 dist = -logf(1.0f - u32_to_unit_f32(blk.z)) * k.inv_sigma_t;
                 surface = dist > t;
+            } else if (METHOD == 4) { // distance-sampling MIS (vpt_f32.cuh mis_distance)
+                const MatF &ls = mats[src];
+                surface = mis_distance(mk(ls.px, ls.py, ls.pz), o, d, t, expf(-k.sigma_t * t), k.sigma_t, k.inv_sigma_t, u32_to_unit_f32(blk.z), u32_to_unit_f32(blk.w), dist, inv_pdf);
             } else {
                 const MatF &sm = mats[src];
                 const float Tr = expf(-k.sigma_t * t);

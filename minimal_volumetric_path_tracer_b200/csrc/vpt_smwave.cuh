@@ -348,6 +348,8 @@ struct SmWave {
             if (METHOD == 0) {
                 dist = -logf(1.0f - u32_to_unit_f32(S.r2[s])) * k.inv_sigma_t; // freeFlightSample, vptSamplingFunctions.h:11
                 surface = dist > t;
+            } else if (METHOD == 4) { // distance-sampling MIS (vpt_f32.cuh mis_distance)
+                surface = mis_distance(mk(sm.px, sm.py, sm.pz), o, d, t, __expf(-k.sigma_t * t), k.sigma_t, k.inv_sigma_t, u32_to_unit_f32(S.r2[s]), u32_to_unit_f32(S.r3[s]), dist, inv_pdf);
             } else { // equiAngularParams2 (volumetricBasicFunctions.h:209-223) + equiAngularProb (vptSamplingFunctions.h:60)
                 const float Tr = __expf(-k.sigma_t * t);
                 float D, dth, tl;

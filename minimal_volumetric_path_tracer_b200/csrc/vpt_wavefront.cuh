@@ -178,6 +178,9 @@ struct Wavefront {
             if (METHOD == 0) {
                 dist = -logf(1.0f - u32_to_unit_f32(P.r2[s])) * k.inv_sigma_t; // freeFlightSample
                 surface = dist > t;
+            } else if (METHOD == 4) { // distance-sampling MIS (vpt_f32.cuh mis_distance)
+                const MatF &ls = sm;
+                surface = mis_distance(mk(ls.px, ls.py, ls.pz), o, d, t, expf(-k.sigma_t * t), k.sigma_t, k.inv_sigma_t, u32_to_unit_f32(P.r2[s]), u32_to_unit_f32(P.r3[s]), dist, inv_pdf);
             } else { // equiAngularParams2 + equiAngularProb
                 const float Tr = expf(-k.sigma_t * t);
                 const F3 dv = mk(sm.px, sm.py, sm.pz) - o;

@@ -2,7 +2,7 @@
 // stderr, "elapsed time: Ns" on stdout; src/rt.cpp:744-830) and replaces its OpenMP pixel loop (rt.cpp:767-805) with one
 // call through the C-ABI of include/vpt.h.  Everything the reference hard-codes is an optional flag here.
 //
-//   rt <spp> [--method free|equi|mis|march] [--march-step x] [--march-source i] [--scene file] [--size WxH] [--sigma-a x] [--sigma-s x] [--seed n] [--ref] [--gpus n]
+//   rt <spp> [--method free|equi|mis|march|mis-distance] [--march-step x] [--march-source i] [--scene file] [--size WxH] [--sigma-a x] [--sigma-s x] [--seed n] [--ref] [--gpus n]
 //            [--max-depth n] [--continue-prob x] [-o image.ppm]
 #include <chrono>
 #include <cstdio>
@@ -14,7 +14,7 @@
 #include "vpt.h"
 
 static int usage() {
-    std::fprintf(stderr, "usage: rt <spp> [--method free|equi|mis|march] [--march-step x] [--march-source i] [--scene file] [--size WxH] [--sigma-a x] [--sigma-s x] [--seed n] [--ref] [--gpus n] "
+    std::fprintf(stderr, "usage: rt <spp> [--method free|equi|mis|march|mis-distance] [--march-step x] [--march-source i] [--scene file] [--size WxH] [--sigma-a x] [--sigma-s x] [--seed n] [--ref] [--gpus n] "
                          "[--max-depth n] [--continue-prob x] [-o image.ppm]\n");
     return 2;
 }
@@ -32,7 +32,7 @@ int main(int argc, char **argv) {
         auto val = [&](const char *name) -> const char * { if (i + 1 >= argc) { std::fprintf(stderr, "%s needs a value\n", name); std::exit(2); } return argv[++i]; };
         if (a == "--method") {
             const std::string m = val("--method");
-            p.method = m == "free" ? VPT_METHOD_FREE_FLIGHT : m == "equi" ? VPT_METHOD_EQUIANGULAR : m == "mis" ? VPT_METHOD_MIS : m == "march" ? VPT_METHOD_RAYMARCH : -1;
+            p.method = m == "free" ? VPT_METHOD_FREE_FLIGHT : m == "equi" ? VPT_METHOD_EQUIANGULAR : m == "mis" ? VPT_METHOD_MIS : m == "march" ? VPT_METHOD_RAYMARCH : m == "mis-distance" ? VPT_METHOD_MIS_DISTANCE : -1;
         } else if (a == "--size") { if (std::sscanf(val("--size"), "%dx%d", &p.width, &p.height) != 2) return usage(); }
         else if (a == "--sigma-a") p.sigma_a = std::atof(val("--sigma-a"));
         else if (a == "--sigma-s") p.sigma_s = std::atof(val("--sigma-s"));

@@ -504,8 +504,40 @@ static inline Vec ray_march3(Scene &sc, const Ray &r, double sigma_a, double sig
     return Li;
 }
 
+/* Method 4, distance-sampling MIS.  NOT in the reference: its "MIS" method (vptShadeMethods.h:1345) is the
+ * equi-angular estimator again.  Both of the reference's distance techniques end at the surface with probability Tr = exp(-sigma_t t) and
+ * otherwise place a medium vertex on [0, t) -- free flight with density sigma_t exp(-sigma_t s) (freeFlightProb, vptSamplingFunctions.h:20),
+ * equi-angular with equiAngularProb(s) (1 - Tr) (:60, vptShadeMethods.h:1093); each density has mass 1 - Tr.  Here ONE technique is chosen
+ * with probability 1/2 and the sample is weighted with the balance heuristic, i.e. divided by the mixture density
+ *     p(s) = (sigma_t exp(-sigma_t s) + equiAngularProb(s) (1 - Tr)) / 2.
+ * Draws as in method 1: xi = S_DIST, then xd = S_DECIDE;  xd < Tr: surface;  xd < (1 + Tr) / 2: free flight restricted to [0, t),
+ * s = -log(1 - xi (1 - Tr)) / sigma_t;  else equi-angular, s = proj + D tan((1 - xi) thetaA + xi thetaB).  Everything after the
+ * distance is method 1's code (singleScattering with 1 / p). */
+struct MisDistance { bool surface; double dist, pdf; };
+static inline MisDistance mis_distance(const Scene &sc, int source, double t, const Ray &r, double sigma_t, double xi, double xd) {
+    MisDistance m{false, 0, 1};
+    const double Tr = std::exp(sigma_t * t * -1.0); /* 0 on a miss (t = MAXFLOAT) */
+    if (xd < Tr) { m.surface = true; return m; }
+    const Vec dv = sc.s[source].p - r.o;
+    const double len = std::sqrt(dot(dv, dv));
+    const double proj = dot(dv, r.d) / dot(r.d, r.d);
+    const double D = std::sqrt(len * len - proj * proj);
+    const double thetaA = std::atan2(0.0 - proj, D), thetaB = std::atan2(t - proj, D);
+    double t_local;
+    if (xd < 0.5 + 0.5 * Tr) {
+        m.dist = -std::log(1 - xi * (1 - Tr)) / sigma_t;
+        t_local = m.dist - proj;
+    } else {
+        t_local = D * std::tan((1 - xi) * thetaA + xi * thetaB);
+        m.dist = t_local + proj;
+    }
+    m.pdf = 0.5 * (free_flight_pdf(sigma_t, m.dist) + equiangular_pdf(D, thetaA, thetaB, t_local) * (1.0 - Tr));
+    return m;
+}
+
 struct Settings {
-    int method = 0;              /* 0 free-flight (vptShadeMethods.h:1263), 1 equi-angular (:1014), 2 "MIS" (:1345) */
+    int method = 0;              /* 0 free-flight (vptShadeMethods.h:1263), 1 equi-angular (:1014), 2 "MIS" (:1345),
+                                    4 distance-sampling MIS (not in the reference, SURVEY.md 8f-4: see mis_distance below) */
     double sigma_a = 0.001, sigma_s = 0.009; /* src/rt.cpp:794 */
     double continue_prob = 0.6;  /* vptShadeMethods.h:1275 */
     int max_depth = 0;           /* <= 0: unlimited (reference) */
@@ -547,6 +579,10 @@ static inline Vec radiance(Rng &rng, Scene &sc, Ray ray, const Settings &cfg, Pa
         if (cfg.method == 0) {
             dist = free_flight_sample(rng, sigma_t); /* :1305 */
             surface = dist > t;
+        } else if (cfg.method == 4) {
+            const double xi = rng.next(S_DIST);
+            const MisDistance m = mis_distance(sc, source, t, ray, sigma_t, xi, rng.next(S_DECIDE));
+            surface = m.surface; dist = m.dist; pdf_medium = m.pdf;
         } else {
             if (cfg.method == 2) Tr = std::exp(sigma_t * t * -1.0); /* psurf :1407 */
             const EquiAngular e = equiangular_setup(rng, sc, source, t, ray);

@@ -67,6 +67,15 @@ double l1_equiAngularParams2(const double *scene, int n, int src, double tMax, c
     out4[0] = e.D; out4[1] = e.thetaA; out4[2] = e.thetaB; out4[3] = e.t_local;
     return e.t_ray;
 }
+/* method 4's distance decision on n rows (source, tMax, o[3], d[3], sigma_t, xi, xd) -> (surface, dist, pdf) */
+void l1_mis_distance(const double *scene, int n_spheres, int n, const double *rows, double *out) {
+    Scene sc = make_scene(scene, n_spheres, 0);
+    for (int i = 0; i < n; ++i) {
+        const double *a = rows + 11 * i;
+        const MisDistance m = mis_distance(sc, (int)a[0], a[1], Ray{V(a + 2), V(a + 5)}, a[8], a[9], a[10]);
+        out[3 * i] = m.surface; out[3 * i + 1] = m.dist; out[3 * i + 2] = m.pdf;
+    }
+}
 void l1_freeSingleScattering(const double *scene, int n, unsigned quirks, const double *xt, int src, double st, double pS, const double *u, int nu, double *o) {
     Scene sc = make_scene(scene, n, quirks);
     ListRng r(u, nu);

@@ -144,6 +144,11 @@ class L1:
         r = self.lib.l1_equiAngularParams2(_p(s), C.c_int(len(s)), C.c_int(src), D(tmax), _p(o), _p(d), pu, nu, _p(out))
         return r, out
 
+    def mis_distance(self, scene, rows):
+        """method 4's distance decision; rows: n x 11 (source, tMax, o[3], d[3], sigma_t, xi, xd) -> n x 3 (surface, dist, mixture pdf)"""
+        s = _v(scene); rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, 11); out = np.zeros((len(rows), 3))
+        self.lib.l1_mis_distance(_p(s), C.c_int(len(s)), C.c_int(len(rows)), _p(rows), _p(out)); return out
+
     def freeSingleScattering(self, scene, quirks, xt, src, st, pS, u):
         s, xt = _v(scene), _v(xt); u, pu, nu = self._u(u); o = np.zeros(3)
         self.lib.l1_freeSingleScattering(_p(s), C.c_int(len(s)), C.c_uint(quirks), _p(xt), C.c_int(src), D(st), D(pS), pu, nu, _p(o)); return o

@@ -43,7 +43,7 @@ def test_default_scene_is_the_references(vpt):
 
 
 def test_unit_strides_table(vpt):
-    for fn in range(18):
+    for fn in range(21):
         si, so = vpt.unit_strides(fn)
         assert si > 0 and so > 0
     with pytest.raises(vpt.VptError):
@@ -63,7 +63,7 @@ def test_argument_validation_precedes_device_work(vpt):
     INVALID, SCENE, UNSUPPORTED = -1, -2, -3
     assert _rc(vpt, P(spp=0)) == INVALID
     assert _rc(vpt, P(width=0)) == INVALID
-    assert _rc(vpt, P(method=4)) == INVALID
+    assert _rc(vpt, P(method=5)) == INVALID
     assert _rc(vpt, P(sample_begin=1, sample_end=1)) == INVALID
     assert _rc(vpt, P(sample_begin=0, sample_end=3)) == INVALID
     assert _rc(vpt, P(tile_rank=2, tile_count=2)) == INVALID

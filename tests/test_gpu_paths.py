@@ -96,7 +96,7 @@ def random_rays(l1, n, seed):
     return o, d, pix, smp
 
 
-@pytest.mark.parametrize("method", [0, 1, 2])
+@pytest.mark.parametrize("method", [0, 1, 2, 4])
 def test_philox_paths_common_random_numbers(gpu, l1, method):
     n = 30000
     o, d, pix, smp = random_rays(l1, n, 11 + method)

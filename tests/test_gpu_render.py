@@ -17,7 +17,7 @@ SA, SS = 0.001, 0.009
 
 
 # ---- common random numbers vs the oracle ------------------------------------------------------------------------------------
-@pytest.mark.parametrize("method", [0, 1, 2])
+@pytest.mark.parametrize("method", [0, 1, 2, 4])
 def test_small_render_crn_fp64(gpu, l1, method):
     w, h, spp = 96, 72, 8
     p = gpu.default_params(width=w, height=h, spp=spp, method=method, precision=gpu.PRECISION_FP64_REF, quirks=0, seed=3, output=gpu.OUTPUT_SUM)
@@ -27,7 +27,7 @@ def test_small_render_crn_fp64(gpu, l1, method):
     np.testing.assert_allclose(hdr, ref, rtol=2e-6, atol=1e-7)  # output buffer is fp32
 
 
-@pytest.mark.parametrize("method", [0, 1, 2])
+@pytest.mark.parametrize("method", [0, 1, 2, 4])
 def test_small_render_crn_fp32(gpu, l1, method):
     w, h, spp = 128, 96, 16
     p = gpu.default_params(width=w, height=h, spp=spp, method=method, seed=3, output=gpu.OUTPUT_SUM)
@@ -60,7 +60,7 @@ def block_means(hdr, block=16):
     return hdr[:h // block * block, :w // block * block].reshape(h // block, block, w // block, block, 3).mean(axis=(1, 3))
 
 
-def z_scores(gpu, golden_name, precision, quirks, spp, scene_rows=None, seed=77, batches=16, stand_ins=6):
+def z_scores(gpu, golden_name, precision, quirks, spp, scene_rows=None, seed=77, batches=16, stand_ins=6, main_method=None):
     """Is the reference render one more draw from the distribution the GPU samples?
 
     Block means at the reference's 256-512 spp are right-skewed (the estimator has fireflies: throughput grows 1.5x per
@@ -76,7 +76,9 @@ def z_scores(gpu, golden_name, precision, quirks, spp, scene_rows=None, seed=77,
     w, h, method, spp_ref = int(g["width"]), int(g["height"]), int(g["method"]), int(g["spp"])
     p = gpu.default_params(width=w, height=h, spp=spp, method=method, precision=precision, quirks=quirks, seed=seed)
     scene = gpu.scene_from_rows(scene_rows) if scene_rows is not None else None
-    main, st = gpu.render(p, scene, stats=True)
+    # main_method: the high-spp render comes from ANOTHER estimator that claims the same expectation; noise model and stand-ins stay the
+    # reference method's (the high-spp render's own variance enters sigma only through the small 1 / spp term)
+    main, st = gpu.render(p if main_method is None else p.copy(method=main_method), scene, stats=True)
     assert st.nonfinite <= 1e-8 * st.paths  # dropped NaN/Inf paths (0 * inf in a BRDF at an exactly grazing fp32 direction): counted, < 1 in 1e8
     main = block_means(main.astype(np.float64))
     per = max(spp // (4 * batches), 4)
@@ -123,6 +125,29 @@ def test_fp32_matches_reference_with_robust_hooks(gpu, method):
 def test_fp32_matches_unmodified_reference_without_point_light(gpu, method):
     """without the r = 0 sphere the UNMODIFIED reference has no rounding-decided branch: direct comparison, no hooks"""
     check_statistically_equal(z_scores(gpu, "no8_m%d" % method, gpu.PRECISION_FP32, 0, spp=4096, scene_rows=scene_without([8])))
+
+
+@pytest.mark.parametrize("golden", ["robust_m0", "robust_m1", "no8_m2"])
+def test_mis_distance_matches_the_reference_renders(gpu, golden):
+    """VPT_METHOD_MIS_DISTANCE (not in the reference) has the expectation of the reference's methods: its renders must be
+    statistically indistinguishable from the reference's free-flight and equi-angular renders (robust hooks) and from the unmodified
+    reference on the scene without the point light.  The 4096-spp render is method 4's; the stand-in ensemble and the noise model are the
+    reference method's own (GPU renders of that method at the reference's spp, shown equal to the reference by the tests above)."""
+    check_statistically_equal(z_scores(gpu, golden, gpu.PRECISION_FP32, 0, spp=4096, main_method=gpu.METHOD_MIS_DISTANCE,
+                                       scene_rows=scene_without([8]) if golden.startswith("no8") else None))
+
+
+def test_mis_distance_lowers_the_variance(gpu):
+    """the balance heuristic's point: per-pixel variance (from 32 independent 8-spp renders) summed over the image is below that of
+    BOTH single-technique estimators, in every channel (FP64 oracle at 96x72: 2.90 / 0.82 / 0.39 against free flight 5.77 / 1.05 / 0.44 and
+    equi-angular 3.39 / 0.90 / 0.50)"""
+    def total_var(method):
+        p = gpu.default_params(width=256, height=192, spp=256, method=method, seed=21, output=gpu.OUTPUT_SUM)
+        parts = np.stack([gpu.render(p.copy(sample_begin=8 * b, sample_end=8 * b + 8)).astype(np.float64) / 8 for b in range(32)])
+        return parts.var(axis=0, ddof=1).mean(axis=(0, 1)), parts.mean(axis=(0, 1, 2))
+    (v0, m0), (v1, m1), (v4, m4) = total_var(0), total_var(1), total_var(gpu.METHOD_MIS_DISTANCE)
+    assert np.all(v4 < 0.97 * np.minimum(v0, v1)), (v0, v1, v4)
+    np.testing.assert_allclose(m4, m0, rtol=0.03); np.testing.assert_allclose(m4, m1, rtol=0.03)
 
 
 def test_fp64_robust_matches_reference_with_robust_hooks(gpu):
@@ -191,7 +216,7 @@ def test_render_multi_single_device_equals_render(gpu):
 def test_statistics_match_the_reference_workload(gpu):
     """events per path = 1/(1-0.6) * 0.6 = 1.5; scans per path about 4.3 (the reference's 5.4 minus
     the scans this implementation proves redundant)"""
-    for method in (0, 1, 2):
+    for method in (0, 1, 2, 4):
         _, st = gpu.render(gpu.default_params(spp=16, method=method), stats=True)
         assert st.paths == 1024 * 768 * 16 and abs(st.events / st.paths - 1.5) < 0.01
         assert 3.5 < st.scene_scans / st.paths < 5.6 and st.kernel_ms > 0 and st.launches == 1
@@ -227,7 +252,7 @@ def test_precision_quirk_contract(gpu):
 
 
 # ---- the two FP32 kernel variants compute the same thing -------------------------------------------------------------------
-@pytest.mark.parametrize("method", [0, 1, 2])
+@pytest.mark.parametrize("method", [0, 1, 2, 4])
 def test_kernel_variants_agree(gpu, l1, method):
     """MEGA (vertex per iteration), MEGA_SCAN (scan-converged state machine), WAVEFRONT (warp-local queues), WAVEFRONT_SM (one pool per SM,
     AUTO) and WAVEFRONT_HBM (multi-kernel, queues in HBM): same streams, same decisions up to fp32 rounding (the SM kernel uses the direct roots for small spheres, so a few more near-tie
@@ -254,7 +279,7 @@ def test_kernel_variants_agree(gpu, l1, method):
         assert np.median(e) < 2e-6 and np.mean(e > 1e-3) < 0.02
 
 
-@pytest.mark.parametrize("method", [0, 1, 2])
+@pytest.mark.parametrize("method", [0, 1, 2, 4])
 def test_auto_kernel_per_path_parity(gpu, l1, method):
     """spp = 1: every pixel of the product kernel (AUTO = the SM-wide wavefront) is ONE path; compare each with the FP64 oracle on the same
     Philox stream.  Tolerance: 1e-5 relative (north_star's unit tolerance) for at least 99 % of the paths -- the remainder are paths where
@@ -285,7 +310,7 @@ def _stress_scene():
     return np.array(rows)
 
 
-@pytest.mark.parametrize("method", [0, 1, 2])
+@pytest.mark.parametrize("method", [0, 1, 2, 4])
 def test_auto_kernel_per_path_parity_on_a_scene_not_in_the_reference(gpu, l1, method):
     """the product kernel against the FP64 oracle, one path per pixel, on the stress scene"""
     sc = _stress_scene()

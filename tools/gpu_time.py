@@ -8,7 +8,7 @@ spp = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 kernels = {"mega": v.KERNEL_MEGA, "scan": v.KERNEL_MEGA_SCAN, "wave": v.KERNEL_WAVEFRONT, "smwave": v.KERNEL_WAVEFRONT_SM, "hbm": v.KERNEL_WAVEFRONT_HBM}
 names = sys.argv[2].split(",") if len(sys.argv) > 2 else list(kernels)
 for kern, name in ((kernels[n], n) for n in names):
-    for method in (0, 1, 2):
+    for method in (0, 1, 2, 4):
         p = v.default_params(spp=spp, method=method, kernel=kern)
         v.render(p)
         best = 0
