@@ -29,7 +29,7 @@ typedef enum {
     VPT_OK = 0,
     VPT_ERR_INVALID_ARGUMENT = -1, /* null pointer, non-positive size, bad enum, sample range outside [0, spp] ... */
     VPT_ERR_SCENE = -2,            /* n_spheres out of range, too many emitters, negative radius, non-finite field */
-    VPT_ERR_UNSUPPORTED = -3,      /* material 2/3 (outside the hot-path scope); quirks requested in fp32 precision */
+    VPT_ERR_UNSUPPORTED = -3,      /* material 3; material 2 with the superseded MEGA_SCAN / WAVEFRONT kernels; quirks requested in fp32 precision */
     VPT_ERR_NO_DEVICE = -4,        /* no CUDA device / bad ordinal */
     VPT_ERR_CUDA = -5,             /* a CUDA runtime call failed; vpt_last_cuda_error() has the text */
     VPT_ERR_IO = -6                /* vpt_write_ppm could not write */
@@ -41,7 +41,9 @@ typedef struct {
     double p[3];        /* centre */
     double c[3];        /* Lambert albedo */
     double radiance[3]; /* > 0 in any channel = emitter (vptShadeMethods.h:1296) */
-    int32_t material;   /* 0 Lambert, 1 Beckmann conductor microfacet (2 dielectric, 3 volumetric: unsupported) */
+    int32_t material;   /* 0 Lambert, 1 Beckmann conductor microfacet, 2 dielectric exactly as the reference writes it (bdsf vptShadeMethods.h:26-46,
+                           softDielectric samplingFunctions.h:209, refraxDielectric microFacetUtilities.h:122 -- not Snell's law; used by no scene of
+                           Sphere.cpp); 3 volumetric sphere: unsupported (undefined in the reference's active methods) */
     int32_t _pad;
     double eta[3], kappa[3];
     double alpha; /* Beckmann roughness */

@@ -50,8 +50,8 @@ int validate_scene(const vpt_sphere *s, int n) {
     int n_emit = 0;
     for (int i = 0; i < n; ++i) {
         if (!(s[i].r >= 0) || !std::isfinite(s[i].r) || !finite3(s[i].p) || !finite3(s[i].c) || !finite3(s[i].radiance)) return VPT_ERR_SCENE;
-        if (s[i].material == 2 || s[i].material == 3) return VPT_ERR_UNSUPPORTED;
-        if (s[i].material != 0 && s[i].material != 1) return VPT_ERR_SCENE;
+        if (s[i].material == 3) return VPT_ERR_UNSUPPORTED; // volumetric spheres: bdsf leaves pdf and direction unset for them in the active methods
+        if (s[i].material != 0 && s[i].material != 1 && s[i].material != 2) return VPT_ERR_SCENE;
         if (s[i].material == 1 && (!(s[i].alpha > 0) || !finite3(s[i].eta) || !finite3(s[i].kappa))) return VPT_ERR_SCENE;
         if (emits(s[i])) ++n_emit;
     }
@@ -211,6 +211,10 @@ int enqueue_render(const vpt_params *p, const vpt_sphere *spheres, int n_spheres
     const int blocks = owned_tiles(lp);
     int n_emit = 0;
     for (int i = 0; i < n_spheres; ++i) n_emit += emits(spheres[i]);
+    // material 2 (dielectric) lives in the product kernels (AUTO = WAVEFRONT_SM, WAVEFRONT_HBM), in MEGA and in FP64 REF; the two superseded
+    // FP32 variants kept for the kernel-by-measurement comparison do not carry it
+    if (p->precision == VPT_PRECISION_FP32 && (p->kernel == VPT_KERNEL_MEGA_SCAN || p->kernel == VPT_KERNEL_WAVEFRONT))
+        for (int i = 0; i < n_spheres; ++i) if (spheres[i].material == 2) return VPT_ERR_UNSUPPORTED;
     if (lp.tile_count > 1 || (n_emit == 0 && lp.method != VPT_METHOD_RAYMARCH) || blocks == 0) CUDA_TRY(cudaMemsetAsync(hdr_dev, 0, bytes, stream));
     if (lp.method == VPT_METHOD_RAYMARCH && lp.march_source >= n_spheres) return VPT_ERR_INVALID_ARGUMENT;
     if ((n_emit == 0 && lp.method != VPT_METHOD_RAYMARCH) || blocks == 0) return VPT_OK; // no emitter: every path returns black (vptShadeMethods.h:1301)
@@ -635,7 +639,7 @@ const char *vpt_strerror(int status) {
     case VPT_OK: return "ok";
     case VPT_ERR_INVALID_ARGUMENT: return "invalid argument";
     case VPT_ERR_SCENE: return "invalid scene (sphere count, emitter count or a non-finite / negative field)";
-    case VPT_ERR_UNSUPPORTED: return "unsupported (material 2/3, wavefront kernel, or quirks requested in fp32 precision)";
+    case VPT_ERR_UNSUPPORTED: return "unsupported (material 3; material 2 with the MEGA_SCAN / WAVEFRONT kernels; wavefront kernel in fp64; quirks in fp32 precision)";
     case VPT_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
     case VPT_ERR_CUDA: return "CUDA runtime error (see vpt_last_cuda_error)";
     case VPT_ERR_IO: return "I/O error";

@@ -221,6 +221,33 @@ __device__ __forceinline__ F3 facet_normal(float alpha, float xi1, float xi2) {
     return mk(s * cp, s * sp, c);
 }
 
+// ---- material 2 (dielectric) AS WRITTEN in the reference, local frame n = +z -----------------------------------------------------------
+// refraxDielectric (microFacetUtilities.h:122-141): local x, y scaled by -etat/etai = -1.5, z = sqrt(1 - (1/1.5)^2 (1 - cos_i^2)) - 1, then
+// normalised by the callers; reflexDielectric (:117-120); fresnelDie(1, 1.5, n.wt, n.wo) (:107-112).  Not Snell's law -- the reference's
+// formulas, restated so that a scene using material 2 renders what the reference renders (FP64 statement: vpt_f64.cuh, oracle/vpt_oracle.hpp).
+// fp32 care: 1 - cos_i^2 = x^2 + y^2 for the unit wo, and sqrt(1 - a) - 1 = -a / (1 + sqrt(1 - a)).
+struct DielF { F3 wr, wt; float F; };
+__device__ __forceinline__ DielF dielectric_setup(F3 wo_l) {
+    DielF r;
+    const float a = (wo_l.x * wo_l.x + wo_l.y * wo_l.y) * (1.0f / 2.25f);
+    const float ct = -a / (1.0f + sqrtf(1.0f - a));
+    r.wt = unit(mk(-1.5f * wo_l.x, -1.5f * wo_l.y, ct));
+    r.wr = mk(-wo_l.x, -wo_l.y, wo_l.z);
+    const float ci = wo_l.z, cn = r.wt.z;
+    const float par = (1.5f * ci - cn) / (1.5f * ci + cn), perp = (ci - 1.5f * cn) / (ci + 1.5f * cn);
+    r.F = 0.5f * (par * par + perp * perp);
+    return r;
+}
+// the BSDF-sampled term of MISv2 for a dielectric (softDielectric, samplingFunctions.h:209-235; misSamplingFunctions.h:144-152), after the
+// scan along the chosen direction: Le / |n.w| (x 1.5^2 when refracted), weighted by powerHeuristics(gpdf left by the light loop, cone pdf)
+__device__ __forceinline__ F3 dielectric_direct(const MatF &em, F3 x, float cos_w, bool refracted, float gpdf_loop) {
+    const F3 g = mk(em.lr, em.lg, em.lb) * ((refracted ? 2.25f : 1.0f) / fabsf(cos_w));
+    if (!(g.x > 0.0f && g.y > 0.0f && g.z > 0.0f)) return mk(0, 0, 0);
+    const F3 cx = mk(em.px, em.py, em.pz) - x;
+    const float omc = one_minus_cos_max(em.r * em.r / dot(cx, cx));
+    return g * power_heuristic(gpdf_loop, 1.0f / (kTwoPi * omc));
+}
+
 // ---- per-path state -----------------------------------------------------------------------------------------------------
 struct Consts { // derived once per launch from LaunchParams
     float sigma_t, inv_sigma_t, sigma_s, albedo_over_cp, inv_cp, q;
@@ -258,6 +285,19 @@ template <class RngT>
 __device__ __forceinline__ F3 surface_direct_mis(const SceneF &sc, const MatF *mats, const MatF &obj, F3 x, const Frame &fr, F3 wo_l,
                                                  const Consts &k, RngT &rng, unsigned &n_scans) {
     F3 total = mk(0, 0, 0);
+    if (obj.material == 2) { // light-sampled terms are zero (fr = 0, samplingFunctions.h:190); the loop only leaves its last gpdf behind (:110-118)
+        const DielF di = dielectric_setup(wo_l);
+        float gpdf_loop = 0.0f;
+        for (int a = 0; a < sc.n_area; ++a) {
+            rng.next_f32(S_AREA + 2 * a); rng.next_f32(S_AREA + 2 * a + 1);
+            gpdf_loop = rng.next_f32(S_DIEL + a) > di.F ? 1.0f - di.F : di.F;
+        }
+        const bool refracted = !(rng.next_f32(S_MIS) < di.F);
+        const F3 w_l = refracted ? di.wt : di.wr;
+        float t; int hit_id;
+        if (scan(sc, x, unit(to_world(fr, w_l)), t, hit_id, n_scans)) total = dielectric_direct(mats[hit_id], x, w_l.z, refracted, gpdf_loop);
+        return total;
+    }
     float omc_last = 1.0f; // 1 - costhetaMax of the last light visited (reference: stale variable, :162); 1 = "cos 0"
     for (int a = 0; a < sc.n_area; ++a) {
         const int lid = sc.area[a];
@@ -326,6 +366,13 @@ __device__ __forceinline__ F3 surface_direct_mis(const SceneF &sc, const MatF *m
 
 // bdsf (vptShadeMethods.h:16-59) folded with its use at :1323-1327: returns fs * cos / pdf and the unit direction wi.
 __device__ __forceinline__ F3 bsdf_sample(const MatF &obj, const Frame &fr, F3 wo_l, float xi1, float xi2, F3 &wi) {
+    if (obj.material == 2) { // :26-46: fs cos / pdf = (F / n.wi) (n.wi) / F = 1 reflected, (1 - F) 1.5^2 / (1 - F) refracted; xi2 unused
+        const DielF di = dielectric_setup(wo_l);
+        const bool reflected = xi1 < di.F;
+        wi = unit(to_world(fr, reflected ? di.wr : di.wt));
+        const float w = reflected ? 1.0f : 2.25f;
+        return mk(w, w, w);
+    }
     if (obj.material == 1) {
         const F3 wh = facet_normal(obj.alpha, xi1, xi2);
         const F3 wi_l = unit(fma3(wh, 2.0f * dot(wh, wo_l), -wo_l));
@@ -409,7 +456,7 @@ __device__ __forceinline__ bool vertex(const SceneF &sc, const MatF *mats, const
         const F3 Ld_point = point_light_direct(sc, obj, src, x, fr, wo_l, k, tally.scans);
         const F3 Ld = surface_direct_mis(sc, mats, obj, x, fr, wo_l, k, rng, tally.scans);
         p.L = p.L + had(Ld_point + Ld, p.beta) * k.inv_cp;
-        const float xi1 = rng.next_f32(S_BSDF), xi2 = rng.next_f32(S_BSDF + 1);
+        const float xi1 = rng.next_f32(S_BSDF), xi2 = obj.material == 2 ? 0.0f : rng.next_f32(S_BSDF + 1); // (the dielectric draws one number)
         F3 wi;
         const F3 weight = bsdf_sample(obj, fr, wo_l, xi1, xi2, wi);
         p.beta = had(p.beta, weight) * k.inv_cp;

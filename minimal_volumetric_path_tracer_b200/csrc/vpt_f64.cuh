@@ -213,6 +213,22 @@ __device__ __forceinline__ D3 facet_brdf(const SphereD &m, D3 wi, D3 wh, D3 wo, 
     return fresnel_conductor(dot(wi, wh), m.eta, m.kappa) * beckmann(dot(n, wh), alpha) * g * (1 / den);
 }
 
+// ---- material 2 (dielectric), restated AS WRITTEN in the reference -----------------------------------------------------------------
+__device__ __forceinline__ double fresnel_dielectric(double etai, double etat, double ct, double ci) { // fresnelDie :107-112
+    const double par = ((etat * ci - etai * ct) / (etat * ci + etai * ct)) * ((etat * ci - etai * ct) / (etat * ci + etai * ct));
+    const double perp = ((etai * ci - etat * ct) / (etai * ci + etat * ct)) * ((etai * ci - etat * ct) / (etai * ci + etat * ct));
+    return 0.5 * (par + perp);
+}
+__device__ __forceinline__ D3 reflect_dielectric(D3 wi, D3 n) { return wi * -1 + n * dot(n, wi) * 2; } // reflexDielectric :117-120
+__device__ __forceinline__ D3 refract_dielectric(double etai, double etat, D3 wi, D3 n) {              // refraxDielectric :122-141
+    const D3 wl = to_local(n, wi);
+    const double ratio = etat / etai * -1;
+    const double cosinei = dot(wi, n);
+    const double invratio = etai / etat;
+    const double cosinet = sqrt(1 - invratio * invratio * (1 - cosinei * cosinei)) - 1;
+    return from_local(n, mk(wl.x * ratio, wl.y * ratio, cosinet));
+}
+
 // muestreoSA -> solidAngle(L), samplingFunctions.h:238-247 and :163-206
 template <class RngT>
 __device__ __forceinline__ D3 light_sampled_direct(const Ctx &c, int light, D3 x, const SphereD &obj, D3 n, D3 wray, double alpha, D3 &wi_out, double &cos_max_out,
@@ -231,6 +247,7 @@ __device__ __forceinline__ D3 light_sampled_direct(const Ctx &c, int light, D3 x
     const D3 wh = unit(wil + wol);
     D3 fr;
     if (obj.material == 0) fr = alb(obj) * (1 / kPi);
+    else if (obj.material == 2) fr = mk(0, 0, 0); // samplingFunctions.h:190-193
     else fr = facet_brdf(obj, wil, wh, wol, alpha, mk(0, 0, 1));
     double t;
     int id = 0;
@@ -244,7 +261,7 @@ template <class RngT>
 __device__ __forceinline__ D3 surface_direct_mis(const Ctx &c, const SphereD &obj, D3 x, D3 n, D3 wray, double alpha, RngT &rng, Tally &tl) {
     D3 total = mk(0, 0, 0);
     D3 wo = wray * -1;
-    double cos_max = 0;
+    double cos_max = 0, gpdf_loop = 0; // (the reference's function-wide `gpdf`: its dielectric branch reads what the light loop left, :148)
     uint32_t area_index = 0;
     for (int light = 0; light < c.n_spheres; ++light) {
         if (c.s[light].r > 0 && c.s[light].lr > 0) {
@@ -253,7 +270,12 @@ __device__ __forceinline__ D3 surface_direct_mis(const Ctx &c, const SphereD &ob
             const double fpdf = cone_pdf(cos_max);
             double gpdf;
             if (obj.material == 0) gpdf = cosine_pdf(dot(n, wi_light));
-            else gpdf = facet_pdf(wo, unit(wi_light + wo), alpha, n);
+            else if (obj.material == 2) { // :110-118
+                const D3 wt = unit(refract_dielectric(1.0, 1.5, wo, n));
+                gpdf = fresnel_dielectric(1.0, 1.5, dot(n, wt), dot(n, wo));
+                if (rng.next_f64(S_DIEL + (area_index - 1)) > gpdf) gpdf = 1 - gpdf;
+            } else gpdf = facet_pdf(wo, unit(wi_light + wo), alpha, n);
+            gpdf_loop = gpdf;
             total = total + f * power_heuristic(fpdf, gpdf);
         }
     }
@@ -267,6 +289,19 @@ __device__ __forceinline__ D3 surface_direct_mis(const Ctx &c, const SphereD &ob
         g = mk(0, 0, 0) + had(Le, alb(obj) * (1 / kPi)) * dot(n, wi) * (1 / cosine_pdf(dot(n, wi)));
         const double gpdf = cosine_pdf(dot(n, wi));
         if (g.x > 0 && g.y > 0 && g.z > 0) wg = power_heuristic(gpdf, cone_pdf(cone_cos(c, source, x)));
+        else wg = 0;
+    } else if (obj.material == 2) { // softDielectric(1.5, 1.0, wo, ...), samplingFunctions.h:209-235; MISv2 :144-152
+        const D3 wt = unit(refract_dielectric(1.0, 1.5, wo, n));
+        const double F = fresnel_dielectric(1.0, 1.5, dot(n, wt), dot(n, wo));
+        int source = -1;
+        if (rng.next_f64(S_MIS) < F) {
+            const D3 wr = unit(reflect_dielectric(wo, n));
+            g = first_hit_radiance(c, x, wr, source, tl) * (1 / fabs(dot(n, wr)));
+        } else {
+            const double ratio = 1.5 / 1.0;
+            g = first_hit_radiance(c, x, wt, source, tl) * (1 / fabs(dot(n, wt))) * ratio * ratio;
+        }
+        if (g.x > 0 && g.y > 0 && g.z > 0) wg = power_heuristic(gpdf_loop, cone_pdf(cone_cos(c, source, x)));
         else wg = 0;
     } else {
         const double xi1 = rng.next_f64(S_MIS), xi2 = rng.next_f64(S_MIS + 1);
@@ -306,6 +341,17 @@ __device__ __forceinline__ D3 point_light_direct(const Ctx &c, const SphereD &ob
 template <class RngT>
 __device__ __forceinline__ D3 bsdf_sample(const SphereD &obj, D3 &wi_out, D3 wray, D3 n, double &pdf, RngT &rng) {
     const D3 wo = wray * -1;
+    if (obj.material == 2) { // :26-46 (ONE draw)
+        const D3 wt = unit(refract_dielectric(1.0, 1.5, wo, n));
+        const double F = fresnel_dielectric(1.0, 1.5, dot(n, wt), dot(n, wo));
+        if (rng.next_f64(S_BSDF) < F) {
+            const D3 wi = unit(reflect_dielectric(wo, n));
+            pdf = F; wi_out = wi;
+            return mk(1, 1, 1) * (1 / dot(n, wi)) * F;
+        }
+        pdf = 1 - F; wi_out = wt;
+        return mk(1, 1, 1) * (1 / dot(n, wt)) * (1 - F) * 1.5 * 1.5;
+    }
     const double xi1 = rng.next_f64(S_BSDF), xi2 = rng.next_f64(S_BSDF + 1);
     if (obj.material == 0) {
         const D3 wi = cosine_hemisphere(n, xi1, xi2);

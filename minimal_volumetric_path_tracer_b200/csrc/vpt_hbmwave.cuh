@@ -122,7 +122,7 @@ struct HbmCtx { // what every stage needs
                 r.o = fma3(r.d, t, r.o);
                 const F3 lx = mk(sm.px, sm.py, sm.pz) - r.o;
                 const bool to_sp = !(sm.r > 0.0f && dot(lx, lx) > sm.r * sm.r);
-                dest = to_sp ? SQ_SURF_P : (obj.material == 1 ? SQ_SURF_F : SQ_SURF_L);
+                dest = to_sp ? SQ_SURF_P : (obj.material != 0 ? SQ_SURF_F : SQ_SURF_L);
                 r.r1 = (uint32_t)src | ((uint32_t)hid << 8);
             } else {
                 r.o = fma3(r.d, dist, r.o);
@@ -188,7 +188,7 @@ struct HbmCtx { // what every stage needs
             ++scans;
             if (!hit || t > dist * (1.0f - 1e-4f)) r.L = r.L + C;
         }
-        dest = act ? (facet ? SQ_SURF_F : SQ_SURF_L) : -1;
+        dest = act ? (obj.material != 0 ? SQ_SURF_F : SQ_SURF_L) : -1;
     }
 
     // ---- SURF ----
@@ -203,6 +203,13 @@ struct HbmCtx { // what every stage needs
         const F3 wo_l = FACET ? unit(to_local(fr, -d)) : mk(0, 0, 1);
         const F3 albedo = mk(obj.cr, obj.cg, obj.cb);
         float omc_last = 1.0f;
+        // material 2 (dielectric, as written in the reference: vpt_f32.cuh dielectric_setup) shares this stage with the microfacet: its
+        // light-sampled terms are zero (samplingFunctions.h:190), the loop below only runs its scans in step with the other lanes
+        const bool diel = FACET && obj.material == 2;
+        DielF di; di.F = 0.0f; di.wr = di.wt = mk(0, 0, 1);
+        if (diel) di = dielectric_setup(wo_l);
+        float gpdf_loop = 0.0f; // the pdf the reference's light loop leaves behind for the dielectric's BSDF term (misSamplingFunctions.h:110-118,148)
+        bool refracted = false;
         uint4 ra = make_uint4(0, 0, 0, 0);
         for (int a = 0; a < sc.n_area; ++a) {
             if ((a & 1) == 0) ra = philox_block(r.pixel, r.sample, r.depth, 2 + (a >> 1), lp.key0, lp.key1);
@@ -218,7 +225,7 @@ struct HbmCtx { // what every stage needs
             const bool hit = scan_sm(S, o, wi, t, hid);
             if (act) {
                 ++scans;
-                if ((hit ? hid : 0) == lid) {
+                if ((hit ? hid : 0) == lid && !diel) {
                     const float cos_i = dot(n_, wi);
                     F3 f = albedo * kInvPi;
                     float gpdf = cos_i * kInvPi;
@@ -233,8 +240,18 @@ struct HbmCtx { // what every stage needs
         {
             const float xi1 = u32_to_unit_f32(b1.z), xi2 = u32_to_unit_f32(b1.w);
             F3 wi_l, wh = mk(0, 0, 1);
-            if (FACET) { wh = facet_normal(obj.alpha, xi1, xi2); wi_l = unit(fma3(wh, 2.0f * dot(wh, wo_l), -wo_l)); }
-            else wi_l = cosine_local(xi1, xi2);
+            if (FACET) {
+                wh = facet_normal(obj.alpha, xi1, xi2); wi_l = unit(fma3(wh, 2.0f * dot(wh, wo_l), -wo_l));
+                if (diel) { // softDielectric (samplingFunctions.h:209-235): reflect with probability F, else the reference's refraction
+                    if (sc.n_area > 0) {
+                        const uint32_t slot = S_DIEL + (uint32_t)sc.n_area - 1u;
+                        const float xg = u32_to_unit_f32(pick_lane(philox_block(r.pixel, r.sample, r.depth, slot >> 2, lp.key0, lp.key1), slot & 3u));
+                        gpdf_loop = xg > di.F ? 1.0f - di.F : di.F;
+                    }
+                    refracted = !(xi1 < di.F);
+                    wi_l = refracted ? di.wt : di.wr;
+                }
+            } else wi_l = cosine_local(xi1, xi2);
             const F3 wi = unit(to_world(fr, wi_l));
             float t; int hid;
             const bool hit = scan_sm(S, o, wi, t, hid);
@@ -244,7 +261,8 @@ struct HbmCtx { // what every stage needs
                     const MatF &em = S.mats[hid];
                     const F3 cx = mk(em.px, em.py, em.pz) - o;
                     float omc = one_minus_cos_max(em.r * em.r / dot(cx, cx));
-                    if (FACET) {
+                    if (diel) L = L + had(dielectric_direct(em, o, wi_l.z, refracted, gpdf_loop), beta) * k.inv_cp;
+                    else if (FACET) {
                         const float gpdf = facet_pdf(wo_l, wh, obj.alpha);
                         const F3 g = had(mk(em.lr, em.lg, em.lb), facet_brdf(obj, wi_l, wh, wo_l)) * (wi_l.z / gpdf);
                         if (!(g.x > 0.0f)) omc = omc_last;

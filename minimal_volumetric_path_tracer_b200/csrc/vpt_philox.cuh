@@ -11,13 +11,15 @@
 //   0 roulette   1 light pick   2 distance (free-flight xi or equi-angular xi)   3 equi-angular surface/medium decision
 //   medium vertex : 4,5 NEE cone sample      6,7 phase-function sample
 //   surface vertex: 4,5 BSDF sample (next direction)   6,7 BSDF-sampled direct light (MISv2)   8+2a, 9+2a cone sample of area light a
+//                   dielectric (material 2): 4 and 6 only (one draw each), 40+a reflect-or-refract pdf choice per area light a
 //   pixel jitter (rt.cpp:787): slots 0,1 of the pseudo-bounce 0xffffffff
 #pragma once
 #include <stdint.h>
 
 namespace vpt {
 
-enum : uint32_t { S_RR = 0, S_SRC = 1, S_DIST = 2, S_DECIDE = 3, S_NEE = 4, S_PHASE = 6, S_BSDF = 4, S_MIS = 6, S_AREA = 8 };
+enum : uint32_t { S_RR = 0, S_SRC = 1, S_DIST = 2, S_DECIDE = 3, S_NEE = 4, S_PHASE = 6, S_BSDF = 4, S_MIS = 6, S_AREA = 8,
+                  S_DIEL = 40 }; // + a: a dielectric surface's extra draw per area light a (misSamplingFunctions.h:116); S_AREA + 2a stays below 40
 constexpr uint32_t kJitterBounce = 0xffffffffu;
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {

@@ -367,7 +367,7 @@ struct SmWave {
                 o = fma3(d, t, o);
                 const F3 lx = mk(sm.px, sm.py, sm.pz) - o;
                 to_sp = !(sm.r > 0.0f && dot(lx, lx) > sm.r * sm.r); // pLight is zero for an area source seen from outside it
-                to_sf = !to_sp && obj.material == 1;
+                to_sf = !to_sp && obj.material != 0; // microfacet and dielectric
                 to_sl = !to_sp && !to_sf;
                 S.r1[s] = (uint32_t)src | ((uint32_t)hid << 8);
             } else {
@@ -449,7 +449,7 @@ struct SmWave {
             ++scans;
             if (!hit || t > dist * (1.0f - 1e-4f)) { S.lr[s] += C.x; S.lg[s] += C.y; S.lb[s] += C.z; }
         }
-        route(act ? (facet ? SQ_SURF_F : SQ_SURF_L) : -1, slot);
+        route(act ? (obj.material != 0 ? SQ_SURF_F : SQ_SURF_L) : -1, slot);
     }
     // microfacet BRDF for world-space directions (rare: kept out of line so that the Lambert stages stay small)
     static __device__ __noinline__ F3 facet_eval_world(const MatF &obj, F3 n_, F3 wi, F3 d) {
@@ -476,6 +476,13 @@ struct SmWave {
         const F3 wo_l = FACET ? unit(to_local(fr, -d)) : mk(0, 0, 1);
         const F3 albedo = mk(obj.cr, obj.cg, obj.cb);
         float omc_last = 1.0f;
+        // material 2 (dielectric, as written in the reference: vpt_f32.cuh dielectric_setup) shares this stage with the microfacet: its
+        // light-sampled terms are zero (samplingFunctions.h:190), the loop below only runs its scans in step with the other lanes
+        const bool diel = FACET && obj.material == 2;
+        DielF di; di.F = 0.0f; di.wr = di.wt = mk(0, 0, 1);
+        if (diel) di = dielectric_setup(wo_l);
+        float gpdf_loop = 0.0f; // the pdf the reference's light loop leaves behind for the dielectric's BSDF term (misSamplingFunctions.h:110-118,148)
+        bool refracted = false;
         uint4 ra = make_uint4(0, 0, 0, 0);
         for (int a = 0; a < sc.n_area; ++a) { // muestreoSA for every area light (misSamplingFunctions.h:105-118)
             if ((a & 1) == 0) ra = philox_block(pixel, sample, depth, 2 + (a >> 1), lp.key0, lp.key1);
@@ -491,7 +498,7 @@ struct SmWave {
             const bool hit = scan_sm(S.scene, o, wi, t, hid);
             if (act) {
                 ++scans;
-                if ((hit ? hid : 0) == lid) { // id stays 0 on a miss, samplingFunctions.h:196
+                if ((hit ? hid : 0) == lid && !diel) { // id stays 0 on a miss, samplingFunctions.h:196
                     const float cos_i = dot(n_, wi);
                     F3 f = albedo * kInvPi;
                     float gpdf = cos_i * kInvPi;
@@ -506,8 +513,18 @@ struct SmWave {
         { // the BSDF-sampled term of MISv2 (:124-167): slots S_MIS = lanes 2,3 of block 1
             const float xi1 = u32_to_unit_f32(b1.z), xi2 = u32_to_unit_f32(b1.w);
             F3 wi_l, wh = mk(0, 0, 1);
-            if (FACET) { wh = facet_normal(obj.alpha, xi1, xi2); wi_l = unit(fma3(wh, 2.0f * dot(wh, wo_l), -wo_l)); }
-            else wi_l = cosine_local(xi1, xi2);
+            if (FACET) {
+                wh = facet_normal(obj.alpha, xi1, xi2); wi_l = unit(fma3(wh, 2.0f * dot(wh, wo_l), -wo_l));
+                if (diel) { // softDielectric (samplingFunctions.h:209-235): reflect with probability F, else the reference's refraction
+                    if (sc.n_area > 0) {
+                        const uint32_t slot = S_DIEL + (uint32_t)sc.n_area - 1u;
+                        const float xg = u32_to_unit_f32(pick_lane(philox_block(pixel, sample, depth, slot >> 2, lp.key0, lp.key1), slot & 3u));
+                        gpdf_loop = xg > di.F ? 1.0f - di.F : di.F;
+                    }
+                    refracted = !(xi1 < di.F);
+                    wi_l = refracted ? di.wt : di.wr;
+                }
+            } else wi_l = cosine_local(xi1, xi2);
             const F3 wi = unit(to_world(fr, wi_l));
             float t; int hid;
             const bool hit = scan_sm(S.scene, o, wi, t, hid);
@@ -517,7 +534,8 @@ struct SmWave {
                     const MatF &em = S.scene.mats[hid];
                     const F3 cx = mk(em.px, em.py, em.pz) - o;
                     float omc = one_minus_cos_max(em.r * em.r / dot(cx, cx));
-                    if (FACET) {
+                    if (diel) L = L + had(dielectric_direct(em, o, wi_l.z, refracted, gpdf_loop), beta) * k.inv_cp;
+                    else if (FACET) {
                         const float gpdf = facet_pdf(wo_l, wh, obj.alpha);
                         const F3 g = had(mk(em.lr, em.lg, em.lb), facet_brdf(obj, wi_l, wh, wo_l)) * (wi_l.z / gpdf);
                         if (!(g.x > 0.0f)) omc = omc_last; // the reference's stale costhetaMax (:162)

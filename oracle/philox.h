@@ -10,6 +10,7 @@
  *       0 roulette   1 light pick   2 distance (free-flight xi or equi-angular xi)   3 equi-angular surface/medium decision
  *       medium vertex : 4,5 NEE cone sample      6,7 phase-function sample
  *       surface vertex: 4,5 BSDF sample (next direction)   6,7 BSDF-sampled direct light (MISv2)   8+2a, 9+2a cone sample of area light a
+ *                       dielectric (material 2): 4 and 6 only (one draw each), 40+a reflect-or-refract pdf choice per area light a
  *   pixel jitter (rt.cpp:787): slots 0,1 of the pseudo-bounce 0xffffffff
  *   uniform = (2 * (word >> 9) + 1) * 2^-24      in (0, 1): never 0 or 1, exactly representable in fp32 and fp64
  */

@@ -24,8 +24,11 @@
  *     them in the reference can change a result when the ray missed.
  *   - MISv2's `costhetaMax` is uninitialised when the scene has no area light and the BSDF sample
  *     of a microfacet surface returns g.x <= 0 (misSamplingFunctions.h:162): here it starts at 0.
- *   - materials 2 (dielectric) and 3 (volumetric sphere) are outside the hot-path scope table
- *     (SURVEY.md section 8f item 3); scenes using them are rejected by the C API.
+ *   - material 2 (dielectric): MISv2 reads `gpdf` uninitialised when no area light with radiance.x > 0 exists
+ *     (misSamplingFunctions.h:148): here it starts at 0 (weight 0).  Everything else of material 2 is restated AS WRITTEN, including
+ *     refraxDielectric's `sqrt(..) - 1` and its -etat/etai scaling (microFacetUtilities.h:130-134).
+ *   - material 3 (volumetric sphere) is outside the hot-path scope table: in the three active methods bdsf
+ *     (vptShadeMethods.h:16-59) leaves `prob` and the new direction unset for it; scenes using it are rejected by the C API.
  * Two reference behaviours are decided by FP64 rounding; both are
  * reproduced by default and can be switched to a well-defined alternative:
  *   quirk R0_FALLTHROUGH   on: as reference.  off: scene scans skip r == 0 spheres, so the point-light
@@ -48,7 +51,8 @@ constexpr double kMaxFloat = 3.40282346638528859811704183484516925e+38; /* MAXFL
 constexpr double kPi = 3.14159265358979323846;                          /* M_PI */
 /* Philox slot of every draw (oracle/philox.h); sequential streams (erand48, explicit lists) ignore the slot, so the
  * CONSUMPTION ORDER below stays the reference's. */
-enum : unsigned { S_RR = 0, S_SRC = 1, S_DIST = 2, S_DECIDE = 3, S_NEE = 4, S_PHASE = 6, S_BSDF = 4, S_MIS = 6, S_AREA = 8 };
+enum : unsigned { S_RR = 0, S_SRC = 1, S_DIST = 2, S_DECIDE = 3, S_NEE = 4, S_PHASE = 6, S_BSDF = 4, S_MIS = 6, S_AREA = 8,
+                  S_DIEL = 40 /* + a: the dielectric's extra draw per area light (misSamplingFunctions.h:116); S_AREA + 2a stays below 40 */ };
 
 enum : unsigned { QUIRK_R0_FALLTHROUGH = 1u, QUIRK_EXACT_VISIBILITY = 2u };
 
@@ -286,6 +290,18 @@ static inline double fresnel_dielectric(double etai, double etat, double ct, dou
     return 0.5 * (par + perp);
 }
 
+/* reflexDielectric :117-120 (wi = outgoing direction, -ray.d) */
+static inline Vec reflect_dielectric(const Vec &wi, const Vec &n) { return wi * -1 + n * dot(n, wi) * 2; }
+/* refraxDielectric :122-141, as written */
+static inline Vec refract_dielectric(double etai, double etat, const Vec &wi, const Vec &n) {
+    const Vec wl = to_local(n, wi);
+    const double ratio = etat / etai * -1;
+    const double cosinei = dot(wi, n);
+    const double invratio = etai / etat;
+    const double cosinet = std::sqrt(1 - invratio * invratio * (1 - cosinei * cosinei)) - 1;
+    return from_local(n, wl.x * ratio, wl.y * ratio, cosinet);
+}
+
 /* powerHeuristics, misSamplingFunctions.h:12-16 */
 static inline double power_heuristic(double f, double g) {
     const double f2 = f * f, g2 = g * g;
@@ -349,12 +365,33 @@ static inline Vec bsdf_sampled_direct_facet(Scene &sc, const Vec &x, const Vec &
     return had(Le, fr) * dot(nl, wi) * (1 / facet_pdf(wo, wh, alpha, nl));
 }
 
-/* MISv2, misSamplingFunctions.h:96-170 (materials 0 and 1) */
+/* softDielectric, samplingFunctions.h:209-235 (called as softDielectric(1.5, 1.0, wo, ...): etat = 1.5, etai = 1.0) */
+template <class Rng>
+static inline Vec bsdf_sampled_direct_dielectric(Rng &rng, Scene &sc, double etat, double etai, const Vec &wi, const Vec &n, const Vec &x, int &source) {
+    Vec Ld;
+    int sid = -1;
+    Vec wt = refract_dielectric(etai, etat, wi, n);
+    wt = unit(wt);
+    const double F = fresnel_dielectric(etai, etat, dot(n, wt), dot(n, wi));
+    if (rng.next(S_MIS) < F) {
+        Vec wr = reflect_dielectric(wi, n);
+        wr = unit(wr);
+        Ld = first_hit_radiance(sc, x, wr, sid) * (1 / std::fabs(dot(n, wr)));
+    } else {
+        const double ratio = etat / etai;
+        Ld = first_hit_radiance(sc, x, wt, sid) * (1 / std::fabs(dot(n, wt))) * ratio * ratio;
+    }
+    source = sid;
+    return Ld;
+}
+
+/* MISv2, misSamplingFunctions.h:96-170 */
 template <class Rng>
 static inline Vec surface_direct_mis(Rng &rng, Scene &sc, const Sphere &obj, const Vec &x, const Vec &n, const Vec &wray, double alpha, double sigma_t) {
     Vec total;
     Vec wo = wray * -1;
     double cos_max = 0; /* reference: uninitialised */
+    double gpdf_loop = 0; /* reference: `gpdf` is function-wide and uninitialised; the dielectric branch reads what the light loop left */
     const int count = (int)sc.s.size();
     unsigned area_index = 0;
     for (int light = 0; light < count; ++light) {
@@ -364,10 +401,16 @@ static inline Vec surface_direct_mis(Rng &rng, Scene &sc, const Sphere &obj, con
             const double fpdf = cone_pdf(cos_max);
             double gpdf;
             if (obj.material == 0) gpdf = cosine_pdf(dot(n, wi_light));
-            else {
+            else if (obj.material == 2) { /* :110-118 */
+                Vec wt = refract_dielectric(1.0, 1.5, wo, n);
+                wt = unit(wt);
+                gpdf = fresnel_dielectric(1.0, 1.5, dot(n, wt), dot(n, wo));
+                if (rng.next(S_DIEL + (area_index - 1)) > gpdf) gpdf = 1 - gpdf;
+            } else {
                 const Vec wh = unit(wi_light + wo);
                 gpdf = facet_pdf(wo, wh, alpha, n);
             }
+            gpdf_loop = gpdf;
             const double wf = power_heuristic(fpdf, gpdf);
             total = total + f * wf;
         }
@@ -383,6 +426,14 @@ static inline Vec surface_direct_mis(Rng &rng, Scene &sc, const Sphere &obj, con
             cos_max = cone_cos(sc, source, x);
             const double fpdf = cone_pdf(cos_max);
             wg = power_heuristic(gpdf, fpdf);
+        } else wg = 0;
+    } else if (obj.material == 2) { /* :144-152 */
+        int source = -1;
+        g = bsdf_sampled_direct_dielectric(rng, sc, 1.5, 1.0, wo, n, x, source);
+        if (g.x > 0 && g.y > 0 && g.z > 0) {
+            cos_max = cone_cos(sc, source, x);
+            const double fpdf = cone_pdf(cos_max);
+            wg = power_heuristic(gpdf_loop, fpdf);
         } else wg = 0;
     } else {
         const Vec wh = facet_normal(rng, alpha, S_MIS);
@@ -417,7 +468,7 @@ static inline Vec point_light_direct(Scene &sc, const Sphere &obj, const Vec &x,
     return had(Le, fr) * dot(n, unit(light - x));
 }
 
-/* bdsf, vptShadeMethods.h:16-59 (materials 0 and 1) */
+/* bdsf, vptShadeMethods.h:16-59 */
 template <class Rng>
 static inline Vec bsdf_sample(Rng &rng, const Scene &sc, Vec &wi_out, const Vec &wray, const Vec &n, double &pdf, int id) {
     const Sphere &obj = sc.s[id];
@@ -427,6 +478,22 @@ static inline Vec bsdf_sample(Rng &rng, const Scene &sc, Vec &wi_out, const Vec 
         const Vec wi = cosine_hemisphere(rng, n, S_BSDF);
         fs = obj.c * (1 / kPi);
         pdf = cosine_pdf(dot(n, wi));
+        wi_out = wi;
+    } else if (obj.material == 2) { /* :26-46 */
+        Vec wt = refract_dielectric(1.0, 1.5, wo, n);
+        wt = unit(wt);
+        const double F = fresnel_dielectric(1.0, 1.5, dot(n, wt), dot(n, wo));
+        Vec wi;
+        if (rng.next(S_BSDF) < F) {
+            wi = reflect_dielectric(wo, n);
+            wi = unit(wi);
+            fs = Vec(1, 1, 1) * (1 / dot(n, wi)) * F;
+            pdf = F;
+        } else {
+            wi = wt;
+            fs = Vec(1, 1, 1) * (1 / dot(n, wi)) * (1 - F) * 1.5 * 1.5;
+            pdf = 1 - F;
+        }
         wi_out = wi;
     } else {
         const double alpha = obj.alpha;

@@ -25,7 +25,7 @@ static int check_scene(const double *d, int n) {
     int emitters = 0;
     for (int i = 0; i < n; ++i) {
         const Sphere s = S(d + 18 * i);
-        if (s.material != 0 && s.material != 1) return -2;
+        if (s.material != 0 && s.material != 1 && s.material != 2) return -2;
         if (s.emits()) ++emitters;
     }
     if (emitters > VPT_ORACLE_MAX_EMITTERS) return -3;

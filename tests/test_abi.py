@@ -75,8 +75,10 @@ def test_argument_validation_precedes_device_work(vpt):
     assert _rc(vpt, P(kernel=9)) == INVALID
     for wave in (vpt.KERNEL_WAVEFRONT, vpt.KERNEL_WAVEFRONT_SM, vpt.KERNEL_WAVEFRONT_HBM):      # the on-chip wavefront kernels are FP32 only
         assert _rc(vpt, P(kernel=wave, precision=vpt.PRECISION_FP64_REF)) == UNSUPPORTED
-    rows = DEFAULT_SCENE.copy(); rows[6, 10] = 2                             # dielectric: outside the hot-path scope
+    rows = DEFAULT_SCENE.copy(); rows[6, 10] = 3                             # volumetric sphere: undefined in the reference's active methods
     assert _rc(vpt, P(), vpt.scene_from_rows(rows)) == UNSUPPORTED
+    rows[6, 10] = 4
+    assert _rc(vpt, P(), vpt.scene_from_rows(rows)) == SCENE
     rows = DEFAULT_SCENE.copy(); rows[6, 0] = -1
     assert _rc(vpt, P(), vpt.scene_from_rows(rows)) == SCENE
     many = np.tile(DEFAULT_SCENE[7], (17, 1))                                # 17 emitters > VPT_MAX_EMITTERS (reference: UB beyond 4)

@@ -6,6 +6,7 @@ oracle/Makefile).  Run in the build container only (the reference tree does not 
   python tools/gen_golden.py images    -> tests/golden/image_*.npz    16x16-block statistics of whole renders
   python tools/gen_golden.py scenes    -> tests/golden/scenes.npz     per-path radiance on the reference's commented alternate scenes (scenes/*.txt)
   python tools/gen_golden.py march     -> tests/golden/march.npz      rayMarching3 (rayMarchingMethods.h:330) on fixed rays
+  python tools/gen_golden.py dielectric -> tests/golden/dielectric.npz per-path radiance with material-2 (dielectric) spheres in the scene
 """
 import os
 import sys
@@ -242,6 +243,39 @@ def gen_scenes():
     print("scenes.npz written:", len(out), "arrays")
 
 
+def dielectric_scenes():
+    """material 2 appears in no scene of Sphere.cpp; its code (bdsf vptShadeMethods.h:26-46, softDielectric samplingFunctions.h:209, the
+    dielectric branches of MISv2 misSamplingFunctions.h:110-118,144-152) is reachable by giving a sphere material 2: the blue ball, and both balls"""
+    a = DEFAULT_SCENE.copy(); a[6, 10] = 2
+    b = DEFAULT_SCENE.copy(); b[5, 10] = 2; b[6, 10] = 2
+    return {"glass6": a, "glass56": b}
+
+
+def gen_dielectric():
+    """the UNMODIFIED reference with dielectric spheres: 240 seeded paths (half aimed at the ball) per scene, method and quirk setting"""
+    l0 = L0(); l1 = L1(); rng = np.random.default_rng(2024)
+    N = 240
+    o, d = rand_rays(rng, l1, N)
+    for i in range(0, N, 2):
+        v = DEFAULT_SCENE[6 if i % 4 == 0 else 5, 1:4] + rng.normal(size=3) * 8 - o[i]; d[i] = v / np.linalg.norm(v)
+    seeds = rng.integers(0, 65536, (N, 3))
+    out = {"o": o, "d": d, "seeds": seeds}
+    for name, rows in dielectric_scenes().items():
+        out["rows_" + name] = rows
+        l0.set_scene(rows)
+        for quirks in (3, 0):
+            l0.set_quirks(quirks)
+            for method in (0, 1, 2):
+                res = np.zeros((N, 4))
+                for i in range(N):
+                    L, nd = l0.radiance(method, o[i], d[i], SA, SS, seed3=tuple(int(s) for s in seeds[i]))
+                    res[i, :3] = L; res[i, 3] = nd
+                out["%s_q%d_m%d" % (name, quirks, method)] = res
+    l0.reset_scene(); l0.set_quirks(3)
+    np.savez_compressed(os.path.join(GOLD, "dielectric.npz"), **out)
+    print("dielectric.npz written:", len(out), "arrays")
+
+
 def gen_march():
     """rayMarching3 of the UNMODIFIED reference (as shipped: quirks 3) and with the robust hooks (quirks 0) on 96 rays: the literals of the
     commented call rt.cpp:791 (sigma 0.001 / 0.0125, step 0.1, source 7), the point light (source 8) and a coarser step"""
@@ -297,6 +331,8 @@ if __name__ == "__main__":
         gen_paths()
     if what in ("scenes", "all"):
         gen_scenes()
+    if what in ("dielectric", "all"):
+        gen_dielectric()
     if what in ("march", "all"):
         gen_march()
     if what in ("images", "all"):
