@@ -39,31 +39,54 @@ enum : int { SQ_PRIMARY = 0, SQ_MED_POINT, SQ_MED_AREA, SQ_SURF_P, SQ_SURF_L, SQ
 // SURF_F, SURF_L, PRIMARY, MED_AREA, MED_POINT, SURF_P, generation
 constexpr unsigned kRankStage = 0x6312045u;
 
-// the scene as the scan and the shading code read it; first in the CTA's shared memory (the unit kernels stage only this part)
+// the scene as the scan and the shading code read it; first in the CTA's shared memory (the unit kernels stage only this part).
+// Scan records are stored in PAIRS for the packed FP32 instructions of sm_100 (FFMA2 / FADD2 / FMUL2: two lanes per issue slot -- the
+// kernel is issue bound, not FMA-pipe bound, profiles/r1_summary.md): component c of spheres 2j and 2j+1 sits in one 64-bit half of a float4.
 struct SmScene {
     MatF mats[kMaxSpheres];
-    float4 ga[2 * kMaxSpheres]; // general-form spheres: (qx qy qz c0) (mx my mz -)
-    float4 gb[kMaxSpheres];     // direct-root spheres: (px py pz r^2)
-    int gid[2 * kMaxSpheres];   // scan order -> caller's sphere index (general ones first)
-    int n_ga, n_gb;
+    float4 ga[2 * kMaxSpheres]; // general-form pair j: (qx0 qx1 qy0 qy1) (qz0 qz1 c0_0 c0_1) (mx0 mx1 my0 my1) (mz0 mz1 - -)
+    float4 gb[kMaxSpheres];     // direct-root pair j:  (px0 px1 py0 py1) (pz0 pz1 r2_0 r2_1)
+    int gid[2 * kMaxSpheres + 2]; // scan slot -> caller's sphere index (general pairs first; -1: the padding slot of an odd class)
+    int n_pa, n_pb;             // pairs per class
 };
 // cooperative staging by the whole block (call, then __syncthreads).  Scan order: general-form spheres (huge / re-anchored ones and anything
 // with r >= 64) first, in scene order, then the direct-root ones; every scan record finds its place with one pass over its predecessors.
+// An odd class is padded with a record that no ray can hit (negative discriminant for every ray).
 __device__ __forceinline__ void stage_scene(SmScene &S, const SceneF &sc, int tid, int n_threads) {
     for (int i = tid; i < sc.n_spheres * (int)(sizeof(MatF) / 4); i += n_threads)
         reinterpret_cast<uint32_t *>(S.mats)[i] = reinterpret_cast<const uint32_t *>(sc.mat)[i];
+    int n_general = 0;
+    for (int g = 0; g < sc.n_geom; ++g) n_general += (sc.geom[g].big || sc.geom[g].r2 >= kSimpleRootMaxR2);
+    const int n_direct = sc.n_geom - n_general, n_pa = (n_general + 1) >> 1, n_pb = (n_direct + 1) >> 1;
+    float *ga = reinterpret_cast<float *>(S.ga), *gb = reinterpret_cast<float *>(S.gb);
     if (tid < sc.n_geom) {
         const GeomF &G = sc.geom[tid];
         const bool general = G.big || G.r2 >= kSimpleRootMaxR2;
-        int before_same = 0, n_general = 0;
-        for (int g = 0; g < sc.n_geom; ++g) {
-            const bool gg = sc.geom[g].big || sc.geom[g].r2 >= kSimpleRootMaxR2;
-            n_general += gg;
-            before_same += (g < tid && gg == general);
+        int before_same = 0;
+        for (int g = 0; g < tid; ++g) before_same += ((sc.geom[g].big || sc.geom[g].r2 >= kSimpleRootMaxR2) == general);
+        const int pair = before_same >> 1, h = before_same & 1;
+        if (general) {
+            float *r = ga + 16 * pair + h;
+            r[0] = G.qx; r[2] = G.qy; r[4] = G.qz; r[6] = G.c0; r[8] = G.mx; r[10] = G.my; r[12] = G.mz; r[14] = 0.0f;
+            S.gid[before_same] = G.id;
+        } else {
+            float *r = gb + 8 * pair + h;
+            r[0] = G.qx; r[2] = G.qy; r[4] = G.qz; r[6] = G.r2;
+            S.gid[2 * n_pa + before_same] = G.id;
         }
-        if (general) { S.ga[2 * before_same] = make_float4(G.qx, G.qy, G.qz, G.c0); S.ga[2 * before_same + 1] = make_float4(G.mx, G.my, G.mz, 0.0f); S.gid[before_same] = G.id; }
-        else { S.gb[before_same] = make_float4(G.qx, G.qy, G.qz, G.r2); S.gid[n_general + before_same] = G.id; }
-        if (tid == 0) { S.n_ga = n_general; S.n_gb = sc.n_geom - n_general; }
+    }
+    if (tid == 0) {
+        S.n_pa = n_pa; S.n_pb = n_pb;
+        if (n_general & 1) { // c = |oq|^2 + 1e30 > b^2: never hit
+            float *r = ga + 16 * (n_pa - 1) + 1;
+            r[0] = 0.0f; r[2] = 0.0f; r[4] = 0.0f; r[6] = 1e30f; r[8] = 0.0f; r[10] = 0.0f; r[12] = 0.0f; r[14] = 0.0f;
+            S.gid[n_general] = -1;
+        }
+        if (n_direct & 1) { // r^2 = -1: never hit
+            float *r = gb + 8 * (n_pb - 1) + 1;
+            r[0] = 0.0f; r[2] = 0.0f; r[4] = 0.0f; r[6] = -1.0f;
+            S.gid[2 * n_pa + n_direct] = -1;
+        }
     }
 }
 
@@ -126,41 +149,60 @@ __device__ __forceinline__ SmShared &sm_shared() { return *reinterpret_cast<SmSh
 // One out-of-line copy: it is called from seven places and must stay resident in the instruction cache.
 struct ScanHit { float t; int index; };
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; } // MUFU.RCP, as __fdividef
+// sign flip that ptxas folds into the operand modifiers of the packed instructions: `neg.f32` without .ftz (under -ftz=true the compiler's
+// own negation is neg.ftz = a separate flushing FADD per lane; the consuming .FTZ instruction flushes anyway)
+__device__ __forceinline__ float neg_fold(float x) { float r; asm("neg.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(neg_fold(a.x), neg_fold(a.y)); }
+__device__ __forceinline__ float2 lo2(float4 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(float4 v) { return make_float2(v.z, v.w); }
 static __device__ __noinline__ ScanHit scan_sm_call(float ox, float oy, float oz, float dx, float dy, float dz) {
     const SmScene &S = *reinterpret_cast<const SmScene *>(smwave_smem);
-    const F3 o = mk(ox, oy, oz), d = mk(dx, dy, dz);
     // Selection without compares: the reference accepts the near root unless it is below 1e-4, else the far one, and then requires
     // t > 1e-4 (Sphere.h:34, pathTracingUtilities.h:20) = the smallest root above 1e-4.  For w = root - 1e-4 the valid candidates are
     // exactly the positive floats, whose bit patterns order like unsigned integers, while negative values (sign bit) and the NaN of a
     // negative discriminant (0x7fffffff) compare above +inf: ONE three-input unsigned minimum per sphere replaces four compares and
     // selects on the half-rate ALU pipe (ncu: ALU 41 % busy, FMA 25 %); the index follows with one compare and one select.
+    // Two spheres per iteration: every add / multiply / fma below is one packed instruction for both (same IEEE roundings as the scalar
+    // form, so the roots are bit-identical to a one-sphere-at-a-time scan); the ray's components are broadcast operands.
     unsigned best = 0x7f800000u; // +inf
     int bi = -1;
-    const int na = S.n_ga, nb = S.n_gb;
-    for (int i = 0; i < na; ++i) {
-        const float4 a = S.ga[2 * i], m = S.ga[2 * i + 1];
-        const F3 oq = mk(o.x - a.x, o.y - a.y, o.z - a.z);
-        const F3 op = mk(oq.x + m.x, oq.y + m.y, oq.z + m.z);
-        const float b = dot(op, d);
-        const float c = fmaf(oq.x, op.x + m.x, fmaf(oq.y, op.y + m.y, fmaf(oq.z, op.z + m.z, a.w))); // |op|^2 - r^2 without cancellation
-        const float det = fmaf(b, b, -c);
-        const float sq = det * rsqrtf(det); // NaN when det <= 0
-        const float q = -(b + copysignf(sq, b)); // the root without cancellation; the other one is c / q
-        const float w1 = q - kEps, w2 = fmaf(c, rcp_approx(q), -kEps);
-        const unsigned k = __vimin3_u32(best, __float_as_uint(w1), __float_as_uint(w2));
-        if (k != best) bi = i;
+    const int na = S.n_pa, nb = S.n_pb;
+    const float2 ox2 = make_float2(ox, ox), oy2 = make_float2(oy, oy), oz2 = make_float2(oz, oz);
+    const float2 dx2 = make_float2(dx, dx), dy2 = make_float2(dy, dy), dz2 = make_float2(dz, dz);
+    const float2 meps = make_float2(-kEps, -kEps);
+    for (int j = 0; j < na; ++j) {
+        const float4 A = S.ga[4 * j], B = S.ga[4 * j + 1], C = S.ga[4 * j + 2], E = S.ga[4 * j + 3];
+        const float2 mx = lo2(C), my = hi2(C), mz = lo2(E);
+        const float2 oqx = __fadd2_rn(ox2, neg2(lo2(A))), oqy = __fadd2_rn(oy2, neg2(hi2(A))), oqz = __fadd2_rn(oz2, neg2(lo2(B)));
+        const float2 opx = __fadd2_rn(oqx, mx), opy = __fadd2_rn(oqy, my), opz = __fadd2_rn(oqz, mz);
+        const float2 b = __ffma2_rn(opx, dx2, __ffma2_rn(opy, dy2, __fmul2_rn(opz, dz2)));
+        const float2 c = __ffma2_rn(oqx, __fadd2_rn(opx, mx), __ffma2_rn(oqy, __fadd2_rn(opy, my), __ffma2_rn(oqz, __fadd2_rn(opz, mz), hi2(B)))); // |op|^2 - r^2 without cancellation
+        const float2 det = __ffma2_rn(b, b, neg2(c));
+        const float2 sq = __fmul2_rn(det, make_float2(rsqrtf(det.x), rsqrtf(det.y))); // NaN when det <= 0
+        const float2 q = __fadd2_rn(neg2(b), neg2(make_float2(copysignf(sq.x, b.x), copysignf(sq.y, b.y)))); // the root without cancellation; the other one is c / q
+        const float2 w1 = __fadd2_rn(q, meps), w2 = __ffma2_rn(c, make_float2(rcp_approx(q.x), rcp_approx(q.y)), meps);
+        unsigned k = __vimin3_u32(best, __float_as_uint(w1.x), __float_as_uint(w2.x));
+        if (k != best) bi = 2 * j;
+        best = k;
+        k = __vimin3_u32(best, __float_as_uint(w1.y), __float_as_uint(w2.y));
+        if (k != best) bi = 2 * j + 1;
         best = k;
     }
-    for (int i = 0; i < nb; ++i) {
-        const float4 a = S.gb[i];
-        const F3 oq = mk(o.x - a.x, o.y - a.y, o.z - a.z);
-        const float b = dot(oq, d);
-        const F3 l = fma3(d, -b, oq);
-        const float det = fmaf(-l.x, l.x, fmaf(-l.y, l.y, fmaf(-l.z, l.z, a.w)));
-        const float sq = det * rsqrtf(det);
-        const float nbe = -b - kEps;
-        const unsigned k = __vimin3_u32(best, __float_as_uint(nbe - sq), __float_as_uint(nbe + sq));
-        if (k != best) bi = na + i;
+    for (int j = 0; j < nb; ++j) {
+        const float4 A = S.gb[2 * j], B = S.gb[2 * j + 1];
+        const float2 oqx = __fadd2_rn(ox2, neg2(lo2(A))), oqy = __fadd2_rn(oy2, neg2(hi2(A))), oqz = __fadd2_rn(oz2, neg2(lo2(B)));
+        const float2 b = __ffma2_rn(oqx, dx2, __ffma2_rn(oqy, dy2, __fmul2_rn(oqz, dz2)));
+        const float2 nb2 = neg2(b);
+        const float2 lx = __ffma2_rn(dx2, nb2, oqx), ly = __ffma2_rn(dy2, nb2, oqy), lz = __ffma2_rn(dz2, nb2, oqz);
+        const float2 det = __ffma2_rn(neg2(lx), lx, __ffma2_rn(neg2(ly), ly, __ffma2_rn(neg2(lz), lz, hi2(B))));
+        const float2 sq = __fmul2_rn(det, make_float2(rsqrtf(det.x), rsqrtf(det.y)));
+        const float2 nbe = __fadd2_rn(nb2, meps);
+        const float2 w1 = __fadd2_rn(nbe, neg2(sq)), w2 = __fadd2_rn(nbe, sq);
+        unsigned k = __vimin3_u32(best, __float_as_uint(w1.x), __float_as_uint(w2.x));
+        if (k != best) bi = 2 * (na + j);
+        best = k;
+        k = __vimin3_u32(best, __float_as_uint(w1.y), __float_as_uint(w2.y));
+        if (k != best) bi = 2 * (na + j) + 1;
         best = k;
     }
     return ScanHit{__uint_as_float(best) + kEps, bi};
