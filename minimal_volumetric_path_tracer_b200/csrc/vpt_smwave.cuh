@@ -27,7 +27,10 @@
 namespace vpt {
 namespace f32 {
 
-constexpr int kSmThreads = 768;
+#ifndef VPT_SM_THREADS
+#define VPT_SM_THREADS 768 // by measurement; tools/build_variant.py builds other values for comparison
+#endif
+constexpr int kSmThreads = VPT_SM_THREADS;
 constexpr int kSmPool = 2048;         // path records per CTA (power of two)
 constexpr int kSmMaxItemPixels = 256; // pixels per work item (power of two multiple of kTile)
 constexpr float kSmFixScale = 1073741824.0f; // 2^30
@@ -663,7 +666,7 @@ struct SmWave {
         const unsigned total = __shfl_sync(0xffffffffu, incl, 7);
         if (lane == 0) {
             S.t_cursor[0] = cur0 + (gen == 0 ? n_gen : 0u); S.t_cursor[1] = cur1 + (gen == 1 ? n_gen : 0u);
-            S.flush_slot = flush; S.gen_slot = gen; S.round_claim = 0u; S.tail_budget = n_free - n_gen; S.tail_used = 0u;
+            S.flush_slot = flush; S.gen_slot = gen; S.round_claim = (unsigned)(kSmThreads / 32); S.tail_budget = n_free - n_gen; S.tail_used = 0u;
             S.exit_flag = (total == 0u && flush < 0 && gen < 0) ? 1 : 0; // nothing queued, nothing to generate, nothing to write out
         }
     }
@@ -702,11 +705,12 @@ struct SmWave {
 #endif
             const unsigned total = S.rb_first[7];
             const int gen_slot = S.gen_slot;
+            // the first batch of a round needs no atomic: warp w takes batch w, the claim counter starts behind those (plan_round); the batch
+            // table does not change during a round: read it once
             unsigned raw = 0;
-            if (lane == 0) raw = smem_add(&S.round_claim, 1u, lz);
-            unsigned kb = __shfl_sync(0xffffffffu, raw, 0);
+            unsigned kb = (unsigned)tid >> 5;
+            const uint4 f0 = *reinterpret_cast<const uint4 *>(&S.rb_first[0]), f1 = *reinterpret_cast<const uint4 *>(&S.rb_first[4]);
             while (kb < total) {
-                const uint4 f0 = *reinterpret_cast<const uint4 *>(&S.rb_first[0]), f1 = *reinterpret_cast<const uint4 *>(&S.rb_first[4]);
                 const int rank = (kb >= f0.y) + (kb >= f0.z) + (kb >= f0.w) + (kb >= f1.x) + (kb >= f1.y) + (kb >= f1.z);
                 const unsigned start = S.rb_begin[rank] + ((kb - S.rb_first[rank]) << 5);
                 const int n = (int)min(32u, S.rb_end[rank] - start);

@@ -194,6 +194,41 @@ def test_determinism_and_sample_shards(gpu, precision):
     np.testing.assert_allclose(mean, whole / 24, rtol=3e-7)
 
 
+def test_c3_full_size_properties(gpu):
+    """BASELINE.json config 3 at its full size (1920x1080, 4096 spp, the reference's "MIS" method; 8.5e9 paths): the two halves of the sample
+    range add up to the whole frame (same samples, fp32 store rounding only), a rerun is bit-identical, and the whole-image mean agrees with
+    the unmodified reference's render of the same scene and method (tests/golden/image_robust_m2.npz is 1024x768: same camera, same field of
+    view per unit height, so the image means are comparable to the noise of the reference render)"""
+    p = gpu.default_params(width=1920, height=1080, spp=4096, method=2, seed=3, output=gpu.OUTPUT_SUM)
+    whole, st = gpu.render(p, stats=True)
+    assert st.paths == 1920 * 1080 * 4096 and st.nonfinite <= 1e-8 * st.paths and abs(st.events / st.paths - 1.5) < 1e-3
+    a = gpu.render(p.copy(sample_begin=0, sample_end=2048)); b = gpu.render(p.copy(sample_begin=2048, sample_end=4096))
+    np.testing.assert_allclose(a.astype(np.float64) + b, whole, rtol=3e-7, atol=1e-6)
+    assert np.array_equal(whole, gpu.render(p))
+    g = np.load(os.path.join(GOLDEN, "image_robust_m2.npz"))
+    ref_mean = g["block_mean"].astype(np.float64).mean(axis=(0, 1))
+    ref_sigma = np.sqrt(g["block_var"].astype(np.float64).sum(axis=(0, 1))) / (g["block_var"].shape[0] * g["block_var"].shape[1])
+    # the 16:9 frame sees more of the side walls than the 4:3 one: compare the central 4:3 part (1440 of the 1920 columns)
+    centre = (whole[:, 240:1680].astype(np.float64) / 4096).mean(axis=(0, 1))
+    assert np.all(np.abs(centre - ref_mean) < 5 * ref_sigma + 0.002 * ref_mean), (centre, ref_mean, ref_sigma)
+
+
+def test_c5_frame_size_tiles_and_determinism(gpu):
+    """BASELINE.json config 5's frame (3840x2160 = 64800 tiles of 128 pixels) at a reduced sample count: eight interleaved tile shards -- the
+    8-GPU partition -- reassemble the one-GPU frame bit for bit, and sample shards add up"""
+    p = gpu.default_params(width=3840, height=2160, spp=16, method=2, seed=5, output=gpu.OUTPUT_SUM)
+    whole, st = gpu.render(p, stats=True)
+    assert st.paths == 3840 * 2160 * 16 and whole.shape == (2160, 3840, 3)
+    acc = np.zeros_like(whole)
+    for r in range(8):
+        part = gpu.render(p.copy(tile_rank=r, tile_count=8))
+        assert not (acc != 0).any(axis=-1)[(part != 0).any(axis=-1)].any()   # disjoint
+        acc += part
+    assert np.array_equal(acc, whole)
+    halves = gpu.render(p.copy(sample_begin=0, sample_end=8)).astype(np.float64) + gpu.render(p.copy(sample_begin=8, sample_end=16))
+    np.testing.assert_allclose(halves, whole, rtol=3e-7, atol=1e-7)
+
+
 def test_tile_shards_reassemble_bit_identically(gpu):
     p = gpu.default_params(width=1000, height=333, spp=8, method=0, seed=4)   # 333000 pixels: not a multiple of the 128-pixel tile
     whole = gpu.render(p)
