@@ -725,6 +725,8 @@ struct SmWave {
                 default: SMW_BATCH(6, stage_gen(gen_slot, start, n)); break;
                 }
                 // (claiming the next batch before running this one hides the atomic's latency but commits warps too early: measured slower)
+                // (taking ALL batches round-robin without atomics: 6750 against 7340 -- the dynamic claim is what balances 12 000-cycle SURF_L batches
+                // against 4 000-cycle ones)
                 if (lane == 0) raw = smem_add(&S.round_claim, 1u, lz);
                 kb = __shfl_sync(0xffffffffu, raw, 0);
             }
