@@ -32,6 +32,13 @@ def test_oracle_matches_the_reference_with_dielectric_spheres(l1, gold, name, qu
         check(l1, gold["rows_" + name], quirks, method, gold["o"], gold["d"], gold["seeds"], res)
 
 
+def test_dielectric_scene_file_loads_through_the_abi(vpt, gold):
+    """scenes/glass_ball.txt = the golden scene `glass6`; material 3 stays rejected, other values are malformed"""
+    from conftest import ROOT
+    rows = vpt.scene_to_rows(vpt.load_scene(os.path.join(ROOT, "scenes", "glass_ball.txt")))
+    assert np.array_equal(rows, gold["rows_glass6"])
+
+
 def _list_rows(gold):
     n = len(gold["o"])
     rows = np.zeros((n, 127))
