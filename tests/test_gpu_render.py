@@ -173,6 +173,12 @@ def test_fp32_matches_the_reference_render_at_4096_spp(gpu):
     assert np.all(rmse > 0.3 * sigma)                                           # ... and not suspiciously small either (the estimate means something)
 
 
+def test_c3_matches_the_reference_render(gpu):
+    """BASELINE.json config 3 as written -- 1920x1080, 4096 spp, the reference's "MIS" method -- rendered by the unmodified reference code (robust
+    hooks; tests/golden/image_robust_m2_c3.npz, half an hour of 8 CPU threads) against the GPU: calibrated ensemble test on the 67 x 120 blocks"""
+    check_statistically_equal(z_scores(gpu, "robust_m2_c3", gpu.PRECISION_FP32, 0, spp=16384, stand_ins=4))
+
+
 def test_fp64_robust_matches_reference_with_robust_hooks(gpu):
     check_statistically_equal(z_scores(gpu, "robust_m0", gpu.PRECISION_FP64_REF, 0, spp=512))
 

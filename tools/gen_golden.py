@@ -302,9 +302,11 @@ def gen_images(which=None):
         ("no8_m0", [8], 3, 0, 256), ("no8_m1", [8], 3, 1, 256), ("no8_m2", [8], 3, 2, 256),
         # north_star's correctness render: the "MIS" method at 4096 spp (14 minutes of 8 CPU threads for the 1024x768 frame)
         ("robust_m2_4096", None, 0, 2, 4096),
+        # BASELINE.json config 3 as written: 1920x1080 at 4096 spp (half an hour of 8 CPU threads)
+        ("robust_m2_c3", None, 0, 2, 4096, 1920, 1080),
     ]
-    w, h = 1024, 768
-    for name, drop, quirks, method, spp in jobs:
+    for name, drop, quirks, method, spp, *size in jobs:
+        w, h = size if size else (1024, 768)
         if which and name not in which:
             continue
         path = os.path.join(GOLD, "image_%s.npz" % name)
