@@ -239,6 +239,7 @@ struct SmWave {
     const unsigned lz; // lane * 0, opaque to the compiler (see smem_add)
     const int log_p, item_pixels, n_owned_tiles;
     unsigned events = 0, scans = 0, nonfinite = 0, paths = 0;
+    unsigned next_raw = 0; // lane 0: the next batch of the round, claimed while the tail of the current one is still running (claim_early)
 #ifdef VPT_SMWAVE_PROFILE
     unsigned long long prof[24] = {};
 #endif
@@ -317,9 +318,14 @@ struct SmWave {
     __device__ __forceinline__ uint32_t pixel_of(uint32_t meta) const {
         return (uint32_t)item_pixel(S.t_item[(meta >> 9) & 1u], (int)(meta & 0x1ffu));
     }
+    // The claim for the NEXT batch is issued a few hundred cycles before the current one ends (at the start of its last step: the roulette's
+    // Philox block or the final routing), so that the atomic's round trip is over when the claim loop needs it; early enough to hide the
+    // latency, late enough not to commit a warp to work while others idle (claiming at the START of a batch measured 15 % slower).
+    __device__ __forceinline__ void claim_early() { if (lane == 0) next_raw = smem_add(&S.round_claim, 1u, lz); }
     // roulette for the next bounce (vptShadeMethods.h:1282); a surviving record (already holding o) gets its new direction,
     // throughput, radiance-so-far and the block-0 words of the new bounce
     __device__ __forceinline__ void continue_or_end(bool act, int slot, uint32_t pixel, uint32_t sample, uint32_t meta, F3 d, F3 beta, F3 L) {
+        claim_early();
         bool alive = false;
         if (act) {
             const uint32_t depth = meta >> 10;
@@ -424,6 +430,7 @@ struct SmWave {
             }
             if (!ended) { S.ox[s] = o.x; S.oy[s] = o.y; S.oz[s] = o.z; }
         }
+        claim_early();
         route(to_mp ? SQ_MED_POINT : to_ma ? SQ_MED_AREA : to_sp ? SQ_SURF_P : to_sl ? SQ_SURF_L : to_sf ? SQ_SURF_F : ended ? kFree : -1, slot);
         count_done(ended, meta);
     }
@@ -494,6 +501,7 @@ struct SmWave {
             ++scans;
             if (!hit || t > dist * (1.0f - 1e-4f)) { S.lr[s] += C.x; S.lg[s] += C.y; S.lb[s] += C.z; }
         }
+        claim_early();
         route(act ? (obj.material != 0 ? SQ_SURF_F : SQ_SURF_L) : -1, slot);
     }
     // microfacet BRDF for world-space directions (rare: kept out of line so that the Lambert stages stay small)
@@ -707,7 +715,6 @@ struct SmWave {
             const int gen_slot = S.gen_slot;
             // the first batch of a round needs no atomic: warp w takes batch w, the claim counter starts behind those (plan_round); the batch
             // table does not change during a round: read it once
-            unsigned raw = 0;
             unsigned kb = (unsigned)tid >> 5;
             const uint4 f0 = *reinterpret_cast<const uint4 *>(&S.rb_first[0]), f1 = *reinterpret_cast<const uint4 *>(&S.rb_first[4]);
             while (kb < total) {
@@ -722,13 +729,12 @@ struct SmWave {
                 case 3: SMW_BATCH(SQ_MED_AREA, stage_med<false>(lane < n ? (int)S.queue[SQ_MED_AREA][e] : -1)); break;
                 case 4: SMW_BATCH(SQ_MED_POINT, stage_med<true>(lane < n ? (int)S.queue[SQ_MED_POINT][e] : -1)); break;
                 case 5: SMW_BATCH(SQ_SURF_P, stage_surf_p(lane < n ? (int)S.queue[SQ_SURF_P][e] : -1)); break;
-                default: SMW_BATCH(6, stage_gen(gen_slot, start, n)); break;
+                default: SMW_BATCH(6, stage_gen(gen_slot, start, n)); claim_early(); break;
                 }
                 // (claiming the next batch before running this one hides the atomic's latency but commits warps too early: measured slower)
                 // (taking ALL batches round-robin without atomics: 6750 against 7340 -- the dynamic claim is what balances 12 000-cycle SURF_L batches
                 // against 4 000-cycle ones)
-                if (lane == 0) raw = smem_add(&S.round_claim, 1u, lz);
-                kb = __shfl_sync(0xffffffffu, raw, 0);
+                kb = __shfl_sync(0xffffffffu, next_raw, 0);
             }
             // tail fill: the round's batches are all claimed; instead of idling at the barrier generate camera samples from the budget
             // the plan left over (one free record per sample is guaranteed), they are consumed in the next round
