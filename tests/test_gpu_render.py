@@ -376,6 +376,39 @@ def _stress_scene():
     return np.array(rows)
 
 
+@pytest.mark.parametrize("n_big", [1, 2])
+def test_auto_kernel_per_path_parity_at_the_sphere_limit(gpu, l1, n_big):
+    """VPT_MAX_SPHERES = 32 spheres (the reference's std::vector is unbounded): the default scene plus small Lambert / microfacet balls and
+    n_big spheres of radius >= 64 (general root form), so that the paired scan records of BOTH classes are exercised with even and odd counts
+    (6 or 7 general-form spheres, 25 or 24 direct-root ones incl. the lights; an odd class carries a padding record no ray may hit)"""
+    rng = np.random.default_rng(40 + n_big)
+    rows = [r.copy() for r in DEFAULT_SCENE]
+    z = [0.0] * 7
+    for k in range(n_big):
+        rows.append(np.array([70.0 + 10 * k, -80 + 160 * k, -95 - 10 * k, 20, .4, .5, .6, 0, 0, 0, 0, *z]))
+    while len(rows) < 32:
+        c = [rng.uniform(-40, 40), rng.uniform(-35, 20), rng.uniform(-70, 120)]
+        if rng.random() < 0.25:
+            rows.append(np.array([rng.uniform(2, 5), *c, 0, 0, 0, 0, 0, 0, 1, 0.2, 0.92, 1.1, 3.9, 2.45, 2.14, rng.uniform(0.1, 0.3)]))
+        else:
+            rows.append(np.array([rng.uniform(2, 6), *c, *rng.uniform(0.2, 0.9, 3), 0, 0, 0, 0, *z]))
+    sc = np.array(rows)
+    assert len(sc) == 32
+    w, h = 192, 144
+    for method in (0, 1):
+        p = gpu.default_params(width=w, height=h, spp=1, method=method, seed=17, output=gpu.OUTPUT_SUM)
+        img, st = gpu.render(p, gpu.scene_from_rows(sc), stats=True)
+        ref, _, rst = l1.render(sc, 0, method, SA, SS, w, h, 17, 1, want_sumsq=False)
+        assert st.paths == w * h and st.nonfinite == 0
+        assert abs(int(st.events) - int(rst["events"])) <= 5e-4 * rst["events"] + 2
+        err = np.abs(img - ref).max(axis=2) / np.maximum(np.abs(ref).max(axis=2), 1e-4)
+        assert np.median(err) < 1e-6 and np.mean(err < 1e-5) > 0.98, (float(np.median(err)), float(np.mean(err < 1e-5)))
+        assert np.array_equal(img, gpu.render(p.copy(kernel=gpu.KERNEL_WAVEFRONT_HBM), gpu.scene_from_rows(sc)))
+    with pytest.raises(gpu.VptError) as e:   # 33 spheres: a checked limit
+        gpu.render(gpu.default_params(width=8, height=8, spp=1), gpu.scene_from_rows(np.vstack([sc, sc[-1:]])))
+    assert e.value.status == -2
+
+
 @pytest.mark.parametrize("method", [0, 1, 2, 4])
 def test_auto_kernel_per_path_parity_on_a_scene_not_in_the_reference(gpu, l1, method):
     """the product kernel against the FP64 oracle, one path per pixel, on the stress scene"""
