@@ -167,6 +167,8 @@ typedef enum {
     VPT_UNIT_MIS_DISTANCE = 20,    /* VPT_METHOD_MIS_DISTANCE's distance decision (not in the reference; free-flight vptSamplingFunctions.h:11-20 and
                                       equi-angular volumetricBasicFunctions.h:209 + vptSamplingFunctions.h:60 under the balance heuristic)
                                       in: source_index, tMax, o[3], d[3], sigma_t, xi, xd                out: surface (0/1), distance, mixture pdf */
+    VPT_UNIT_DIELECTRIC = 21,      /* microFacetUtilities.h:107-141 as used by bdsf / softDielectric / MISv2 for material 2 (etai 1, etat 1.5)
+                                      in: n[3], wo[3] (unit, world; wo = -ray direction)   out: normalize(refraxDielectric)[3], normalize(reflexDielectric)[3], fresnelDie */
     VPT_UNIT_COUNT_
 } vpt_unit_fn;
 int vpt_unit(int32_t fn, const vpt_params *p, const vpt_sphere *spheres, int32_t n_spheres, int32_t n, const double *in, int32_t in_stride,

@@ -17,7 +17,7 @@ QUIRK_R0_FALLTHROUGH, QUIRK_EXACT_VISIBILITY, QUIRKS_REFERENCE, QUIRKS_NONE = 1,
 
 class UNIT:
     SPHERE_INTERSECT, INTERSECT, VISIBILITY, TRANSMITTANCE, FREE_FLIGHT, PHASE_SAMPLE, EQUIANGULAR, POWER_HEURISTIC = range(8)
-    COSINE_HEMISPHERE, CONE_SAMPLE, MICROFACET, FACET_NORMAL, MEDIUM_NEE, POINT_LIGHT, SURFACE_MIS, BSDF_SAMPLE, RADIANCE, CAMERA_RAY, RADIANCE_LIST, RAYMARCH, MIS_DISTANCE = range(8, 21)
+    COSINE_HEMISPHERE, CONE_SAMPLE, MICROFACET, FACET_NORMAL, MEDIUM_NEE, POINT_LIGHT, SURFACE_MIS, BSDF_SAMPLE, RADIANCE, CAMERA_RAY, RADIANCE_LIST, RAYMARCH, MIS_DISTANCE, DIELECTRIC = range(8, 22)
 
 
 class Sphere(C.Structure):  # vpt_sphere

@@ -519,7 +519,7 @@ int vpt_write_ppm(const float *hdr_rgb, int32_t width, int32_t height, const cha
 
 // ---- unit kernels -----------------------------------------------------------------------------------------------------------------
 static const int kUnitStrides[VPT_UNIT_COUNT_][2] = {
-    {7, 1}, {6, 3}, {6, 1}, {7, 1}, {2, 4}, {2, 3}, {9, 6}, {2, 1}, {5, 4}, {7, 4}, {13, 6}, {3, 3}, {10, 3}, {11, 3}, {19, 3}, {9, 6}, {8, 4}, {4, 3}, {127, 4}, {8, 4}, {11, 3},
+    {7, 1}, {6, 3}, {6, 1}, {7, 1}, {2, 4}, {2, 3}, {9, 6}, {2, 1}, {5, 4}, {7, 4}, {13, 6}, {3, 3}, {10, 3}, {11, 3}, {19, 3}, {9, 6}, {8, 4}, {4, 3}, {127, 4}, {8, 4}, {11, 3}, {6, 7},
 };
 int vpt_unit_strides(int32_t fn, int32_t *in_stride, int32_t *out_stride) {
     if (fn < 0 || fn >= VPT_UNIT_COUNT_) return VPT_ERR_INVALID_ARGUMENT;

@@ -369,6 +369,11 @@ __global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const
         const bool surface = mis_distance(mk(src.px, src.py, src.pz), ld3(a + 2), ld3(a + 5), tmax, expf(-st * tmax), st, 1.0f / st, (float)a[9], (float)a[10], dist, inv_pdf);
         o[0] = surface; o[1] = dist; o[2] = surface ? 1.0f : 1.0f / inv_pdf;
     } break;
+    case VPT_UNIT_DIELECTRIC: {
+        const Frame fr = make_frame(ld3(a));
+        const DielF di = dielectric_setup(unit(to_local(fr, ld3(a + 3))));
+        st3(o, unit(to_world(fr, di.wt))); st3(o + 3, unit(to_world(fr, di.wr))); o[6] = di.F;
+    } break;
     case VPT_UNIT_POWER_HEURISTIC: o[0] = power_heuristic((float)a[0], (float)a[1]); break;
     case VPT_UNIT_COSINE_HEMISPHERE: {
         const F3 nrm = ld3(a);

@@ -154,6 +154,11 @@ __global__ void unit_f64_kernel(int fn, const __grid_constant__ SceneD sc, const
         const bool surface = mis_distance(pos(c.s[(int)a[0]]), v3(a + 2), v3(a + 5), a[1], a[8], a[9], a[10], dist, pdf);
         o[0] = surface; o[1] = dist; o[2] = pdf;
     } break;
+    case VPT_UNIT_DIELECTRIC: {
+        const D3 n = v3(a), wo = v3(a + 3);
+        const D3 wt = unit(refract_dielectric(1.0, 1.5, wo, n));
+        st3(o, wt); st3(o + 3, unit(reflect_dielectric(wo, n))); o[6] = fresnel_dielectric(1.0, 1.5, dot(n, wt), dot(n, wo));
+    } break;
     case VPT_UNIT_POWER_HEURISTIC: o[0] = power_heuristic(a[0], a[1]); break;
     case VPT_UNIT_COSINE_HEMISPHERE: {
         const D3 w = cosine_hemisphere(v3(a), a[3], a[4]);

@@ -165,6 +165,8 @@ void l0_frMicroFacet(const double *eta, const double *kappa, const double *wi, c
     put(o, frMicroFacet(V(eta), V(kappa), V(wi), V(wh), V(wo), a, V(n)));
 }
 double l0_fresnelDie(double ei, double et, double ct, double ci) { return fresnelDie(ei, et, ct, ci); }
+void l0_reflexDielectric(const double *wi, const double *n, double *o) { put(o, reflexDielectric(V(wi), V(n))); }
+void l0_refraxDielectric(double ei, double et, const double *wi, const double *n, double *o) { put(o, refraxDielectric(ei, et, V(wi), V(n))); }
 double l0_powerHeuristics(double f, double g) { return powerHeuristics(f, g); }
 void l0_muestreoSA(int light, const double *x, int obj, const double *n, const double *wray, double alpha, double *L, double *wi, double *cmax) {
     Vector aux; double cm = 0;

@@ -67,6 +67,16 @@ double l1_equiAngularParams2(const double *scene, int n, int src, double tMax, c
     out4[0] = e.D; out4[1] = e.thetaA; out4[2] = e.thetaB; out4[3] = e.t_local;
     return e.t_ray;
 }
+/* material 2's direction / Fresnel functions on n rows (n[3], wo[3]) -> (normalize(refraxDielectric(1, 1.5, wo, n))[3], normalize(reflexDielectric(wo, n))[3],
+ * fresnelDie(1, 1.5, n.wt, n.wo)) -- the call pattern of bdsf (vptShadeMethods.h:27-29) */
+void l1_dielectric(int n, const double *rows, double *out) {
+    for (int i = 0; i < n; ++i) {
+        const Vec nn = V(rows + 6 * i), wo = V(rows + 6 * i + 3);
+        const Vec wt = unit(refract_dielectric(1.0, 1.5, wo, nn));
+        put(out + 7 * i, wt); put(out + 7 * i + 3, unit(reflect_dielectric(wo, nn)));
+        out[7 * i + 6] = fresnel_dielectric(1.0, 1.5, dot(nn, wt), dot(nn, wo));
+    }
+}
 /* method 4's distance decision on n rows (source, tMax, o[3], d[3], sigma_t, xi, xd) -> (surface, dist, pdf) */
 void l1_mis_distance(const double *scene, int n_spheres, int n, const double *rows, double *out) {
     Scene sc = make_scene(scene, n_spheres, 0);

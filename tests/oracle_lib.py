@@ -144,6 +144,11 @@ class L1:
         r = self.lib.l1_equiAngularParams2(_p(s), C.c_int(len(s)), C.c_int(src), D(tmax), _p(o), _p(d), pu, nu, _p(out))
         return r, out
 
+    def dielectric(self, rows):
+        """material 2's refraxDielectric / reflexDielectric / fresnelDie; rows: n x 6 (n[3], wo[3]) -> n x 7 (wt[3], wr[3], F)"""
+        rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, 6); out = np.zeros((len(rows), 7))
+        self.lib.l1_dielectric(C.c_int(len(rows)), _p(rows), _p(out)); return out
+
     def mis_distance(self, scene, rows):
         """method 4's distance decision; rows: n x 11 (source, tMax, o[3], d[3], sigma_t, xi, xd) -> n x 3 (surface, dist, mixture pdf)"""
         s = _v(scene); rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, 11); out = np.zeros((len(rows), 3))
@@ -373,6 +378,13 @@ class L0:
         self.lib.l0_frMicroFacet(_p(e), _p(k), _p(wi), _p(wh), _p(wo), D(a), _p(n), _p(o)); return o
 
     def fresnelDie(self, ei, et, ct, ci): return self.lib.l0_fresnelDie(D(ei), D(et), D(ct), D(ci))
+
+    def reflexDielectric(self, wi, n):
+        wi, n = _v(wi), _v(n); o = np.zeros(3); self.lib.l0_reflexDielectric(_p(wi), _p(n), _p(o)); return o
+
+    def refraxDielectric(self, ei, et, wi, n):
+        wi, n = _v(wi), _v(n); o = np.zeros(3); self.lib.l0_refraxDielectric(D(ei), D(et), _p(wi), _p(n), _p(o)); return o
+
     def powerHeuristics(self, f, g): return self.lib.l0_powerHeuristics(D(f), D(g))
 
     def muestreoSA(self, light, x, obj, n, wray, alpha, u):

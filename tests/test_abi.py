@@ -43,7 +43,7 @@ def test_default_scene_is_the_references(vpt):
 
 
 def test_unit_strides_table(vpt):
-    for fn in range(21):
+    for fn in range(22):
         si, so = vpt.unit_strides(fn)
         assert si > 0 and so > 0
     with pytest.raises(vpt.VptError):

@@ -39,6 +39,49 @@ def test_dielectric_scene_file_loads_through_the_abi(vpt, gold):
     assert np.array_equal(rows, gold["rows_glass6"])
 
 
+def _dielectric_rows(n, seed):
+    rng = np.random.default_rng(seed)
+    nn = rng.normal(size=(n, 3)); nn /= np.linalg.norm(nn, axis=1, keepdims=True)
+    wo = rng.normal(size=(n, 3)); wo /= np.linalg.norm(wo, axis=1, keepdims=True)
+    return np.hstack([nn, wo])
+
+
+def test_oracle_dielectric_functions_are_the_references(l1, l0):
+    """refraxDielectric / reflexDielectric / fresnelDie of the restatement against the unmodified reference functions"""
+    rows = _dielectric_rows(300, 1)
+    got = l1.dielectric(rows)
+    for i in range(len(rows)):
+        n, wo = rows[i, :3], rows[i, 3:]
+        wt = l0.refraxDielectric(1.0, 1.5, wo, n); wt = wt / np.sqrt(wt @ wt)
+        wr = l0.reflexDielectric(wo, n); wr = wr / np.sqrt(wr @ wr)
+        F = l0.fresnelDie(1.0, 1.5, float(n @ wt), float(n @ wo))
+        np.testing.assert_allclose(got[i, :3], wt, rtol=0, atol=1e-15); np.testing.assert_allclose(got[i, 3:6], wr, rtol=0, atol=1e-15)
+        assert abs(got[i, 6] - F) <= 1e-12 * max(abs(F), 1.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", [0, 1])
+def test_gpu_unit_dielectric(gpu, l1, precision):
+    """unit level: the device's material-2 directions and Fresnel term against the oracle on identical inputs -- FP64 to rounding, FP32 within
+    north_star's 1e-5 (directions: absolute on unit vectors; F: relative, away from the two poles of fresnelDie where the reference's own value
+    runs through +-inf)"""
+    rows = _dielectric_rows(20000, 2)
+    if precision == 0:
+        rows = rows.astype(np.float32).astype(np.float64)
+        rows[:, :3] /= np.linalg.norm(rows[:, :3], axis=1, keepdims=True); rows[:, 3:] /= np.linalg.norm(rows[:, 3:], axis=1, keepdims=True)
+        rows = rows.astype(np.float32).astype(np.float64)
+    want = l1.dielectric(rows)
+    got = gpu.unit(gpu.UNIT.DIELECTRIC, rows, gpu.default_params(precision=precision))
+    if precision == 1:
+        np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-13)
+        return
+    assert np.abs(got[:, :6] - want[:, :6]).max() < 1e-5
+    ci = np.einsum("ij,ij->i", rows[:, :3], rows[:, 3:]); cn = np.einsum("ij,ij->i", rows[:, :3], want[:, :3])
+    away = (np.abs(1.5 * ci + cn) > 0.05) & (np.abs(ci + 1.5 * cn) > 0.05)
+    assert away.mean() > 0.85
+    assert (np.abs(got[away, 6] - want[away, 6]) / np.abs(want[away, 6])).max() < 1e-5
+
+
 def _list_rows(gold):
     n = len(gold["o"])
     rows = np.zeros((n, 127))
