@@ -16,6 +16,7 @@
  */
 #ifndef VPT_H
 #define VPT_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -24,6 +25,9 @@ extern "C" {
 
 #define VPT_MAX_SPHERES 32  /* reference: unbounded std::vector */
 #define VPT_MAX_EMITTERS 16 /* reference: `int arr[4]` overflows beyond 4 (vptShadeMethods.h:1293); here a checked limit */
+#define VPT_MAX_DEPTH 4095  /* hard bounce cap of every kernel (the on-chip path record keeps the depth in 12 bits).  The reference has no depth limit
+                               (roulette only, continue probability 0.6: P(depth > 4095) = 0.6^4095 = 0); see vpt_params.max_depth */
+#define VPT_MAX_SAMPLES_PER_CALL (1 << 24) /* samples per pixel rendered by ONE call (sample_end - sample_begin); larger renders are split into calls */
 
 typedef enum {
     VPT_OK = 0,
@@ -82,7 +86,9 @@ typedef struct {
     int32_t sample_begin, sample_end; /* this call renders samples [begin, end); 0,0 = [0, spp) (shard / resume) */
     int32_t tile_rank, tile_count;    /* this call renders pixel tiles with tile_id % tile_count == tile_rank; 0,0 = all */
     int32_t method;                   /* VPT_METHOD_*: which line of rt.cpp:791-796 is active */
-    int32_t max_depth;                /* <= 0: unlimited (reference) */
+    int32_t max_depth;                /* <= 0: roulette only, as the reference (needs continue_prob <= 0.99; paths are cut at VPT_MAX_DEPTH bounces, which
+                                         roulette reaches with probability < 1e-17); otherwise 1 .. VPT_MAX_DEPTH.  continue_prob > 0.99 needs max_depth > 0:
+                                         a roulette that never fires would never end a path in a scene without emitter geometry */
     double sigma_a, sigma_s;          /* 0.001, 0.009 (rt.cpp:794) */
     double continue_prob;             /* 0.6 (vptShadeMethods.h:1275) */
     double cam_o[3], cam_dir[3], fov; /* (0,11.2,214), (0,-0.042612,-1), 0.5095 (rt.cpp:755-759) */
@@ -101,7 +107,8 @@ typedef struct {
     uint64_t paths;       /* camera paths traced = pixels rendered x samples */
     uint64_t events;      /* path vertices that survived Russian roulette */
     uint64_t scene_scans; /* all-sphere intersection passes */
-    uint64_t nonfinite;   /* paths whose radiance was NaN/Inf and was dropped (0 in a healthy run) */
+    uint64_t nonfinite;   /* radiance contributions that were NaN/Inf or >= 2^32 in magnitude (outside the range of the 64-bit fixed-point pixel sums,
+                             2^-30 .. 2^33) and were dropped (0 in a healthy run; FP64_REF: whole paths) */
     double kernel_ms;     /* CUDA-event time of the render kernels only */
     double total_ms;      /* wall time of the call including copies */
     uint64_t launches;    /* kernels launched by this call */
@@ -119,7 +126,10 @@ int vpt_default_scene(vpt_sphere *out, int32_t cap);
 int vpt_load_scene(const char *path, vpt_sphere *out, int32_t cap);
 
 /* Replaces the pixel loop rt.cpp:767-805.  hdr_rgb: HOST buffer, width*height*3 floats, pixel index (h-y-1)*w+x as
- * rt.cpp:773 (row 0 = top of the image), UNCLAMPED linear radiance; pixels outside this call's tiles are written as 0. */
+ * rt.cpp:773 (row 0 = top of the image), UNCLAMPED linear radiance; pixels outside this call's tiles are written as 0.
+ * Any host memory works.  If hdr_rgb is page-locked and mapped (vpt_host_alloc, cudaHostAlloc, cudaHostRegister) the kernel stores its
+ * pixels straight into it over PCIe while it renders (no staging copy after the kernel); pageable memory gets a device frame + one copy.
+ * The calling thread's current CUDA device is left unchanged. */
 int vpt_render(const vpt_params *p, const vpt_sphere *spheres, int32_t n_spheres, float *hdr_rgb, vpt_stats *stats /* nullable */);
 /* Same, but hdr_rgb is a DEVICE buffer on p->device and the work is enqueued on `cuda_stream` (a cudaStream_t, may be 0).
  * With stats == NULL the call does not synchronise; with stats != NULL it synchronises the stream before returning. */
@@ -180,6 +190,10 @@ int vpt_philox(int32_t device, int32_t n, const uint32_t *ctr, const uint32_t *k
 
 /* Register-resident FFMA microbenchmark: the measured FP32 roofline denominator. */
 int vpt_measure_fp32_peak(int32_t device, double *tflops_out, double *sm_clock_mhz_out /* nullable */);
+
+/* Page-locked, device-mapped host memory for the frame buffers handed to vpt_render / vpt_render_multi (optional, see vpt_render). */
+void *vpt_host_alloc(size_t bytes);
+void vpt_host_free(void *p);
 
 int vpt_device_count(void);
 const char *vpt_strerror(int status);

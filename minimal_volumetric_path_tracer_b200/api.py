@@ -85,6 +85,8 @@ def load_library(path=None):
     lib.vpt_strerror.restype = C.c_char_p; lib.vpt_strerror.argtypes = [C.c_int]
     lib.vpt_last_cuda_error.restype = C.c_char_p
     lib.vpt_version.restype = C.c_char_p
+    lib.vpt_host_alloc.restype = C.c_void_p; lib.vpt_host_alloc.argtypes = [C.c_size_t]
+    lib.vpt_host_free.restype = None; lib.vpt_host_free.argtypes = [C.c_void_p]
     if path == LIB_PATH:
         _lib = lib
     return lib
@@ -222,6 +224,39 @@ def write_ppm(hdr_mean, path):
     hdr = np.ascontiguousarray(hdr_mean, dtype=np.float32)
     h, w = hdr.shape[:2]
     _check(lib, lib.vpt_write_ppm(hdr.ctypes.data_as(C.POINTER(C.c_float)), w, h, os.fsencode(path)))
+
+
+class PinnedFrame:
+    """(h, w, 3) float32 frame in page-locked, device-mapped host memory (vpt_host_alloc): vpt_render stores its pixels straight into it
+    while it renders.  `.array` is a numpy view; the memory is released when the object is dropped (or by close())."""
+
+    def __init__(self, height, width):
+        lib = load_library()
+        self._lib, self.nbytes = lib, height * width * 3 * 4
+        self._ptr = lib.vpt_host_alloc(self.nbytes)
+        if not self._ptr:
+            raise VptError(-5, "vpt_host_alloc failed", lib.vpt_last_cuda_error().decode())
+        self.array = np.ctypeslib.as_array((C.c_float * (height * width * 3)).from_address(self._ptr)).reshape(height, width, 3)
+
+    def close(self):
+        if self._ptr:
+            self.array = None
+            self._lib.vpt_host_free(self._ptr); self._ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def render_into(params, scene, frame, stats=None):
+    """vpt_render into a caller-owned host frame (numpy float32 (h, w, 3), e.g. PinnedFrame.array)."""
+    lib = load_library()
+    scene = scene if scene is not None else default_scene()
+    assert frame.dtype == np.float32 and frame.shape == (params.height, params.width, 3) and frame.flags.c_contiguous
+    _check(lib, lib.vpt_render(C.byref(params), scene, len(scene), frame.ctypes.data_as(C.POINTER(C.c_float)), C.byref(stats) if stats is not None else None))
+    return frame
 
 
 def device_count():

@@ -66,6 +66,7 @@ int validate_params(const vpt_params *p, bool need_image) {
         if ((long long)p->width * p->height > 0x7fffffffLL / 4) return VPT_ERR_INVALID_ARGUMENT;
         const bool whole = p->sample_begin == 0 && p->sample_end == 0;
         if (!whole && (p->sample_begin < 0 || p->sample_end <= p->sample_begin || p->sample_end > p->spp)) return VPT_ERR_INVALID_ARGUMENT;
+        if ((whole ? p->spp : p->sample_end - p->sample_begin) >= VPT_MAX_SAMPLES_PER_CALL) return VPT_ERR_INVALID_ARGUMENT; // 32-bit sample counters per work item
         const bool all_tiles = p->tile_rank == 0 && p->tile_count == 0;
         if (!all_tiles && (p->tile_count <= 0 || p->tile_rank < 0 || p->tile_rank >= p->tile_count)) return VPT_ERR_INVALID_ARGUMENT;
         if (p->output != VPT_OUTPUT_SUM && p->output != VPT_OUTPUT_MEAN) return VPT_ERR_INVALID_ARGUMENT;
@@ -75,6 +76,11 @@ int validate_params(const vpt_params *p, bool need_image) {
     if (p->precision != VPT_PRECISION_FP32 && p->precision != VPT_PRECISION_FP64_REF) return VPT_ERR_INVALID_ARGUMENT;
     if (!(p->sigma_a >= 0) || !(p->sigma_s >= 0) || !(p->sigma_a + p->sigma_s > 0) || !std::isfinite(p->sigma_a + p->sigma_s)) return VPT_ERR_INVALID_ARGUMENT;
     if (!(p->continue_prob > 0) || !(p->continue_prob <= 1)) return VPT_ERR_INVALID_ARGUMENT;
+    // Path length: the reference bounds it by roulette alone (max_depth <= 0).  A roulette that (almost) never fires would let a path in a scene
+    // without emitter geometry run forever -- a GPU hang -- so unlimited depth needs continue_prob <= 0.99 (the kernels' internal cap of
+    // VPT_MAX_DEPTH bounces is then reached with probability < 1e-17), anything above needs an explicit 0 < max_depth <= VPT_MAX_DEPTH.
+    if (p->max_depth > VPT_MAX_DEPTH) return VPT_ERR_INVALID_ARGUMENT;
+    if (p->max_depth <= 0 && p->continue_prob > 0.99) return VPT_ERR_INVALID_ARGUMENT;
     if (!finite3(p->cam_o) || !finite3(p->cam_dir) || !(p->fov > 0) || dot(v3(p->cam_dir), v3(p->cam_dir)) == 0) return VPT_ERR_INVALID_ARGUMENT;
     if (p->quirks & ~(uint32_t)VPT_QUIRKS_REFERENCE) return VPT_ERR_INVALID_ARGUMENT;
     if (p->precision == VPT_PRECISION_FP32 && p->quirks != 0) return VPT_ERR_UNSUPPORTED; // rounding-decided behaviours exist in FP64 only
@@ -88,7 +94,7 @@ void build_scene_f32(const vpt_sphere *s, int n, SceneF &out) {
     std::memset(&out, 0, sizeof(out));
     out.n_spheres = n;
     // reference point for anchoring: centroid of the ordinary (non-huge) spheres
-    const double kHuge = 4096.0;
+    const double kHuge = 64.0; // = the product scan's class boundary (vpt_smwave.cuh kSimpleRootMaxR2): every general-form sphere gets its own anchor
     V3 ref{0, 0, 0};
     int n_small = 0;
     for (int i = 0; i < n; ++i)
@@ -195,14 +201,24 @@ void build_consts_f32(const LaunchParams &lp, int n_emitters, ConstsF &k) {
 
 int owned_tiles(const LaunchParams &lp) { return (lp.n_tiles_total - lp.tile_rank + lp.tile_count - 1) / lp.tile_count; }
 
-int select_device(int device) {
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
-    if (n <= 0 || device < 0 || device >= n) { g_last_cuda_error = "no such CUDA device"; return VPT_ERR_NO_DEVICE; }
-    CUDA_TRY(cudaSetDevice(device));
-    return VPT_OK;
-}
+// Makes `device` current for the lifetime of the guard and restores the caller's device afterwards: a library embedded in a process that
+// has its own current device (PyTorch, one rank per GPU) must not move it.
+struct DeviceGuard {
+    int prev = -1, rc = VPT_OK;
+    explicit DeviceGuard(int device) {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaGetDeviceCount"); return; }
+        if (n <= 0 || device < 0 || device >= n) { g_last_cuda_error = "no such CUDA device"; rc = VPT_ERR_NO_DEVICE; return; }
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev == device) { prev = -1; return; }
+        e = cudaSetDevice(device);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaSetDevice"); prev = -1; }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
 
 // core: enqueue one render into a device buffer. counters_dev may be null.
 int enqueue_render(const vpt_params *p, const vpt_sphere *spheres, int n_spheres, float *hdr_dev, cudaStream_t stream, Counters *counters_dev,
@@ -269,8 +285,43 @@ cudaError_t scratch_alloc(int device, void **ptr, size_t bytes, cudaStream_t str
     return cudaMallocFromPoolAsync(ptr, bytes, pool, stream);
 }
 
+// trim a device's scratch pool down to `keep` bytes (the HBM wavefront parks 3.6 GB of queues there for one render)
+void scratch_trim(int device, size_t keep) {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (device >= 0 && device < kMaxDevices && g_pools[device]) cudaMemPoolTrimTo(g_pools[device], keep);
+}
+
+// One non-blocking stream per (host thread, device) for the host-buffer entry points, created on first use and kept: creating and
+// destroying a stream per call cost as much as the copy of a small frame.
+struct ThreadStreams {
+    cudaStream_t s[kMaxDevices] = {};
+    ~ThreadStreams() {
+        for (int d = 0; d < kMaxDevices; ++d)
+            if (s[d]) { int prev = -1; if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(d) == cudaSuccess) { cudaStreamDestroy(s[d]); cudaSetDevice(prev); } }
+    }
+};
+thread_local ThreadStreams g_streams;
+cudaError_t thread_stream(int device, cudaStream_t *out) { // `device` is current
+    if (device < 0 || device >= kMaxDevices) return cudaErrorInvalidDevice;
+    if (!g_streams.s[device]) {
+        cudaError_t e = cudaStreamCreateWithFlags(&g_streams.s[device], cudaStreamNonBlocking);
+        if (e != cudaSuccess) { g_streams.s[device] = nullptr; return e; }
+    }
+    *out = g_streams.s[device];
+    return cudaSuccess;
+}
+
+// is `p` page-locked host memory the device can address?  (then the render kernel writes the frame straight into it)
+float *mapped_device_pointer(float *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+    return (float *)a.devicePointer;
+}
+
 } // namespace
 
+void vpt::scratch_trim_(int device, size_t keep) { scratch_trim(device, keep); }
 int vpt::scratch_alloc_(int device, void **ptr, size_t bytes, void *stream) { return (int)scratch_alloc(device, ptr, bytes, (cudaStream_t)stream); }
 
 #pragma GCC visibility push(default)
@@ -364,8 +415,8 @@ int vpt_render_device(const vpt_params *p, const vpt_sphere *spheres, int32_t n_
     rc = validate_scene(spheres, n_spheres);
     if (rc) return rc;
     if (!hdr_dev) return VPT_ERR_INVALID_ARGUMENT;
-    rc = select_device(p->device);
-    if (rc) return rc;
+    DeviceGuard guard(p->device);
+    if (guard.rc) return guard.rc;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     LaunchParams lp;
     build_launch(p, lp);
@@ -411,23 +462,30 @@ int vpt_render(const vpt_params *p, const vpt_sphere *spheres, int32_t n_spheres
     rc = validate_scene(spheres, n_spheres);
     if (rc) return rc;
     if (!hdr_rgb) return VPT_ERR_INVALID_ARGUMENT;
-    rc = select_device(p->device);
-    if (rc) return rc;
+    DeviceGuard guard(p->device);
+    if (guard.rc) return guard.rc;
     const size_t bytes = (size_t)p->width * p->height * 3 * sizeof(float);
-    float *dev = nullptr;
     cudaStream_t stream = nullptr;
-    CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    cudaError_t ce = scratch_alloc(p->device, (void **)&dev, bytes, stream); // stream-ordered, from the library's per-device pool
-    if (ce != cudaSuccess) { cudaStreamDestroy(stream); return cuda_fail(ce, "cudaMallocAsync"); }
-    rc = vpt_render_device(p, spheres, n_spheres, dev, stream, stats); // with stats == NULL nothing synchronises before the copy below
-    if (rc == VPT_OK) {
-        ce = cudaMemcpyAsync(hdr_rgb, dev, bytes, cudaMemcpyDeviceToHost, stream);
-        if (ce != cudaSuccess) rc = cuda_fail(ce, "copy HDR to host");
+    CUDA_TRY(thread_stream(p->device, &stream));
+    cudaError_t ce;
+    if (float *mapped = mapped_device_pointer(hdr_rgb)) {
+        // page-locked, mapped host frame: the kernel stores every pixel once, straight into the caller's buffer, while it renders
+        rc = vpt_render_device(p, spheres, n_spheres, mapped, stream, stats);
+        ce = cudaStreamSynchronize(stream);
+        if (ce != cudaSuccess && rc == VPT_OK) rc = cuda_fail(ce, "vpt_render");
+    } else {
+        float *dev = nullptr;
+        ce = scratch_alloc(p->device, (void **)&dev, bytes, stream); // stream-ordered, from the library's per-device pool
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaMallocAsync");
+        rc = vpt_render_device(p, spheres, n_spheres, dev, stream, stats); // with stats == NULL nothing synchronises before the copy below
+        if (rc == VPT_OK) {
+            ce = cudaMemcpyAsync(hdr_rgb, dev, bytes, cudaMemcpyDeviceToHost, stream);
+            if (ce != cudaSuccess) rc = cuda_fail(ce, "copy HDR to host");
+        }
+        cudaFreeAsync(dev, stream);
+        ce = cudaStreamSynchronize(stream);
+        if (ce != cudaSuccess && rc == VPT_OK) rc = cuda_fail(ce, "vpt_render");
     }
-    cudaFreeAsync(dev, stream);
-    ce = cudaStreamSynchronize(stream);
-    if (ce != cudaSuccess && rc == VPT_OK) rc = cuda_fail(ce, "vpt_render");
-    cudaStreamDestroy(stream);
     if (rc == VPT_OK && stats) stats->total_ms = now_ms() - t0;
     return rc;
 }
@@ -451,11 +509,13 @@ int vpt_render_multi(const vpt_params *p, const vpt_sphere *spheres, int32_t n_s
         vpt_params q = *p;
         q.device = devices[k];
         q.tile_rank = k; q.tile_count = n_devices;
-        int r = select_device(q.device);
+        DeviceGuard guard(q.device);
+        int r = guard.rc;
         float *dev = nullptr;
         cudaStream_t stream = nullptr;
-        if (!r && cudaMalloc(&dev, bytes) != cudaSuccess) r = cuda_fail(cudaGetLastError(), "cudaMalloc");
-        if (!r && cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) r = cuda_fail(cudaGetLastError(), "cudaStreamCreate");
+        cudaError_t ae;
+        if (!r && (ae = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)) != cudaSuccess) r = cuda_fail(ae, "cudaStreamCreate");
+        if (!r && (ae = scratch_alloc(q.device, (void **)&dev, bytes, stream)) != cudaSuccess) r = cuda_fail(ae, "cudaMallocAsync"); // pooled: kept between calls
         if (!r) r = vpt_render_device(&q, spheres, n_spheres, dev, stream, &sts[k]);
         if (!r) {
             // this device's tiles are disjoint strided ranges of the frame: copy them straight into the caller's buffer
@@ -473,8 +533,8 @@ int vpt_render_multi(const vpt_params *p, const vpt_sphere *spheres, int32_t n_s
                 if (ce != cudaSuccess) r = cuda_fail(ce, "copy tiles to host");
             }
         }
-        if (stream) cudaStreamDestroy(stream);
-        if (dev) cudaFree(dev);
+        if (dev) cudaFreeAsync(dev, stream);
+        if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
         rcs[k] = r;
         errs[k] = g_last_cuda_error;
     };
@@ -536,8 +596,8 @@ int vpt_unit(int32_t fn, const vpt_params *p, const vpt_sphere *spheres, int32_t
     if (rc) return rc;
     rc = validate_scene(spheres, n_spheres);
     if (rc) return rc;
-    rc = select_device(p->device);
-    if (rc) return rc;
+    DeviceGuard guard(p->device);
+    if (guard.rc) return guard.rc;
     LaunchParams lp;
     vpt_params q = *p;
     if (q.width <= 0) q.width = 1;
@@ -576,8 +636,8 @@ int vpt_unit(int32_t fn, const vpt_params *p, const vpt_sphere *spheres, int32_t
 
 int vpt_philox(int32_t device, int32_t n, const uint32_t *ctr, const uint32_t *key, uint32_t *out) {
     if (!ctr || !key || !out || n <= 0) return VPT_ERR_INVALID_ARGUMENT;
-    int rc = select_device(device);
-    if (rc) return rc;
+    DeviceGuard guard(device);
+    if (guard.rc) return guard.rc;
     uint32_t *dc = nullptr, *dk = nullptr, *dout = nullptr;
     cudaError_t ce;
     do {
@@ -597,8 +657,8 @@ int vpt_philox(int32_t device, int32_t n, const uint32_t *ctr, const uint32_t *k
 
 int vpt_measure_fp32_peak(int32_t device, double *tflops_out, double *sm_clock_mhz_out) {
     if (!tflops_out) return VPT_ERR_INVALID_ARGUMENT;
-    int rc = select_device(device);
-    if (rc) return rc;
+    DeviceGuard guard(device);
+    if (guard.rc) return guard.rc;
     int sms = 0, khz = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
@@ -627,6 +687,13 @@ int vpt_measure_fp32_peak(int32_t device, double *tflops_out, double *sm_clock_m
     if (sm_clock_mhz_out) *sm_clock_mhz_out = khz / 1000.0;
     return VPT_OK;
 }
+
+void *vpt_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void vpt_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 int vpt_device_count(void) {
     int n = 0;

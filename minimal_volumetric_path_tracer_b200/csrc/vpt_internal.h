@@ -100,6 +100,7 @@ struct Counters { // device-side, accumulated with atomics at thread exit
 int launch_hbmwave_f32(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, void *stream, int n_owned_tiles, uint64_t *launches);
 // stream-ordered allocation from the library's per-device scratch pool (vpt_api.cpp); free with cudaFreeAsync
 int scratch_alloc_(int device, void **ptr, size_t bytes, void *stream);
+void scratch_trim_(int device, size_t keep_bytes); // give the pool's unused memory above keep_bytes back to the driver
 int launch_march_f32(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks);
 int launch_render_f32(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks, int kernel);
 int launch_render_f64(const SceneD &scene, const LaunchParams &lp, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks);

@@ -99,8 +99,11 @@ static int run_hbmwave(const SceneF &scene, const LaunchParams &lp, const Consts
     {
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
         if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
-        const char *cap_env = std::getenv("VPT_HBM_CAP"); // development knob: paths in flight
-        unsigned cap = cap_env ? (unsigned)std::strtoul(cap_env, nullptr, 10) : (1u << 23); // 8 Mi paths in flight = 3.6 GB of queues: best of 1 / 2 / 4 / 6 / 8 / 12 Mi by measurement
+        unsigned cap = 1u << 23; // 8 Mi paths in flight = 3.6 GB of queues: best of 1 / 2 / 4 / 6 / 8 / 12 Mi by measurement
+#ifdef VPT_DEV_KNOBS // profiling builds only (tools/build_variant.py -DVPT_DEV_KNOBS): the shipped library does not read the environment
+        if (const char *cap_env = std::getenv("VPT_HBM_CAP")) cap = (unsigned)std::strtoul(cap_env, nullptr, 10);
+        cap = cap < (1u << 16) ? (1u << 16) : (cap > (1u << 25) ? (1u << 25) : cap);
+#endif
         cap = (cap + 1023u) & ~1023u;
         H.cap = cap;
         H.n_owned_pixels = (unsigned)n_owned_tiles * (unsigned)kTile;
@@ -118,8 +121,12 @@ static int run_hbmwave(const SceneF &scene, const LaunchParams &lp, const Consts
         flags_host[0] = flags_host[1] = 0u;
         HBM_TRY(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
         HBM_TRY(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
-        const char *grid_env = std::getenv("VPT_HBM_GRID"); // development knob: CTAs per SM
-        const int grid = n_sm * (grid_env ? std::atoi(grid_env) : 4); // best of 3 / 4 / 6 / 8 / 16 by measurement
+        int ctas_per_sm = 4; // best of 3 / 4 / 6 / 8 / 16 by measurement
+#ifdef VPT_DEV_KNOBS
+        if (const char *grid_env = std::getenv("VPT_HBM_GRID")) ctas_per_sm = std::atoi(grid_env);
+        ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 32 ? 32 : ctas_per_sm);
+#endif
+        const int grid = n_sm * ctas_per_sm;
         // rounds are enqueued in batches; after each batch the "nothing left" counter is copied to the host, and the host looks at the
         // copy of the batch BEFORE the one it has just enqueued, so the GPU never waits for the host
         const int kBatch = 16;
@@ -156,6 +163,7 @@ fail:
     if (ev[0]) cudaEventDestroy(ev[0]);
     if (ev[1]) cudaEventDestroy(ev[1]);
     if (flags_host) { cudaStreamSynchronize(st); cudaFreeHost(flags_host); }
+    scratch_trim_(dev, (size_t)256 << 20); // the queues (3.6 GB) go back to the driver; a frame buffer's worth stays pooled
     return (int)e;
 #undef HBM_TRY
 }

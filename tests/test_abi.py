@@ -68,6 +68,17 @@ def test_argument_validation_precedes_device_work(vpt):
     assert _rc(vpt, P(sample_begin=0, sample_end=3)) == INVALID
     assert _rc(vpt, P(tile_rank=2, tile_count=2)) == INVALID
     assert _rc(vpt, P(continue_prob=0.0)) == INVALID
+    # a roulette that never fires + no depth limit = paths that never end in a scene without emitter geometry (scenes/scene2,3,5,6): a GPU hang.
+    # Unlimited depth needs continue_prob <= 0.99; above that an explicit max_depth; every kernel caps paths at VPT_MAX_DEPTH = 4095 bounces.
+    assert _rc(vpt, P(continue_prob=1.0)) == INVALID
+    assert _rc(vpt, P(continue_prob=0.995, max_depth=0)) == INVALID
+    assert _rc(vpt, P(continue_prob=1.0, max_depth=4096)) == INVALID
+    assert _rc(vpt, P(max_depth=1 << 22)) == INVALID
+    assert _rc(vpt, P(continue_prob=1.0, max_depth=64)) in (0, -4, -5)        # valid: refused only for lack of a device
+    assert _rc(vpt, P(continue_prob=0.99)) in (0, -4, -5)
+    assert _rc(vpt, P(spp=1 << 24)) == INVALID                               # samples per call: 32-bit per-item counters
+    assert _rc(vpt, P(spp=1 << 25, sample_begin=5, sample_end=5 + (1 << 24))) == INVALID
+    assert _rc(vpt, P(spp=1 << 25, sample_begin=5, sample_end=9)) in (0, -4, -5)
     assert _rc(vpt, P(sigma_a=0.0, sigma_s=0.0)) == INVALID
     assert _rc(vpt, P(quirks=8)) == INVALID
     assert _rc(vpt, P(), hdr=False) == INVALID
