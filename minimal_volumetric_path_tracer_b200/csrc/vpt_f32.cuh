@@ -1,12 +1,9 @@
-// vpt_f32.cuh -- FP32 device implementation of the reference's per-path radiance estimators (the performance path).
+// vpt_f32.cuh -- FP32 building blocks of the performance path: vector algebra, local frames, the reference's sampling routines and pdfs,
+// the Beckmann conductor model, the dielectric as the reference writes it, the equi-angular and MIS distance samplers.
 //
-// Written for the GPU from the reference's behaviour (file:line cited per function), not translated: geometry uses a
-// re-anchored, cancellation-free ray/sphere form so the r = 1e5 wall spheres survive fp32; angles are never
-// materialised where the reference goes acos -> sin/cos (algebraic forms instead); local frames are built once per
-// surface event.  Semantics = the reference with its two FP64-rounding-decided behaviours replaced by their
-// well-defined alternative (include/vpt.h VPT_QUIRK_*): r == 0 spheres are never ray-intersected and visibility uses
-// `t > distance * (1 - 1e-4)`.  The draw order of random numbers is the reference's, so that the
-// FP64 CPU oracle consumes the identical stream.
+// Written for the GPU from the reference's behaviour (file:line cited per function), not translated: angles are never
+// materialised where the reference goes acos -> sin/cos (algebraic forms instead).  The scene scan lives in vpt_scan.cuh, the estimators
+// built from these blocks -- ONE copy for every FP32 kernel and for the unit kernels -- in vpt_stages.cuh.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -34,54 +31,6 @@ __device__ __forceinline__ F3 had(F3 a, F3 b) { return mk(a.x * b.x, a.y * b.y, 
 __device__ __forceinline__ F3 cross(F3 a, F3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 __device__ __forceinline__ F3 fma3(F3 a, float s, F3 b) { return mk(fmaf(a.x, s, b.x), fmaf(a.y, s, b.y), fmaf(a.z, s, b.z)); } // a*s + b
 __device__ __forceinline__ F3 unit(F3 a) { return a * rsqrtf(dot(a, a)); }
-
-// ---- Sphere::intersect (Sphere.h:27-37) in the re-anchored form -------------------------------------------------------
-// returns the reference's choice of root: the near one unless it is negative or within 1e-4 of the origin, else the far
-// one (which may be negative); 0 when the ray misses.
-__device__ __forceinline__ float sphere_t(const GeomF &g, F3 o, F3 d) {
-    const F3 oq = mk(o.x - g.qx, o.y - g.qy, o.z - g.qz);
-    const F3 m = mk(g.mx, g.my, g.mz);
-    const float c = fmaf(2.0f, dot(oq, m), dot(oq, oq)) + g.c0;
-    const F3 op = oq + m;
-    const float b = dot(op, d);
-    float det;
-    if (g.big) {
-        det = fmaf(b, b, -c);
-    } else { // r^2 - |op - (op.d) d|^2 : no cancellation for small far-away spheres
-        const F3 l = fma3(d, -b, op);
-        det = g.r2 - dot(l, l);
-    }
-    if (det < 0.0f) return 0.0f;
-    const float sq = sqrtf(det);
-    const float q = -(b + copysignf(sq, b)); // the root without cancellation; the other one is c / q
-    const float other = c / q;
-    const float t_near = fminf(q, other), t_far = fmaxf(q, other);
-    return (t_near < 0.0f || fabsf(t_near) < kEps) ? t_far : t_near;
-}
-
-// intersect (pathTracingUtilities.h:12-36).  Returns hit; t and id (caller's sphere index) only written on a hit.
-__device__ __forceinline__ bool scan(const SceneF &sc, F3 o, F3 d, float &t, int &id, unsigned &n_scans) {
-    float best = CUDART_INF_F;
-    int best_id = -1;
-    ++n_scans;
-    for (int i = 0; i < sc.n_geom; ++i) {
-        const float ti = sphere_t(sc.geom[i], o, d);
-        if (ti > kEps && ti < best) { best = ti; best_id = sc.geom[i].id; }
-    }
-    if (best_id < 0) return false;
-    t = best; id = best_id;
-    return true;
-}
-
-// visibility (pathTracingUtilities.h:39-53), well-defined variant: nothing hit before distance * (1 - 1e-4)
-__device__ __forceinline__ bool visible(const SceneF &sc, F3 light, F3 x, unsigned &n_scans) {
-    const F3 lx = light - x;
-    const float d2 = dot(lx, lx);
-    const float inv = rsqrtf(d2);
-    float t; int id;
-    if (!scan(sc, light, lx * (-inv), t, id, n_scans)) return true;
-    return t > d2 * inv * (1.0f - 1e-4f);
-}
 
 // coordinateSystem (mathUtilities.h:10-19): t from n, s = t x n
 struct Frame { F3 s, t, n; };
@@ -248,120 +197,10 @@ __device__ __forceinline__ F3 dielectric_direct(const MatF &em, F3 x, float cos_
     return g * power_heuristic(gpdf_loop, 1.0f / (kTwoPi * omc));
 }
 
-// ---- per-path state -----------------------------------------------------------------------------------------------------
-struct Consts { // derived once per launch from LaunchParams
-    float sigma_t, inv_sigma_t, sigma_s, albedo_over_cp, inv_cp, q;
-    float n_emitters; // 1 / probSource
-    int method, max_depth;
-};
-struct Path { F3 o, d, beta, L; int depth; };
-struct Tally { unsigned events, scans; };
-
 // Surface BRDF value for an incoming local direction wi (Lambert c/pi or microfacet)
 __device__ __forceinline__ F3 brdf_eval(const MatF &obj, F3 wi_l, F3 wo_l) {
     if (obj.material == 1) return facet_brdf(obj, wi_l, unit(wi_l + wo_l), wo_l);
     return mk(obj.cr, obj.cg, obj.cb) * kInvPi;
-}
-
-// pLight (vptShadeMethods.h:62-91) * transmittance * 1/probSource, as used at :1316 / :1113 / :1444.
-// For an area source the reference's visibility ray starts at the sphere centre and hits that sphere at t = r, so the
-// term is zero whenever the shaded point lies outside the source sphere.
-__device__ __forceinline__ F3 point_light_direct(const SceneF &sc, const MatF &obj, const MatF &src, F3 x, const Frame &fr, F3 wo_l, const Consts &k, unsigned &n_scans) {
-    const F3 light = mk(src.px, src.py, src.pz);
-    const F3 lx = light - x;
-    const float d2 = dot(lx, lx);
-    if (src.r > 0.0f && d2 > src.r * src.r) return mk(0, 0, 0);
-    if (!visible(sc, light, x, n_scans)) return mk(0, 0, 0);
-    const float inv = rsqrtf(d2), dist = d2 * inv;
-    const F3 wi = lx * inv;
-    const F3 wi_l = unit(to_local(fr, wi));
-    const F3 f = brdf_eval(obj, wi_l, wo_l);
-    const float scale = dot(fr.n, wi) / d2 * expf(-k.sigma_t * dist) * k.n_emitters;
-    return had(mk(src.lr, src.lg, src.lb), f) * scale;
-}
-
-// MISv2 (misSamplingFunctions.h:96-170), materials 0 and 1
-template <class RngT>
-__device__ __forceinline__ F3 surface_direct_mis(const SceneF &sc, const MatF *mats, const MatF &obj, F3 x, const Frame &fr, F3 wo_l,
-                                                 const Consts &k, RngT &rng, unsigned &n_scans) {
-    F3 total = mk(0, 0, 0);
-    if (obj.material == 2) { // light-sampled terms are zero (fr = 0, samplingFunctions.h:190); the loop only leaves its last gpdf behind (:110-118)
-        const DielF di = dielectric_setup(wo_l);
-        float gpdf_loop = 0.0f;
-        for (int a = 0; a < sc.n_area; ++a) {
-            rng.next_f32(S_AREA + 2 * a); rng.next_f32(S_AREA + 2 * a + 1);
-            gpdf_loop = rng.next_f32(S_DIEL + a) > di.F ? 1.0f - di.F : di.F;
-        }
-        const bool refracted = !(rng.next_f32(S_MIS) < di.F);
-        const F3 w_l = refracted ? di.wt : di.wr;
-        float t; int hit_id;
-        if (scan(sc, x, unit(to_world(fr, w_l)), t, hit_id, n_scans)) total = dielectric_direct(mats[hit_id], x, w_l.z, refracted, gpdf_loop);
-        return total;
-    }
-    float omc_last = 1.0f; // 1 - costhetaMax of the last light visited (reference: stale variable, :162); 1 = "cos 0"
-    for (int a = 0; a < sc.n_area; ++a) {
-        const int lid = sc.area[a];
-        const MatF &src = mats[lid];
-        const float xi1 = rng.next_f32(S_AREA + 2 * a), xi2 = rng.next_f32(S_AREA + 2 * a + 1);
-        const F3 cx = mk(src.px, src.py, src.pz) - x;
-        const float len2 = dot(cx, cx), inv_len = rsqrtf(len2);
-        const float omc_max = one_minus_cos_max(src.r * src.r / len2);
-        omc_last = omc_max;
-        const F3 wi = cone_sample(cx * inv_len, omc_max, xi1, xi2);
-        float t; int hit_id = 0;
-        scan(sc, x, wi, t, hit_id, n_scans);
-        if (hit_id != lid) continue; // Le = 0 (samplingFunctions.h:199-200)
-        const F3 wi_l = unit(to_local(fr, wi));
-        const float cos_i = dot(fr.n, wi);
-        const float inv_fpdf = kTwoPi * omc_max, fpdf = 1.0f / inv_fpdf;
-        F3 f; float gpdf;
-        if (obj.material == 1) {
-            const F3 wh = unit(wi_l + wo_l);
-            f = facet_brdf(obj, wi_l, wh, wo_l);
-            gpdf = facet_pdf(wo_l, wh, obj.alpha);
-        } else {
-            f = mk(obj.cr, obj.cg, obj.cb) * kInvPi;
-            gpdf = cos_i * kInvPi;
-        }
-        const float Tr = expf(-k.sigma_t * len2 * inv_len);
-        const float w = power_heuristic(fpdf, gpdf);
-        total = total + had(mk(src.lr, src.lg, src.lb), f) * (cos_i * inv_fpdf * Tr * w);
-    }
-    // one BSDF sample (uniform :250 / microfacet :97)
-    const float xi1 = rng.next_f32(S_MIS), xi2 = rng.next_f32(S_MIS + 1);
-    if (obj.material == 1) {
-        const F3 wh = facet_normal(obj.alpha, xi1, xi2);
-        const F3 wi_l = unit(fma3(wh, 2.0f * dot(wh, wo_l), -wo_l));
-        const F3 wi = unit(to_world(fr, wi_l));
-        float t; int hit_id;
-        if (scan(sc, x, wi, t, hit_id, n_scans)) {
-            const MatF &src = mats[hit_id];
-            if (src.emits) {
-                const float gpdf = facet_pdf(wo_l, wh, obj.alpha);
-                const F3 g = had(mk(src.lr, src.lg, src.lb), facet_brdf(obj, wi_l, wh, wo_l)) * (wi_l.z / gpdf);
-                if (g.x > 0.0f) {
-                    const F3 cx = mk(src.px, src.py, src.pz) - x;
-                    omc_last = one_minus_cos_max(src.r * src.r / dot(cx, cx));
-                }
-                const float w = power_heuristic(gpdf, 1.0f / (kTwoPi * omc_last));
-                total = total + g * w;
-            }
-        }
-    } else {
-        const F3 wi = unit(to_world(fr, cosine_local(xi1, xi2)));
-        float t; int hit_id;
-        if (scan(sc, x, wi, t, hit_id, n_scans)) {
-            const MatF &src = mats[hit_id];
-            const F3 g = had(mk(src.lr, src.lg, src.lb), mk(obj.cr, obj.cg, obj.cb)); // Le*c/pi * cos / (cos/pi)
-            if (g.x > 0.0f && g.y > 0.0f && g.z > 0.0f) {
-                const F3 cx = mk(src.px, src.py, src.pz) - x;
-                const float omc = one_minus_cos_max(src.r * src.r / dot(cx, cx));
-                const float w = power_heuristic(dot(fr.n, wi) * kInvPi, 1.0f / (kTwoPi * omc));
-                total = total + g * w;
-            }
-        }
-    }
-    return total;
 }
 
 // bdsf (vptShadeMethods.h:16-59) folded with its use at :1323-1327: returns fs * cos / pdf and the unit direction wi.
@@ -383,101 +222,6 @@ __device__ __forceinline__ F3 bsdf_sample(const MatF &obj, const Frame &fr, F3 w
     }
     wi = unit(to_world(fr, cosine_local(xi1, xi2)));
     return mk(obj.cr, obj.cg, obj.cb); // c/pi * cos / (cos/pi)
-}
-
-// freeSingleScattering (volumetricBasicFunctions.h:284-340) / singleScattering (:225-281) without the 1/probSource,
-// transmitanceXT and sigma_s factors (the caller applies them).  The reference always draws two cone numbers (slots S_NEE); the point-light case needs none.
-template <class RngT>
-__device__ __forceinline__ F3 medium_direct(const SceneF &sc, const MatF &src, int src_id, F3 xt, const Consts &k, RngT &rng, unsigned &n_scans) {
-    const F3 light = mk(src.px, src.py, src.pz);
-    const F3 wc = light - xt;
-    const float d2 = dot(wc, wc), inv = rsqrtf(d2);
-    if (src.r == 0.0f) { // the reference draws two cone numbers here too (sequential list streams must still consume them)
-        rng.next_f32(S_NEE); rng.next_f32(S_NEE + 1);
-        if (!visible(sc, light, xt, n_scans)) return mk(0, 0, 0);
-        return mk(src.lr, src.lg, src.lb) * (expf(-k.sigma_t * d2 * inv) * kInv4Pi / d2);
-    }
-    const float xi1 = rng.next_f32(S_NEE), xi2 = rng.next_f32(S_NEE + 1);
-    const float omc_max = one_minus_cos_max(src.r * src.r / d2);
-    const F3 wl = cone_sample(wc * inv, omc_max, xi1, xi2);
-    float t; int hit_id = -1;
-    scan(sc, xt, wl, t, hit_id, n_scans);
-    if (hit_id != src_id) return mk(0, 0, 0);
-    return mk(src.lr, src.lg, src.lb) * (expf(-k.sigma_t * t) * kInv4Pi * kTwoPi * omc_max);
-}
-
-// One path vertex after a successful roulette draw: iterativeVPTracerFree (vptShadeMethods.h:1263-1340),
-// explicitVPTracerRecursive (:1014-1149) and MISVPTTracerRecursive (:1345-1481) in throughput form.
-// Returns false when the path ends here.
-template <int METHOD, class RngT>
-__device__ __forceinline__ bool vertex(const SceneF &sc, const MatF *mats, const Consts &k, Path &p, RngT &rng, Tally &tally) {
-    ++tally.events;
-    float t; int id = 0;
-    const bool hit = scan(sc, p.o, p.d, t, id, tally.scans);
-    if (!hit) t = kMaxFloat;
-
-    const int pick = min((int)(rng.next_f32(S_SRC) * k.n_emitters), sc.n_emitters - 1);
-    const int src_id = sc.emitters[pick];
-    const MatF &src = mats[src_id];
-
-    bool surface;
-    float dist, inv_pdf = 1.0f;
-    if (METHOD == 0) {
-        dist = -logf(1.0f - rng.next_f32(S_DIST)) * k.inv_sigma_t; // freeFlightSample, vptSamplingFunctions.h:11
-        surface = dist > t;
-    } else if (METHOD == 4) {
-        const float xi = rng.next_f32(S_DIST);
-        surface = mis_distance(mk(src.px, src.py, src.pz), p.o, p.d, t, expf(-k.sigma_t * t), k.sigma_t, k.inv_sigma_t, xi, rng.next_f32(S_DECIDE), dist, inv_pdf);
-    } else {
-        // equiAngularParams2 (volumetricBasicFunctions.h:209-223) + equiAngularProb (vptSamplingFunctions.h:60)
-        const float Tr = expf(-k.sigma_t * t); // TrActual :1046 / psurf :1407 (0 on a miss)
-        const F3 dv = mk(src.px, src.py, src.pz) - p.o;
-        const float proj = dot(dv, p.d);
-        const F3 perp = fma3(p.d, -proj, dv);
-        const float D = sqrtf(dot(perp, perp));
-        const float thA = atan2f(-proj, D), thB = atan2f(t - proj, D);
-        const float xi = rng.next_f32(S_DIST);
-        const float tl = D * tanf((1.0f - xi) * thA + xi * thB);
-        dist = tl + proj;
-        inv_pdf = fabsf(thB - thA) * (tl * tl + D * D) / (D * (1.0f - Tr));
-        const float xs = rng.next_f32(S_DECIDE);
-        surface = (METHOD == 1) ? (xs <= Tr) : (xs < Tr);
-    }
-
-    if (surface) {
-        const MatF &obj = mats[id];
-        if (obj.emits) { // :1308-1313
-            if (p.depth == 0) p.L = had(mk(obj.lr, obj.lg, obj.lb), p.beta);
-            return false;
-        }
-        const F3 x = fma3(p.d, t, p.o);
-        const Frame fr = make_frame(unit(x - mk(obj.px, obj.py, obj.pz)));
-        const F3 wo_l = unit(to_local(fr, -p.d));
-        const F3 Ld_point = point_light_direct(sc, obj, src, x, fr, wo_l, k, tally.scans);
-        const F3 Ld = surface_direct_mis(sc, mats, obj, x, fr, wo_l, k, rng, tally.scans);
-        p.L = p.L + had(Ld_point + Ld, p.beta) * k.inv_cp;
-        const float xi1 = rng.next_f32(S_BSDF), xi2 = obj.material == 2 ? 0.0f : rng.next_f32(S_BSDF + 1); // (the dielectric draws one number)
-        F3 wi;
-        const F3 weight = bsdf_sample(obj, fr, wo_l, xi1, xi2, wi);
-        p.beta = had(p.beta, weight) * k.inv_cp;
-        p.d = wi;
-        p.o = x;
-    } else {
-        const F3 xt = fma3(p.d, dist, p.o);
-        const F3 Ld = medium_direct(sc, src, src_id, xt, k, rng, tally.scans) * k.n_emitters;
-        const float xi1 = rng.next_f32(S_PHASE), xi2 = rng.next_f32(S_PHASE + 1);
-        if (METHOD == 0) {
-            p.L = p.L + had(Ld, p.beta) * k.albedo_over_cp;
-            p.beta = p.beta * k.albedo_over_cp;
-        } else {
-            const float w = k.sigma_s * expf(-k.sigma_t * dist) * inv_pdf * k.inv_cp; // sigma_s * T / (pdf * cp)
-            p.L = p.L + had(Ld, p.beta) * w;
-            p.beta = p.beta * w;
-        }
-        p.o = xt;
-        p.d = phase_sample(xi1, xi2);
-    }
-    return true;
 }
 
 } // namespace f32

@@ -1,0 +1,179 @@
+// vpt_scan.cuh -- the scene as every FP32 kernel reads it (shared memory) and THE all-sphere scan of the FP32 path.
+//
+// intersect (pathTracingUtilities.h:12-36) over Sphere::intersect (Sphere.h:27-37), FP32 semantics (include/vpt.h): r == 0 spheres have no
+// scan record.  One out-of-line copy (scan_sm_call) serves the product wavefront, the HBM wavefront, the megakernel, the ray marcher and
+// the unit kernels; the per-pair root arithmetic lives in pair_general / pair_direct, which VPT_UNIT_SPHERE_INTERSECT evaluates directly.
+//   * scan records are staged in shared memory as float4 and read with broadcast LDS.128;
+//   * ordinary spheres (r < 64) take the roots directly as -b -+ sqrt(det) with det = r^2 - |op - (op.d)d|^2 (no cancellation for small
+//     far-away spheres); spheres with r >= 64 (the r = 1e5 walls of Sphere.cpp:11-15 above all) use the re-anchored cancellation-free
+//     form: the host picks an anchor q on the sphere nearest the scene and m = q - p, then c = |o-q|^2 + 2 (o-q).m + c0 and the far root
+//     is c / q' with q' = -(b + sign(b) sqrt(det));
+//   * two spheres per iteration in the packed FP32 instructions of sm_100 (FFMA2 / FADD2 / FMUL2: one issue slot, two lanes);
+//   * the nearest accepted root is selected with one three-input unsigned minimum per sphere (see scan_sm_call).
+#pragma once
+#include "vpt_f32.cuh"
+
+namespace vpt {
+namespace f32 {
+
+constexpr float kSimpleRootMaxR2 = 64.0f * 64.0f; // = vpt_api.cpp kHuge^2: below it the direct-root form, from it on the re-anchored general form
+
+// Scan records are stored in PAIRS: component c of spheres 2j and 2j+1 sits in one 64-bit half of a float4.
+struct SmScene {
+    MatF mats[kMaxSpheres];
+    float4 ga[2 * kMaxSpheres]; // general-form pair j: (qx0 qx1 qy0 qy1) (qz0 qz1 c0_0 c0_1) (mx0 mx1 my0 my1) (mz0 mz1 - -)
+    float4 gb[kMaxSpheres];     // direct-root pair j:  (px0 px1 py0 py1) (pz0 pz1 r2_0 r2_1)
+    int gid[2 * kMaxSpheres + 2]; // scan slot -> caller's sphere index (general pairs first; -1: the padding slot of an odd class)
+    int n_pa, n_pb;             // pairs per class
+    int n_emitters, n_area;
+    int emitters[kMaxEmitters]; // spheres with any radiance channel > 0 (vptShadeMethods.h:1296), in index order
+    int area[kMaxEmitters];     // spheres with r > 0 && radiance.x > 0 (misSamplingFunctions.h:106), in index order
+};
+// cooperative staging by the whole block (call, then __syncthreads).  Scan order: general-form spheres first, in scene order, then the
+// direct-root ones; every scan record finds its place with one pass over its predecessors.  An odd class is padded with a record that no
+// ray can hit (negative discriminant for every ray).
+__device__ __forceinline__ void stage_scene(SmScene &S, const SceneF &sc, int tid, int n_threads) {
+    for (int i = tid; i < sc.n_spheres * (int)(sizeof(MatF) / 4); i += n_threads)
+        reinterpret_cast<uint32_t *>(S.mats)[i] = reinterpret_cast<const uint32_t *>(sc.mat)[i];
+    for (int i = tid; i < kMaxEmitters; i += n_threads) { S.emitters[i] = sc.emitters[i]; S.area[i] = sc.area[i]; }
+    int n_general = 0;
+    for (int g = 0; g < sc.n_geom; ++g) n_general += (sc.geom[g].big || sc.geom[g].r2 >= kSimpleRootMaxR2);
+    const int n_direct = sc.n_geom - n_general, n_pa = (n_general + 1) >> 1, n_pb = (n_direct + 1) >> 1;
+    float *ga = reinterpret_cast<float *>(S.ga), *gb = reinterpret_cast<float *>(S.gb);
+    if (tid < sc.n_geom) {
+        const GeomF &G = sc.geom[tid];
+        const bool general = G.big || G.r2 >= kSimpleRootMaxR2;
+        int before_same = 0;
+        for (int g = 0; g < tid; ++g) before_same += ((sc.geom[g].big || sc.geom[g].r2 >= kSimpleRootMaxR2) == general);
+        const int pair = before_same >> 1, h = before_same & 1;
+        if (general) {
+            float *r = ga + 16 * pair + h;
+            r[0] = G.qx; r[2] = G.qy; r[4] = G.qz; r[6] = G.c0; r[8] = G.mx; r[10] = G.my; r[12] = G.mz; r[14] = 0.0f;
+            S.gid[before_same] = G.id;
+        } else {
+            float *r = gb + 8 * pair + h;
+            r[0] = G.qx; r[2] = G.qy; r[4] = G.qz; r[6] = G.r2;
+            S.gid[2 * n_pa + before_same] = G.id;
+        }
+    }
+    if (tid == 0) {
+        S.n_pa = n_pa; S.n_pb = n_pb; S.n_emitters = sc.n_emitters; S.n_area = sc.n_area;
+        if (n_general & 1) { // c = |oq|^2 + 1e30 > b^2: never hit
+            float *r = ga + 16 * (n_pa - 1) + 1;
+            r[0] = 0.0f; r[2] = 0.0f; r[4] = 0.0f; r[6] = 1e30f; r[8] = 0.0f; r[10] = 0.0f; r[12] = 0.0f; r[14] = 0.0f;
+            S.gid[n_general] = -1;
+        }
+        if (n_direct & 1) { // r^2 = -1: never hit
+            float *r = gb + 8 * (n_pb - 1) + 1;
+            r[0] = 0.0f; r[2] = 0.0f; r[4] = 0.0f; r[6] = -1.0f;
+            S.gid[2 * n_pa + n_direct] = -1;
+        }
+    }
+}
+
+extern __shared__ __align__(16) unsigned char smwave_smem[]; // every kernel's dynamic shared memory starts with its SmScene
+
+struct ScanHit { float t; int index; };
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; } // MUFU.RCP, as __fdividef
+// sign flip that ptxas folds into the operand modifiers of the packed instructions: `neg.f32` without .ftz (under -ftz=true the compiler's
+// own negation is neg.ftz = a separate flushing FADD per lane; the consuming .FTZ instruction flushes anyway)
+__device__ __forceinline__ float neg_fold(float x) { float r; asm("neg.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(neg_fold(a.x), neg_fold(a.y)); }
+__device__ __forceinline__ float2 lo2(float4 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(float4 v) { return make_float2(v.z, v.w); }
+
+struct Ray2 { float2 ox, oy, oz, dx, dy, dz; }; // the ray with every component broadcast to both packed lanes
+__device__ __forceinline__ Ray2 ray2(float ox, float oy, float oz, float dx, float dy, float dz) {
+    return Ray2{make_float2(ox, ox), make_float2(oy, oy), make_float2(oz, oz), make_float2(dx, dx), make_float2(dy, dy), make_float2(dz, dz)};
+}
+// The two roots of both spheres of a pair, each MINUS 1e-4 (w = root - eps: see scan_sm_call).  NaN when the ray misses (det < 0).
+// Every add / multiply / fma is one packed instruction for both spheres (same IEEE roundings as a scalar, one-sphere-at-a-time form).
+__device__ __forceinline__ void pair_general(const float4 *__restrict__ rec, const Ray2 &r, float2 &w1, float2 &w2) {
+    const float4 A = rec[0], B = rec[1], C = rec[2], E = rec[3];
+    const float2 meps = make_float2(-kEps, -kEps);
+    const float2 mx = lo2(C), my = hi2(C), mz = lo2(E);
+    const float2 oqx = __fadd2_rn(r.ox, neg2(lo2(A))), oqy = __fadd2_rn(r.oy, neg2(hi2(A))), oqz = __fadd2_rn(r.oz, neg2(lo2(B)));
+    const float2 opx = __fadd2_rn(oqx, mx), opy = __fadd2_rn(oqy, my), opz = __fadd2_rn(oqz, mz);
+    const float2 b = __ffma2_rn(opx, r.dx, __ffma2_rn(opy, r.dy, __fmul2_rn(opz, r.dz)));
+    const float2 c = __ffma2_rn(oqx, __fadd2_rn(opx, mx), __ffma2_rn(oqy, __fadd2_rn(opy, my), __ffma2_rn(oqz, __fadd2_rn(opz, mz), hi2(B)))); // |op|^2 - r^2 without cancellation
+    const float2 det = __ffma2_rn(b, b, neg2(c));
+    const float2 sq = __fmul2_rn(det, make_float2(rsqrtf(det.x), rsqrtf(det.y))); // NaN when det <= 0
+    const float2 q = __fadd2_rn(neg2(b), neg2(make_float2(copysignf(sq.x, b.x), copysignf(sq.y, b.y)))); // the root without cancellation; the other one is c / q
+    w1 = __fadd2_rn(q, meps);
+    w2 = __ffma2_rn(c, make_float2(rcp_approx(q.x), rcp_approx(q.y)), meps);
+}
+__device__ __forceinline__ void pair_direct(const float4 *__restrict__ rec, const Ray2 &r, float2 &w1, float2 &w2) {
+    const float4 A = rec[0], B = rec[1];
+    const float2 meps = make_float2(-kEps, -kEps);
+    const float2 oqx = __fadd2_rn(r.ox, neg2(lo2(A))), oqy = __fadd2_rn(r.oy, neg2(hi2(A))), oqz = __fadd2_rn(r.oz, neg2(lo2(B)));
+    const float2 b = __ffma2_rn(oqx, r.dx, __ffma2_rn(oqy, r.dy, __fmul2_rn(oqz, r.dz)));
+    const float2 nb2 = neg2(b);
+    const float2 lx = __ffma2_rn(r.dx, nb2, oqx), ly = __ffma2_rn(r.dy, nb2, oqy), lz = __ffma2_rn(r.dz, nb2, oqz);
+    const float2 det = __ffma2_rn(neg2(lx), lx, __ffma2_rn(neg2(ly), ly, __ffma2_rn(neg2(lz), lz, hi2(B))));
+    const float2 sq = __fmul2_rn(det, make_float2(rsqrtf(det.x), rsqrtf(det.y)));
+    const float2 nbe = __fadd2_rn(nb2, meps);
+    w1 = __fadd2_rn(nbe, neg2(sq));
+    w2 = __fadd2_rn(nbe, sq);
+}
+
+// nearest accepted hit over all spheres: distance (+inf: none) and scan index.
+// Selection without compares: the reference accepts the near root unless it is below 1e-4, else the far one, and then requires
+// t > 1e-4 (Sphere.h:34, pathTracingUtilities.h:20) = the smallest root above 1e-4.  For w = root - 1e-4 the valid candidates are
+// exactly the positive floats, whose bit patterns order like unsigned integers, while negative values (sign bit) and the NaN of a
+// negative discriminant (0x7fffffff) compare above +inf: ONE three-input unsigned minimum per sphere replaces four compares and
+// selects on the half-rate ALU pipe; the index follows with one compare and one select.
+static __device__ __noinline__ ScanHit scan_sm_call(float ox, float oy, float oz, float dx, float dy, float dz) {
+    const SmScene &S = *reinterpret_cast<const SmScene *>(smwave_smem);
+    unsigned best = 0x7f800000u; // +inf
+    int bi = -1;
+    const int na = S.n_pa, nb = S.n_pb;
+    const Ray2 r = ray2(ox, oy, oz, dx, dy, dz);
+    for (int j = 0; j < na; ++j) {
+        float2 w1, w2;
+        pair_general(&S.ga[4 * j], r, w1, w2);
+        unsigned k = __vimin3_u32(best, __float_as_uint(w1.x), __float_as_uint(w2.x));
+        if (k != best) bi = 2 * j;
+        best = k;
+        k = __vimin3_u32(best, __float_as_uint(w1.y), __float_as_uint(w2.y));
+        if (k != best) bi = 2 * j + 1;
+        best = k;
+    }
+    for (int j = 0; j < nb; ++j) {
+        float2 w1, w2;
+        pair_direct(&S.gb[2 * j], r, w1, w2);
+        unsigned k = __vimin3_u32(best, __float_as_uint(w1.x), __float_as_uint(w2.x));
+        if (k != best) bi = 2 * (na + j);
+        best = k;
+        k = __vimin3_u32(best, __float_as_uint(w1.y), __float_as_uint(w2.y));
+        if (k != best) bi = 2 * (na + j) + 1;
+        best = k;
+    }
+    return ScanHit{__uint_as_float(best) + kEps, bi};
+}
+__device__ __forceinline__ bool scan_sm(const SmScene &S, F3 o, F3 d, float &t, int &id) {
+    const ScanHit h = scan_sm_call(o.x, o.y, o.z, d.x, d.y, d.z);
+    t = h.t;
+    id = h.index >= 0 ? S.gid[h.index] : -1;
+    return h.index >= 0;
+}
+
+// Sphere::intersect (Sphere.h:27-37) for ONE sphere through the scan's own pair arithmetic: the near root unless it is negative or within
+// 1e-4 of the origin, else the far one (which may be negative); 0 when the ray misses or the sphere has no scan record (r == 0).
+__device__ __forceinline__ float sphere_t_sm(const SmScene &S, int sphere, F3 o, F3 d) {
+    const Ray2 r = ray2(o.x, o.y, o.z, d.x, d.y, d.z);
+    const int n_slots = 2 * (S.n_pa + S.n_pb);
+    for (int slot = 0; slot < n_slots; ++slot) {
+        if (S.gid[slot] != sphere) continue;
+        float2 w1, w2;
+        if (slot < 2 * S.n_pa) pair_general(&S.ga[4 * (slot >> 1)], r, w1, w2);
+        else pair_direct(&S.gb[2 * ((slot - 2 * S.n_pa) >> 1)], r, w1, w2);
+        const float a = ((slot & 1) ? w1.y : w1.x) + kEps, b = ((slot & 1) ? w2.y : w2.x) + kEps;
+        if (!(a == a) || !(b == b)) return 0.0f;
+        const float t_near = fminf(a, b), t_far = fmaxf(a, b);
+        return (t_near < 0.0f || fabsf(t_near) < kEps) ? t_far : t_near;
+    }
+    return 0.0f;
+}
+
+} // namespace f32
+} // namespace vpt
