@@ -85,7 +85,8 @@ int validate_params(const vpt_params *p, bool need_image) {
     if (p->quirks & ~(uint32_t)VPT_QUIRKS_REFERENCE) return VPT_ERR_INVALID_ARGUMENT;
     if (p->precision == VPT_PRECISION_FP32 && p->quirks != 0) return VPT_ERR_UNSUPPORTED; // rounding-decided behaviours exist in FP64 only
     if (p->kernel < VPT_KERNEL_AUTO || p->kernel > VPT_KERNEL_WAVEFRONT_HBM) return VPT_ERR_INVALID_ARGUMENT;
-    if ((p->kernel == VPT_KERNEL_WAVEFRONT || p->kernel == VPT_KERNEL_WAVEFRONT_SM || p->kernel == VPT_KERNEL_WAVEFRONT_HBM) && p->precision != VPT_PRECISION_FP32) return VPT_ERR_UNSUPPORTED;
+    if (p->kernel == VPT_KERNEL_WAVEFRONT || p->kernel == VPT_KERNEL_MEGA_SCAN) return VPT_ERR_UNSUPPORTED; // superseded variants, no longer built (profiles/r1_summary.md has their measurements)
+    if ((p->kernel == VPT_KERNEL_WAVEFRONT_SM || p->kernel == VPT_KERNEL_WAVEFRONT_HBM) && p->precision != VPT_PRECISION_FP32) return VPT_ERR_UNSUPPORTED;
     return VPT_OK;
 }
 
@@ -227,10 +228,6 @@ int enqueue_render(const vpt_params *p, const vpt_sphere *spheres, int n_spheres
     const int blocks = owned_tiles(lp);
     int n_emit = 0;
     for (int i = 0; i < n_spheres; ++i) n_emit += emits(spheres[i]);
-    // material 2 (dielectric) lives in the product kernels (AUTO = WAVEFRONT_SM, WAVEFRONT_HBM), in MEGA and in FP64 REF; the two superseded
-    // FP32 variants kept for the kernel-by-measurement comparison do not carry it
-    if (p->precision == VPT_PRECISION_FP32 && (p->kernel == VPT_KERNEL_MEGA_SCAN || p->kernel == VPT_KERNEL_WAVEFRONT))
-        for (int i = 0; i < n_spheres; ++i) if (spheres[i].material == 2) return VPT_ERR_UNSUPPORTED;
     if (lp.tile_count > 1 || (n_emit == 0 && lp.method != VPT_METHOD_RAYMARCH) || blocks == 0) CUDA_TRY(cudaMemsetAsync(hdr_dev, 0, bytes, stream));
     if (lp.method == VPT_METHOD_RAYMARCH && lp.march_source >= n_spheres) return VPT_ERR_INVALID_ARGUMENT;
     if ((n_emit == 0 && lp.method != VPT_METHOD_RAYMARCH) || blocks == 0) return VPT_OK; // no emitter: every path returns black (vptShadeMethods.h:1301)
@@ -706,7 +703,7 @@ const char *vpt_strerror(int status) {
     case VPT_OK: return "ok";
     case VPT_ERR_INVALID_ARGUMENT: return "invalid argument";
     case VPT_ERR_SCENE: return "invalid scene (sphere count, emitter count or a non-finite / negative field)";
-    case VPT_ERR_UNSUPPORTED: return "unsupported (material 3; material 2 with the MEGA_SCAN / WAVEFRONT kernels; wavefront kernel in fp64; quirks in fp32 precision)";
+    case VPT_ERR_UNSUPPORTED: return "unsupported (material 3; the superseded MEGA_SCAN / WAVEFRONT kernels; wavefront kernel in fp64; quirks in fp32 precision)";
     case VPT_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
     case VPT_ERR_CUDA: return "CUDA runtime error (see vpt_last_cuda_error)";
     case VPT_ERR_IO: return "I/O error";

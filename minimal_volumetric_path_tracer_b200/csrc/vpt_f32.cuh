@@ -91,7 +91,7 @@ __device__ __forceinline__ float equiangular_sample(F3 light, F3 o, F3 d, float 
     dtheta = atan2f((b - a) * D, fmaf(a, b, D * D));
     const float tau = tanf(xi * dtheta);
     t_local = D * fmaf(D, tau, a) / fmaf(-a, tau, D);
-    return t_local + proj;
+    return __fadd_rn(t_local, proj); // (explicit roundings wherever a product meets a sum: every kernel that inlines this code must round alike)
 }
 
 // VPT_METHOD_MIS_DISTANCE (not in the reference, whose "MIS" method :1345 is the equi-angular estimator again):
@@ -112,15 +112,15 @@ __device__ __forceinline__ bool mis_distance(F3 light, F3 o, F3 d, float tmax, f
     const float dtheta = atan2f((b - a) * D, fmaf(a, b, D2));
     float tl;
     if (xd < fmaf(0.5f, Tr, 0.5f)) {
-        dist = -logf(1.0f - xi * (1.0f - Tr)) * inv_sigma_t;
+        dist = -logf(fmaf(-xi, 1.0f - Tr, 1.0f)) * inv_sigma_t;
         tl = dist - proj;
     } else {
         const float tau = tanf(xi * dtheta);
         tl = D * fmaf(D, tau, a) / fmaf(-a, tau, D);
-        dist = tl + proj;
+        dist = __fadd_rn(tl, proj);
     }
-    const float p_free = sigma_t * expf(-sigma_t * dist), p_equi = D * (1.0f - Tr) / (dtheta * fmaf(tl, tl, D2));
-    inv_pdf = 2.0f / (p_free + p_equi);
+    const float p_equi = D * (1.0f - Tr) / (dtheta * fmaf(tl, tl, D2));
+    inv_pdf = 2.0f / fmaf(sigma_t, expf(-sigma_t * dist), p_equi); // p_free + p_equi
     return false;
 }
 

@@ -1,16 +1,7 @@
-// vpt_kernels_f32.cu -- FP32 kernels of libvpt_b200 for sm_100a: the render megakernel (persistent per-pixel threads with
-// in-register path regeneration), the unit kernels behind vpt_unit(), the Philox test kernel and the FFMA peak probe.
-//
-// Kernel design (DESIGN.md "Megakernel"): one thread owns one pixel and walks its samples; a lane whose path died
-// (Russian roulette kills 40 % of paths before their first vertex, vptShadeMethods.h:1282) immediately regenerates the
-// next camera path in a cheap inner loop, so that every lane entering the expensive vertex() code has live work.  The
-// scene scan reads the sphere records from kernel-parameter constant memory with a warp-uniform index; the shading
-// records are staged in shared memory because they are indexed by the (divergent) hit id.  HBM traffic is the final
-// 12 B / pixel store.
+// vpt_kernels_f32.cu -- FP32 kernels of libvpt_b200 for sm_100a: the product kernel's launch (vpt_smwave.cuh), the one-thread-per-pixel
+// megakernel kept as the measured alternative, the ray marcher, the unit kernels behind vpt_unit(), the Philox test kernel and the FFMA
+// peak probe.  Every estimator evaluated here is vpt_stages.cuh -- the same functions the product kernel runs.
 #include <cuda_runtime.h>
-#include "vpt_f32.cuh"
-#include "vpt_mega_scan.cuh"
-#include "vpt_wavefront.cuh"
 #include "vpt_smwave.cuh"
 #include "vpt_march.cuh"
 
@@ -18,187 +9,85 @@ namespace vpt {
 
 using namespace f32;
 
-__device__ __forceinline__ Consts make_consts(const ConstsF &c) {
-    Consts k;
-    k.sigma_t = c.sigma_t; k.inv_sigma_t = c.inv_sigma_t; k.sigma_s = c.sigma_s; k.albedo_over_cp = c.albedo_over_cp;
-    k.inv_cp = c.inv_cp; k.q = c.q; k.n_emitters = c.n_emitters; k.method = c.method; k.max_depth = c.max_depth;
-    return k;
-}
-__device__ __forceinline__ CameraF make_camera(const ConstsF &c) {
-    CameraF cam;
-    cam.o = mk(c.cam_o[0], c.cam_o[1], c.cam_o[2]); cam.d = mk(c.cam_d[0], c.cam_d[1], c.cam_d[2]);
-    cam.cx = mk(c.cam_cx[0], c.cam_cx[1], c.cam_cx[2]); cam.cy = mk(c.cam_cy[0], c.cam_cy[1], c.cam_cy[2]);
-    cam.inv_w = c.inv_w; cam.inv_h = c.inv_h;
-    return cam;
-}
-// rt.cpp:787
-__device__ __forceinline__ F3 camera_dir(const CameraF &c, float x, float y, float xi1, float xi2) {
-    const float u = (x + xi1 - 0.5f) * c.inv_w - 0.5f, v = (y + xi2 - 0.5f) * c.inv_h - 0.5f;
-    return unit(fma3(c.cx, u, fma3(c.cy, v, c.d)));
-}
+// ---- context of the megakernel and the unit kernels: ONE thread drives one record through the stages ---------------------------------
+struct ThreadCtx {
+    const SmScene &S;
+    const ConstsF &k;
+    uint32_t key0, key1;
+    unsigned events = 0, scans = 0, nonfinite = 0;
+    double acc[3] = {0.0, 0.0, 0.0}; // radiance collected (the pixel's sum in the megakernel)
+    __device__ ThreadCtx(const SmScene &S_, const ConstsF &k_, uint32_t k0, uint32_t k1) : S(S_), k(k_), key0(k0), key1(k1) {}
+    __device__ __forceinline__ float4 rnd(const Rec &r, uint32_t block) const {
+        const uint4 b = philox_block(r.pixel, r.sample, r.depth, block, key0, key1);
+        return make_float4(u32_to_unit_f32(b.x), u32_to_unit_f32(b.y), u32_to_unit_f32(b.z), u32_to_unit_f32(b.w));
+    }
+    __device__ __forceinline__ float4 jitter(const Rec &r) const {
+        const uint4 b = philox_block(r.pixel, r.sample, kJitterBounce, 0, key0, key1);
+        return make_float4(u32_to_unit_f32(b.x), u32_to_unit_f32(b.y), 0.0f, 0.0f);
+    }
+    __device__ __forceinline__ bool scan(F3 o, F3 d, float &t, int &id) { return scan_sm(S, o, d, t, id); }
+    __device__ __forceinline__ void add(const Rec &, F3 L) {
+        if (!(fabsf(L.x) < kSmMaxContribution && fabsf(L.y) < kSmMaxContribution && fabsf(L.z) < kSmMaxContribution)) { ++nonfinite; return; }
+        acc[0] += (double)L.x; acc[1] += (double)L.y; acc[2] += (double)L.z;
+    }
+    __device__ __forceinline__ void last_step() {}
+    __device__ __forceinline__ void vertex(const Rec &, int) {}
+};
 
+// ---- the megakernel (VPT_KERNEL_MEGA): one thread owns one pixel and walks its samples, each path through trace_path --------------------
+// Kept as the measured alternative to the wavefronts (north_star: "megakernel or wavefront, chosen by measurement"): lanes of a warp sit in
+// different stages of different paths, so the scans run at a third of the lanes (profiles/r1_summary.md v0).
 template <int METHOD>
 __global__ void __launch_bounds__(kThreadsPerBlock) render_f32_kernel(const __grid_constant__ SceneF sc, const __grid_constant__ LaunchParams lp,
                                                                        const __grid_constant__ ConstsF cf, float *__restrict__ hdr, Counters *__restrict__ counters) {
-    __shared__ MatF mats[kMaxSpheres];
-    for (int i = threadIdx.x; i < sc.n_spheres * (int)(sizeof(MatF) / 4); i += blockDim.x)
-        reinterpret_cast<uint32_t *>(mats)[i] = reinterpret_cast<const uint32_t *>(sc.mat)[i];
-    __syncthreads();
-
-    const long long tile = (long long)blockIdx.x * lp.tile_count + lp.tile_rank;
-    const long long pixel = tile * kTile + threadIdx.x;
-    if (pixel >= lp.n_pixels) return;
-
-    const Consts k = make_consts(cf);
-    const CameraF cam = make_camera(cf);
-    const int row = (int)(pixel / lp.width), col = (int)(pixel - (long long)row * lp.width);
-    const float fx = (float)col, fy = (float)(lp.height - 1 - row); // rt.cpp:773: storage row 0 is the top of the image
-
-    double acc_r = 0, acc_g = 0, acc_b = 0;
-    Tally tally{0u, 0u};
-    unsigned nonfinite = 0;
-    Path p;
-    Rng rng;
-    int s = lp.sample_begin;
-    bool active = false;
-    p.depth = 0;
-
-    for (;;) {
-        // phase A: make sure this lane holds a vertex that survived roulette (regenerate as often as needed)
-        bool have = false;
-        for (;;) {
-            if (!active) {
-                if (s >= lp.sample_end) break;
-                rng.start((uint32_t)pixel, (uint32_t)s, lp.key0, lp.key1);
-                float j1, j2;
-                rng.jitter_f32(j1, j2);
-                p.o = cam.o; p.d = camera_dir(cam, fx, fy, j1, j2);
-                p.beta = mk(1, 1, 1); p.L = mk(0, 0, 0); p.depth = 0;
-                active = true; ++s;
-            }
-            rng.begin_bounce((uint32_t)p.depth);
-            const bool too_deep = k.max_depth > 0 && p.depth >= k.max_depth;
-            if (too_deep || rng.next_f32(S_RR) < k.q) { // roulette at every vertex including the first (:1282)
-                const float sum = p.L.x + p.L.y + p.L.z;
-                if (isfinite(sum)) { acc_r += p.L.x; acc_g += p.L.y; acc_b += p.L.z; } else ++nonfinite;
-                active = false;
-                continue;
-            }
-            have = true;
-            break;
-        }
-        if (!have) break;
-        // phase B: one path vertex
-        if (vertex<METHOD>(sc, mats, k, p, rng, tally)) {
-            ++p.depth;
-        } else {
-            const float sum = p.L.x + p.L.y + p.L.z;
-            if (isfinite(sum)) { acc_r += p.L.x; acc_g += p.L.y; acc_b += p.L.z; } else ++nonfinite;
-            active = false;
-        }
-    }
-
-    float *out = hdr + pixel * 3;
-    out[0] = (float)(acc_r * lp.out_scale);
-    out[1] = (float)(acc_g * lp.out_scale);
-    out[2] = (float)(acc_b * lp.out_scale);
-
-    if (!counters) return;
-    // statistics: warp-reduce, one atomic per warp
-    unsigned long long ev = tally.events, scn = tally.scans, nf = nonfinite, np = (unsigned long long)(lp.sample_end - lp.sample_begin);
-    const unsigned mask = __activemask();
-    for (int off = 16; off > 0; off >>= 1) {
-        ev += __shfl_down_sync(mask, ev, off); scn += __shfl_down_sync(mask, scn, off);
-        nf += __shfl_down_sync(mask, nf, off); np += __shfl_down_sync(mask, np, off);
-    }
-    if (mask != 0xffffffffu) { // partial warp at the image end: fall back to per-lane atomics
-        atomicAdd(&counters->events, (unsigned long long)tally.events); atomicAdd(&counters->scans, (unsigned long long)tally.scans);
-        atomicAdd(&counters->nonfinite, (unsigned long long)nonfinite); atomicAdd(&counters->paths, (unsigned long long)(lp.sample_end - lp.sample_begin));
-    } else if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&counters->events, ev); atomicAdd(&counters->scans, scn); atomicAdd(&counters->nonfinite, nf); atomicAdd(&counters->paths, np);
-    }
-}
-
-// ---- scan-converged megakernel (vpt_mega_scan.cuh) ------------------------------------------------------------------------------
-template <int METHOD>
-__global__ void __launch_bounds__(kThreadsPerBlock) render_f32_scan_kernel(const __grid_constant__ SceneF sc, const __grid_constant__ LaunchParams lp,
-                                                                            const __grid_constant__ ConstsF cf, float *__restrict__ hdr, Counters *__restrict__ counters) {
-    __shared__ MatF mats[kMaxSpheres];
-    for (int i = threadIdx.x; i < sc.n_spheres * (int)(sizeof(MatF) / 4); i += blockDim.x)
-        reinterpret_cast<uint32_t *>(mats)[i] = reinterpret_cast<const uint32_t *>(sc.mat)[i];
+    SmScene &S = *reinterpret_cast<SmScene *>(smwave_smem);
+    stage_scene(S, sc, (int)threadIdx.x, (int)blockDim.x);
     __syncthreads();
     const long long tile = (long long)blockIdx.x * lp.tile_count + lp.tile_rank;
     const long long pixel = tile * kTile + threadIdx.x;
     if (pixel >= lp.n_pixels) return;
-    const Consts k = make_consts(cf);
-    const CameraF cam = make_camera(cf);
-    const int row = (int)(pixel / lp.width), col = (int)(pixel - (long long)row * lp.width);
-    double acc[3] = {0, 0, 0};
-    Tally tally{0u, 0u};
-    unsigned nonfinite = 0;
-    render_pixel_scan<METHOD>(sc, mats, k, cam, (float)col, (float)(lp.height - 1 - row), (uint32_t)pixel, lp.sample_begin, lp.sample_end, lp.key0, lp.key1, acc, tally, nonfinite);
+    ThreadCtx c(S, cf, lp.key0, lp.key1);
+    for (int s = lp.sample_begin; s < lp.sample_end; ++s) {
+        Rec r;
+        r.aux = 0u;
+        if (stage_gen(c, true, (uint32_t)pixel, (uint32_t)s, lp.width, lp.height, r)) trace_path<METHOD>(c, r);
+    }
     float *out = hdr + pixel * 3;
-    out[0] = (float)(acc[0] * lp.out_scale);
-    out[1] = (float)(acc[1] * lp.out_scale);
-    out[2] = (float)(acc[2] * lp.out_scale);
+    out[0] = (float)(c.acc[0] * lp.out_scale);
+    out[1] = (float)(c.acc[1] * lp.out_scale);
+    out[2] = (float)(c.acc[2] * lp.out_scale);
     if (!counters) return;
-    atomicAdd(&counters->events, (unsigned long long)tally.events); atomicAdd(&counters->scans, (unsigned long long)tally.scans);
-    if (nonfinite) atomicAdd(&counters->nonfinite, (unsigned long long)nonfinite);
+    atomicAdd(&counters->events, (unsigned long long)c.events); atomicAdd(&counters->scans, (unsigned long long)c.scans);
+    if (c.nonfinite) atomicAdd(&counters->nonfinite, (unsigned long long)c.nonfinite);
     atomicAdd(&counters->paths, (unsigned long long)(lp.sample_end - lp.sample_begin));
 }
-
-// ---- warp-local wavefront (vpt_wavefront.cuh) ----------------------------------------------------------------------------------
-template <int METHOD>
-__global__ void __launch_bounds__(kThreadsPerBlock) render_f32_wave_kernel(const __grid_constant__ SceneF sc, const __grid_constant__ LaunchParams lp,
-                                                                            const __grid_constant__ ConstsF cf, float *__restrict__ hdr, Counters *__restrict__ counters) {
-    __shared__ MatF mats[kMaxSpheres];
-    __shared__ WarpPool pools[kWarpsPerBlock];
-    for (int i = threadIdx.x; i < sc.n_spheres * (int)(sizeof(MatF) / 4); i += blockDim.x)
-        reinterpret_cast<uint32_t *>(mats)[i] = reinterpret_cast<const uint32_t *>(sc.mat)[i];
-    __syncthreads();
-    const long long tile = (long long)blockIdx.x * lp.tile_count + lp.tile_rank;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long pixel_base = tile * kTile + warp * 32;
-    const int n_valid = (int)min(32LL, (long long)lp.n_pixels - pixel_base);
-    if (n_valid <= 0) return;
-    const Consts k = make_consts(cf);
-    const CameraF cam = make_camera(cf);
-    WarpPool &P = pools[warp];
-    Wavefront<METHOD> wf(sc, mats, k, cam, P, lp.key0, lp.key1, (uint32_t)pixel_base, n_valid, lp.width, lp.height);
-    wf.run(lp.sample_begin, lp.sample_end);
-    __syncwarp();
-    if (lane < n_valid) {
-        float *out = hdr + (pixel_base + lane) * 3;
-        for (int c = 0; c < 3; ++c) out[c] = (float)((double)(long long)P.acc[lane][c] * kFixInv * lp.out_scale);
-    }
-    if (!counters) return;
-    atomicAdd(&counters->events, (unsigned long long)wf.events); atomicAdd(&counters->scans, (unsigned long long)wf.scans);
-    if (wf.nonfinite) atomicAdd(&counters->nonfinite, (unsigned long long)wf.nonfinite);
-    atomicAdd(&counters->paths, (unsigned long long)wf.paths);
-}
-
 
 // ---- SM-wide wavefront (vpt_smwave.cuh) -----------------------------------------------------------------------------------------
 template <int METHOD>
 __global__ void __launch_bounds__(kSmThreads, 1) render_f32_smwave_kernel(const __grid_constant__ SceneF sc, const __grid_constant__ LaunchParams lp,
                                                                            const __grid_constant__ ConstsF cf, float *__restrict__ hdr, Counters *__restrict__ counters,
                                                                            int log_p, int n_owned_tiles, int n_items, int zero) {
-    SmShared &S = sm_shared();
+    SmShared &M = sm_shared();
     const int tid = (int)threadIdx.x;
-    stage_scene(S.scene, sc, tid, kSmThreads);
-    for (int i = tid; i < kSmPool; i += kSmThreads) { S.freelist[i] = (uint16_t)i; S.r1[i] = 0u; S.meta[i] = 0u; }
-    for (int i = tid; i < 2 * kSmMaxItemPixels * 3; i += kSmThreads) (&S.acc[0][0][0])[i] = 0ull;
+    stage_scene(M.scene, sc, tid, kSmThreads);
+    for (int i = tid; i < kSmPool; i += kSmThreads) { M.freelist[i] = (uint16_t)i; M.meta[i] = 0u; }
+    if (tid < 32) { // record 0 backs the idle lanes of partial batches before it is first allocated: give it in-range values
+        M.ox[0] = M.oy[0] = M.oz[0] = 0.0f; M.dx[0] = M.dy[0] = 0.0f; M.dz[0] = 1.0f; M.br[0] = M.bg[0] = M.bb[0] = 0.0f;
+        M.sample[0] = 0u; M.xd[0] = M.xs[0] = 0.5f;
+    }
+    for (int i = tid; i < 2 * kSmMaxItemPixels * 3; i += kSmThreads) (&M.acc[0][0][0])[i] = 0ull;
     if (tid == 0) {
-        for (int q = 0; q < SQ_COUNT; ++q) { S.q_tail[q] = 0u; S.q_end[q] = 0u; }
-        S.free_head = 0u; S.free_tail = (unsigned)kSmPool;
+        for (int q = 0; q < SQ_COUNT; ++q) { M.q_tail[q] = 0u; M.q_end[q] = 0u; }
+        M.free_head = 0u; M.free_tail = (unsigned)kSmPool;
         for (int b = 0; b < 2; ++b) {
             const int item = (int)blockIdx.x + b * (int)gridDim.x;
-            S.t_item[b] = item < n_items ? item : -1; S.t_cursor[b] = 0u; S.t_done[b] = 0u;
+            M.t_item[b] = item < n_items ? item : -1; M.t_cursor[b] = 0u; M.t_done[b] = 0u;
         }
-        S.next_item = (int)blockIdx.x + 2 * (int)gridDim.x;
+        M.next_item = (int)blockIdx.x + 2 * (int)gridDim.x;
+        M.gen_slot = -1; M.tail_limit = 0u;
     }
     __syncthreads();
-    SmWave<METHOD> wf(S, sc, cf, lp, log_p, n_owned_tiles, zero);
+    SmWave<METHOD> wf(M, cf, lp, log_p, n_owned_tiles, zero);
     wf.run(hdr, n_items);
     if (!counters) return;
     unsigned long long ev = wf.events, scn = wf.scans, nf = wf.nonfinite, np = wf.paths;
@@ -240,15 +129,13 @@ __global__ void __launch_bounds__(kThreadsPerBlock) render_f32_march_kernel(cons
     const long long tile = (long long)blockIdx.x * lp.tile_count + lp.tile_rank;
     const long long pixel = tile * kTile + threadIdx.x;
     if (pixel >= lp.n_pixels) return;
-    const CameraF cam = make_camera(cf);
-    const int row = (int)(pixel / lp.width), col = (int)(pixel - (long long)row * lp.width);
     double acc[3] = {0, 0, 0};
     unsigned scans = 0, nonfinite = 0;
     for (int s = lp.sample_begin; s < lp.sample_end; ++s) {
         const uint4 j = philox_block((uint32_t)pixel, (uint32_t)s, kJitterBounce, 0, lp.key0, lp.key1);
-        const F3 d = camera_dir(cam, (float)col, (float)(lp.height - 1 - row), u32_to_unit_f32(j.x), u32_to_unit_f32(j.y));
+        const F3 d = camera_dir(cf, (uint32_t)pixel, lp.width, lp.height, u32_to_unit_f32(j.x), u32_to_unit_f32(j.y));
         double L[3]; unsigned n_steps;
-        ray_march3(S, cam.o, d, lp.march_step, cf.march_source, cf.sigma_t, cf.sigma_s, L, n_steps, scans);
+        ray_march3(S, mk(cf.cam_o[0], cf.cam_o[1], cf.cam_o[2]), d, lp.march_step, cf.march_source, cf.sigma_t, cf.sigma_s, L, n_steps, scans);
         if (isfinite(L[0] + L[1] + L[2])) { acc[0] += L[0]; acc[1] += L[1]; acc[2] += L[2]; } else ++nonfinite;
     }
     float *out = hdr + pixel * 3;
@@ -267,45 +154,77 @@ int launch_render_f32(const SceneF &scene, const LaunchParams &lp, const ConstsF
     cudaStream_t st = (cudaStream_t)stream;
     if (kernel == VPT_KERNEL_MEGA) {
         switch (lp.method) {
-        case 0: render_f32_kernel<0><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
-        case 1: render_f32_kernel<1><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
-        case 4: render_f32_kernel<4><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
-        default: render_f32_kernel<2><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
+        case 0: render_f32_kernel<0><<<n_blocks, kThreadsPerBlock, sizeof(SmScene), st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
+        case 1: render_f32_kernel<1><<<n_blocks, kThreadsPerBlock, sizeof(SmScene), st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
+        case 4: render_f32_kernel<4><<<n_blocks, kThreadsPerBlock, sizeof(SmScene), st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
+        default: render_f32_kernel<2><<<n_blocks, kThreadsPerBlock, sizeof(SmScene), st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
         }
-    } else if (kernel == VPT_KERNEL_WAVEFRONT_SM) {
-        switch (lp.method) {
-        case 0: return launch_smwave<0>(scene, lp, cf, hdr_dev, counters_dev, st, n_blocks);
-        case 1: return launch_smwave<1>(scene, lp, cf, hdr_dev, counters_dev, st, n_blocks);
-        case 4: return launch_smwave<4>(scene, lp, cf, hdr_dev, counters_dev, st, n_blocks);
-        default: return launch_smwave<2>(scene, lp, cf, hdr_dev, counters_dev, st, n_blocks);
-        }
-    } else if (kernel == VPT_KERNEL_WAVEFRONT) {
-        switch (lp.method) {
-        case 0: render_f32_wave_kernel<0><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
-        case 1: render_f32_wave_kernel<1><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
-        case 4: render_f32_wave_kernel<4><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
-        default: render_f32_wave_kernel<2><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
-        }
-    } else {
-        switch (lp.method) {
-        case 0: render_f32_scan_kernel<0><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
-        case 1: render_f32_scan_kernel<1><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
-        case 4: render_f32_scan_kernel<4><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
-        default: render_f32_scan_kernel<2><<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, cf, hdr_dev, counters_dev); break;
-        }
+        return (int)cudaGetLastError();
     }
-    return (int)cudaGetLastError();
+    switch (lp.method) { // VPT_KERNEL_WAVEFRONT_SM
+    case 0: return launch_smwave<0>(scene, lp, cf, hdr_dev, counters_dev, st, n_blocks);
+    case 1: return launch_smwave<1>(scene, lp, cf, hdr_dev, counters_dev, st, n_blocks);
+    case 4: return launch_smwave<4>(scene, lp, cf, hdr_dev, counters_dev, st, n_blocks);
+    default: return launch_smwave<2>(scene, lp, cf, hdr_dev, counters_dev, st, n_blocks);
+    }
 }
 
 // ---- unit kernels (include/vpt.h vpt_unit_fn) ---------------------------------------------------------------------------
 __device__ __forceinline__ F3 ld3(const double *p) { return mk((float)p[0], (float)p[1], (float)p[2]); }
 __device__ __forceinline__ void st3(double *p, F3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+__device__ __forceinline__ void st3d(double *p, const double *v) { p[0] = v[0]; p[1] = v[1]; p[2] = v[2]; }
 
-// explicit uniforms of a test row, served through the stream interface the render code uses
-struct ListRng {
-    const double *u; int i; int n = 1 << 30; bool overrun = false;
-    __device__ float next_f32(uint32_t = 0) { if (i >= n) { overrun = true; return 0.0f; } /* 0 < q: the next roulette draw ends the path */ return (float)u[i++]; }
-    __device__ void begin_bounce(uint32_t) {}
+// A stage context whose random numbers are an EXPLICIT list of uniforms in the reference's consumption order (e.g. the reference's own
+// erand48 sequence, or the draws of one golden vector): per bounce  roulette, light pick, distance[, decision]  then
+//   medium vertex:   2 cone numbers (NEE), 2 phase-function numbers
+//   surface vertex:  per area light 2 cone numbers (+ 1 for a dielectric, misSamplingFunctions.h:116), 2 (dielectric: 1) for the BSDF-sampled
+//                    light term of MISv2, 2 (dielectric: 1) for bdsf
+// vertex() deals the vertex's numbers into the Philox block layout the stages ask for (vpt_philox.cuh slot table); block 0 of the next
+// bounce is dealt on demand, so that a path ended by the roulette has consumed exactly the reference's count.
+struct ListCtx {
+    const SmScene &S;
+    const ConstsF &k;
+    const double *u; int n; int i = 0; bool overrun = false;
+    unsigned events = 0, scans = 0, nonfinite = 0;
+    double acc[3] = {0.0, 0.0, 0.0};
+    float tab[12][4]; // blocks 1 .. 11 of the current vertex (block 10 + : the dielectric's per-light draws, slots 40 ..)
+    __device__ ListCtx(const SmScene &S_, const ConstsF &k_, const double *u_, int n_) : S(S_), k(k_), u(u_), n(n_) {
+        for (int b = 0; b < 12; ++b) tab[b][0] = tab[b][1] = tab[b][2] = tab[b][3] = 0.5f;
+    }
+    __device__ float next() { if (i >= n) { overrun = true; return 0.0f; } /* 0 < q: the next roulette draw ends the path */ return (float)u[i++]; }
+    __device__ float4 rnd(const Rec &r, uint32_t block) {
+        if (block == 0u) { // the header of bounce r.depth, in the reference's order and with its short-circuits
+            if ((k.max_depth > 0 && (int)r.depth >= k.max_depth) || r.depth >= (uint32_t)VPT_MAX_DEPTH) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            float4 h = make_float4(next(), 0.0f, 0.0f, 0.5f);
+            if (h.x < k.q) return h;
+            h.y = next(); h.z = next();
+            if (k.method != 0) h.w = next();
+            return h;
+        }
+        const uint32_t b = block < 12u ? block : 11u;
+        return make_float4(tab[b][0], tab[b][1], tab[b][2], tab[b][3]);
+    }
+    __device__ float4 jitter(const Rec &) { return make_float4(0.5f, 0.5f, 0.0f, 0.0f); }
+    __device__ __forceinline__ bool scan(F3 o, F3 d, float &t, int &id) { return scan_sm(S, o, d, t, id); }
+    __device__ __forceinline__ void add(const Rec &, F3 L) {
+        if (!(fabsf(L.x) < kSmMaxContribution && fabsf(L.y) < kSmMaxContribution && fabsf(L.z) < kSmMaxContribution)) { ++nonfinite; return; }
+        acc[0] += (double)L.x; acc[1] += (double)L.y; acc[2] += (double)L.z;
+    }
+    __device__ __forceinline__ void last_step() {}
+    __device__ void set_slot(uint32_t slot, float v) { const uint32_t b = slot >> 2; if (b >= 1u && b < 12u) tab[b][slot & 3u] = v; }
+    __device__ void vertex(const Rec &r, int dest) {
+        if (dest == SQ_MED_POINT || dest == SQ_MED_AREA) {
+            set_slot(S_NEE, next()); set_slot(S_NEE + 1, next()); set_slot(S_PHASE, next()); set_slot(S_PHASE + 1, next());
+        } else if (dest == SQ_SURF_P || dest == SQ_SURF_L || dest == SQ_SURF_F) {
+            const bool diel = S.mats[r.hid].material == 2;
+            for (int a = 0; a < S.n_area; ++a) {
+                set_slot(S_AREA + 2 * a, next()); set_slot(S_AREA + 2 * a + 1, next());
+                if (diel) set_slot(S_DIEL + a, next());
+            }
+            set_slot(S_MIS, next()); if (!diel) set_slot(S_MIS + 1, next());
+            set_slot(S_BSDF, next()); if (!diel) set_slot(S_BSDF + 1, next());
+        }
+    }
 };
 
 __global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const __grid_constant__ LaunchParams lp, const __grid_constant__ ConstsF cf, int n, const double *__restrict__ in,
@@ -318,35 +237,30 @@ __global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const
     if (row >= n) return;
     const double *a = in + (size_t)row * in_stride;
     double *o = out + (size_t)row * out_stride;
-    const Consts k = make_consts(cf);
-    unsigned scans = 0;
+    Rec r;
+    r.o = mk(0, 0, 0); r.d = mk(0, 0, 1); r.beta = mk(1, 1, 1); r.pixel = r.sample = r.depth = r.src = r.hid = r.aux = 0u; r.xi_dist = r.xi_decide = 0.5f;
     switch (fn) {
-    case VPT_UNIT_SPHERE_INTERSECT: {
-        const int idx = (int)a[0];
-        float t = 0.0f; // r == 0 spheres have no scan record in fp32: they are never hit
-        for (int g = 0; g < sc.n_geom; ++g) if (sc.geom[g].id == idx) t = sphere_t(sc.geom[g], ld3(a + 1), ld3(a + 4));
-        o[0] = t;
-    } break;
-    case VPT_UNIT_INTERSECT: { // the product kernel's scan (vpt_smwave.cuh scan_sm); on a miss the reference leaves id untouched (0)
+    case VPT_UNIT_SPHERE_INTERSECT: o[0] = sphere_t_sm(PS, (int)a[0], ld3(a + 1), ld3(a + 4)); break; // the scan's own root arithmetic, one sphere
+    case VPT_UNIT_INTERSECT: { // the product kernel's scan (vpt_scan.cuh); on a miss the reference leaves id untouched (0)
         float t = 0.0f; int id = 0;
         const bool h = scan_sm(PS, ld3(a), ld3(a + 3), t, id);
         o[0] = h; o[1] = h ? t : 0.0; o[2] = h ? id : 0;
     } break;
-    case VPT_UNIT_VISIBILITY: { // as the product kernel's point-light shadow ray: nothing hit before distance * (1 - 1e-4)
+    case VPT_UNIT_VISIBILITY: { // as the stages' point-light shadow rays: nothing hit before distance * (1 - 1e-4)
         const F3 light = ld3(a), lx = light - ld3(a + 3);
         const float d2 = dot(lx, lx), inv = rsqrtf(d2);
         float t; int id;
         const bool h = scan_sm(PS, light, lx * (-inv), t, id);
         o[0] = !h || t > d2 * inv * (1.0f - 1e-4f);
     } break;
-    case VPT_UNIT_TRANSMITTANCE: {
+    case VPT_UNIT_TRANSMITTANCE: { // the stages' transmittance (vpt_stages.cuh transmit: ex2.approx)
         const F3 v = ld3(a + 3) - ld3(a);
-        o[0] = expf(-(float)a[6] * sqrtf(dot(v, v)));
+        o[0] = transmit((float)a[6] * sqrtf(dot(v, v)));
     } break;
-    case VPT_UNIT_FREE_FLIGHT: {
-        const float st = (float)a[0], xi = (float)a[1];
-        const float d = -logf(1.0f - xi) / st;
-        const float e = expf(-st * d);
+    case VPT_UNIT_FREE_FLIGHT: { // stage_primary<0>'s distance and the stages' transmittance
+        const float st = (float)a[0], inv_st = (float)(1.0 / a[0]), xi = (float)a[1];
+        const float d = -logf(1.0f - xi) * inv_st;
+        const float e = transmit(st * d);
         o[0] = d; o[1] = st * e; o[2] = 1.0f - e; o[3] = e;
     } break;
     case VPT_UNIT_PHASE_SAMPLE: st3(o, phase_sample((float)a[0], (float)a[1])); break;
@@ -356,7 +270,7 @@ __global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const
         const F3 org = ld3(a + 2), dir = ld3(a + 5);
         const float xi = (float)a[8];
         const F3 light = mk(src.px, src.py, src.pz);
-        float D, dth, tl; // the product kernel's form (vpt_f32.cuh equiangular_sample): the two angles are reported for the comparison only
+        float D, dth, tl; // the stages' form (vpt_f32.cuh equiangular_sample): the two angles are reported for the comparison only
         const float dist = equiangular_sample(light, org, dir, tmax, xi, D, dth, tl);
         const float thA = atan2f(-dot(light - org, dir), D);
         o[0] = D; o[1] = thA; o[2] = thA + dth; o[3] = tl; o[4] = dist;
@@ -366,7 +280,7 @@ __global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const
         const MatF &src = mats[(int)a[0]];
         const float tmax = (float)fmin(a[1], (double)kMaxFloat), st = (float)a[8];
         float dist, inv_pdf;
-        const bool surface = mis_distance(mk(src.px, src.py, src.pz), ld3(a + 2), ld3(a + 5), tmax, expf(-st * tmax), st, 1.0f / st, (float)a[9], (float)a[10], dist, inv_pdf);
+        const bool surface = mis_distance(mk(src.px, src.py, src.pz), ld3(a + 2), ld3(a + 5), tmax, transmit(st * tmax), st, 1.0f / st, (float)a[9], (float)a[10], dist, inv_pdf);
         o[0] = surface; o[1] = dist; o[2] = surface ? 1.0f : 1.0f / inv_pdf;
     } break;
     case VPT_UNIT_DIELECTRIC: {
@@ -381,8 +295,8 @@ __global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const
         st3(o, w); o[3] = dot(nrm, w) * kInvPi;
     } break;
     case VPT_UNIT_CONE_SAMPLE: {
-        const float r = (float)a[3], dist = (float)a[4];
-        const float omc = one_minus_cos_max(r * r / (dist * dist));
+        const float rr = (float)a[3], dist = (float)a[4];
+        const float omc = one_minus_cos_max(rr * rr / (dist * dist));
         st3(o, cone_sample(ld3(a), omc, (float)a[5], (float)a[6]));
         o[3] = 1.0f / (kTwoPi * omc);
     } break;
@@ -396,81 +310,63 @@ __global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const
         o[3] = facet_pdf(wo, wh, m.alpha); o[4] = beckmann(wh, m.alpha); o[5] = smith_g1(wi, wh, m.alpha) * smith_g1(wo, wh, m.alpha);
     } break;
     case VPT_UNIT_FACET_NORMAL: st3(o, facet_normal((float)a[0], (float)a[1], (float)a[2])); break;
-    case VPT_UNIT_MEDIUM_NEE: {
+    // ---- the composite functions: ONE record pushed through the product's stage function, contributions captured -------------------
+    case VPT_UNIT_MEDIUM_NEE: { // stage_med<POINT / AREA>: (free)SingleScattering = the stage's radiance contribution for throughput T sigma_s (or 1)
         const int sid = (int)a[3];
         const float sigma_s = (float)a[5], T = (float)a[6], pS = (float)a[7];
-        Consts kk = k; kk.sigma_t = (float)a[4];
-        ListRng lr{a + 8, 0};
-        F3 Ld = medium_direct(sc, mats[sid], sid, ld3(a), kk, lr, scans) * (1.0f / pS);
-        if (T >= 0.0f) Ld = Ld * (T * sigma_s);
-        st3(o, Ld);
+        ConstsF kk = cf; kk.sigma_t = (float)a[4]; kk.n_emitters = 1.0f / pS; kk.q = 2.0f; // (the roulette after the vertex always ends the path)
+        ListCtx c(PS, kk, a + 8, 2);
+        r.o = ld3(a); r.src = (uint32_t)sid;
+        if (T >= 0.0f) r.beta = mk(T * sigma_s, T * sigma_s, T * sigma_s);
+        const bool point = mats[sid].r == 0.0f;
+        c.vertex(r, point ? SQ_MED_POINT : SQ_MED_AREA);
+        if (point) stage_med<true>(c, true, r); else stage_med<false>(c, true, r);
+        st3d(o, c.acc);
     } break;
-    case VPT_UNIT_POINT_LIGHT: {
-        const int oid = (int)a[0], sid = (int)a[10];
-        const F3 x = ld3(a + 1), nrm = ld3(a + 4), wray = ld3(a + 7);
-        const Frame fr = make_frame(nrm);
-        const F3 wo_l = unit(to_local(fr, -wray));
-        Consts kk = k; kk.sigma_t = 0.0f; kk.n_emitters = 1.0f; // bare pLight: no transmittance, no 1/probSource
-        st3(o, point_light_direct(sc, mats[oid], mats[sid], x, fr, wo_l, kk, scans));
+    case VPT_UNIT_POINT_LIGHT: { // stage_surf_p: bare pLight (no transmittance, no 1 / probSource, no 1 / cp)
+        ConstsF kk = cf; kk.sigma_t = 0.0f; kk.n_emitters = 1.0f; kk.inv_cp = 1.0f;
+        ListCtx c(PS, kk, a, 0);
+        r.hid = (uint32_t)a[0]; r.o = ld3(a + 1); r.d = ld3(a + 7); r.src = (uint32_t)a[10];
+        stage_surf_p(c, true, r);
+        st3d(o, c.acc);
     } break;
-    case VPT_UNIT_SURFACE_MIS: {
-        const int oid = (int)a[0];
-        const F3 x = ld3(a + 1), nrm = ld3(a + 4), wray = ld3(a + 7);
-        const Frame fr = make_frame(nrm);
-        const F3 wo_l = unit(to_local(fr, -wray));
-        Consts kk = k; kk.sigma_t = (float)a[10];
-        ListRng lr{a + 11, 0};
-        st3(o, surface_direct_mis(sc, mats, mats[oid], x, fr, wo_l, kk, lr, scans));
+    case VPT_UNIT_SURFACE_MIS: { // stage_surf<LAMBERT / FACET>: MISv2 = the stage's radiance contribution for unit throughput and cp = 1
+        ConstsF kk = cf; kk.sigma_t = (float)a[10]; kk.inv_cp = 1.0f; kk.q = 2.0f;
+        ListCtx c(PS, kk, a + 11, 8);
+        r.hid = (uint32_t)a[0]; r.o = ld3(a + 1); r.d = ld3(a + 7);
+        const bool facet = mats[r.hid].material != 0;
+        c.vertex(r, facet ? SQ_SURF_F : SQ_SURF_L);
+        if (facet) stage_surf<true>(c, true, r); else stage_surf<false>(c, true, r);
+        st3d(o, c.acc);
     } break;
-    case VPT_UNIT_BSDF_SAMPLE: {
-        const int oid = (int)a[0];
-        const F3 nrm = ld3(a + 1), wray = ld3(a + 4);
-        const Frame fr = make_frame(nrm);
-        const F3 wo_l = unit(to_local(fr, -wray));
-        F3 wi;
-        st3(o, bsdf_sample(mats[oid], fr, wo_l, (float)a[7], (float)a[8], wi));
-        st3(o + 3, wi);
+    case VPT_UNIT_BSDF_SAMPLE: { // stage_surf's scatter step: bdsf folded with its use (fs cos / pdf) and the new direction, for cp = 1
+        ConstsF kk = cf; kk.inv_cp = 1.0f; kk.q = 2.0f;
+        ListCtx c(PS, kk, a, 0);
+        const MatF &obj = mats[(int)a[0]];
+        r.hid = (uint32_t)a[0]; r.o = mk(obj.px, obj.py, obj.pz) + ld3(a + 1) * obj.r; r.d = ld3(a + 4);
+        c.set_slot(S_BSDF, (float)a[7]); c.set_slot(S_BSDF + 1, (float)a[8]);
+        if (obj.material != 0) stage_surf<true>(c, true, r); else stage_surf<false>(c, true, r);
+        st3(o, r.beta); st3(o + 3, r.d);
     } break;
-    case VPT_UNIT_RADIANCE: {
-        Path p; p.o = ld3(a); p.d = ld3(a + 3); p.beta = mk(1, 1, 1); p.L = mk(0, 0, 0); p.depth = 0;
-        Rng rng; rng.start((uint32_t)a[6], (uint32_t)a[7], lp.key0, lp.key1);
-        Tally tally{0u, 0u};
-        for (;;) {
-            rng.begin_bounce((uint32_t)p.depth);
-            if ((k.max_depth > 0 && p.depth >= k.max_depth) || rng.next_f32(S_RR) < k.q) break;
-            bool alive;
-            if (lp.method == 0) alive = vertex<0>(sc, mats, k, p, rng, tally);
-            else if (lp.method == 1) alive = vertex<1>(sc, mats, k, p, rng, tally);
-            else if (lp.method == 4) alive = vertex<4>(sc, mats, k, p, rng, tally);
-            else alive = vertex<2>(sc, mats, k, p, rng, tally);
-            if (!alive) break;
-            ++p.depth;
-        }
-        st3(o, p.L); o[3] = tally.events;
+    case VPT_UNIT_RADIANCE: { // a whole path on the Philox stream (pixel, sample) from a given ray: roulette of bounce 0, then the stages
+        ThreadCtx c(PS, cf, lp.key0, lp.key1);
+        r.o = ld3(a); r.d = ld3(a + 3); r.pixel = (uint32_t)a[6]; r.sample = (uint32_t)a[7];
+        if (roulette(c, true, r) == SQ_PRIMARY) trace_path_method(lp.method, c, r);
+        st3d(o, c.acc); o[3] = c.events;
     } break;
-    case VPT_UNIT_RADIANCE_LIST: {
-        Path p; p.o = ld3(a); p.d = ld3(a + 3); p.beta = mk(1, 1, 1); p.L = mk(0, 0, 0); p.depth = 0;
-        ListRng rng{a + 7, 0, min((int)a[6], 120)};
-        Tally tally{0u, 0u};
-        for (;;) {
-            if ((k.max_depth > 0 && p.depth >= k.max_depth) || rng.next_f32(S_RR) < k.q) break;
-            bool alive;
-            if (lp.method == 0) alive = vertex<0>(sc, mats, k, p, rng, tally);
-            else if (lp.method == 1) alive = vertex<1>(sc, mats, k, p, rng, tally);
-            else if (lp.method == 4) alive = vertex<4>(sc, mats, k, p, rng, tally);
-            else alive = vertex<2>(sc, mats, k, p, rng, tally);
-            if (!alive) break;
-            ++p.depth;
-        }
-        st3(o, p.L); o[3] = rng.overrun ? -1.0 : (double)rng.i;
+    case VPT_UNIT_RADIANCE_LIST: { // a whole path on an explicit list of uniforms in the reference's consumption order
+        ListCtx c(PS, cf, a + 7, min((int)a[6], 120));
+        r.o = ld3(a); r.d = ld3(a + 3);
+        if (roulette(c, true, r) == SQ_PRIMARY) trace_path_method(lp.method, c, r);
+        st3d(o, c.acc); o[3] = c.overrun ? -1.0 : (double)c.i;
     } break;
-    case VPT_UNIT_CAMERA_RAY: {
-        const CameraF cam = make_camera(cf);
-        st3(o, camera_dir(cam, (float)a[0], (float)a[1], (float)a[2], (float)a[3]));
+    case VPT_UNIT_CAMERA_RAY: { // stage_gen's camera ray for pixel (x, y) (y counted from the bottom, rt.cpp:773) and jitter (xi1, xi2)
+        const uint32_t pixel = (uint32_t)((lp.height - 1 - (int)a[1]) * lp.width + (int)a[0]);
+        st3(o, camera_dir(cf, pixel, lp.width, lp.height, (float)a[2], (float)a[3]));
     } break;
     case VPT_UNIT_RAYMARCH: {
-        double L[3]; unsigned n_steps;
-        ray_march3(PS, ld3(a), ld3(a + 3), a[6], (int)a[7], k.sigma_t, k.sigma_s, L, n_steps, scans);
+        double L[3]; unsigned n_steps, scans = 0;
+        ray_march3(PS, ld3(a), ld3(a + 3), a[6], (int)a[7], cf.sigma_t, cf.sigma_s, L, n_steps, scans);
         o[0] = L[0]; o[1] = L[1]; o[2] = L[2]; o[3] = n_steps;
     } break;
     default: break;

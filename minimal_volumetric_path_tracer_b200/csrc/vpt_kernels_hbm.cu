@@ -35,25 +35,26 @@ __global__ void __launch_bounds__(kHbmThreads) hbm_stage_kernel(const __grid_con
     stage_scene(S, sc, (int)threadIdx.x, (int)blockDim.x);
     if (threadIdx.x < 8) blk_cnt[threadIdx.x] = 0u;
     __syncthreads();
-    HbmCtx C(S, sc, cf, lp, H);
+    HbmCtx C(S, cf, lp, H);
     const unsigned lane = threadIdx.x & 31u;
     for (unsigned first = blockIdx.x * blockDim.x; first < n; first += per_pass) { // block-uniform trip count
         const unsigned i = first + threadIdx.x;
         const bool act = i < n;
         Rec r;
-        if (STAGE == HK_GEN) C.generate(act, H.cursor[1] + i, r);
+        int dest;
+        if (STAGE == HK_GEN) dest = C.generate(act, H.cursor[1] + i, r);
         else {
             if (act) r = hbm_load(H, STAGE, i);
-            else { r.o = mk(0, 0, 0); r.d = mk(0, 0, 1); r.beta = mk(0, 0, 0); r.L = mk(0, 0, 0); r.pixel = r.sample = r.depth = r.r1 = r.r2 = r.r3 = 0u; }
-            if (STAGE == SQ_PRIMARY) C.template primary<METHOD>(act, r);
-            else if (STAGE == SQ_MED_POINT) C.template med<true>(act, r);
-            else if (STAGE == SQ_MED_AREA) C.template med<false>(act, r);
-            else if (STAGE == SQ_SURF_P) C.surf_p(act, r);
-            else if (STAGE == SQ_SURF_L) C.template surf<false>(act, r);
-            else C.template surf<true>(act, r);
+            else { r.o = mk(0, 0, 0); r.d = mk(0, 0, 1); r.beta = mk(0, 0, 0); r.xi_dist = r.xi_decide = 0.5f; r.pixel = r.sample = r.depth = r.src = r.hid = r.aux = 0u; }
+            if (STAGE == SQ_PRIMARY) dest = stage_primary<METHOD>(C, act, r);
+            else if (STAGE == SQ_MED_POINT) dest = stage_med<true>(C, act, r);
+            else if (STAGE == SQ_MED_AREA) dest = stage_med<false>(C, act, r);
+            else if (STAGE == SQ_SURF_P) dest = stage_surf_p(C, act, r);
+            else if (STAGE == SQ_SURF_L) dest = stage_surf<false>(C, act, r);
+            else dest = stage_surf<true>(C, act, r);
+            if (dest == kDestFree) dest = -1; // the path ended: its record simply is not written anywhere
         }
         // ---- block-wide emit: offsets inside the block from shared-memory counters, one global atomic per destination and block ----
-        const int dest = C.dest;
         const unsigned grp = __match_any_sync(0xffffffffu, dest);
         unsigned local = 0;
         if (dest >= 0) {

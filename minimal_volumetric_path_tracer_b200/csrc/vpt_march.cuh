@@ -5,7 +5,7 @@
 // FP32 semantics as everywhere in this precision: r == 0 spheres are not ray-intersected, visibility = nothing hit before
 // distance * (1 - 1e-4).  The per-step terms are fp32, their sum is accumulated in double (3000 terms).
 #pragma once
-#include "vpt_smwave.cuh"
+#include "vpt_scan.cuh"
 
 namespace vpt {
 namespace f32 {

@@ -7,7 +7,7 @@
 // through a context type C that supplies the record's random numbers, the scene scan, the radiance sink and the counters:
 //   float4 C::rnd(const Rec &, uint32_t block)   uniforms of Philox block `block` of (pixel, sample, bounce = rec.depth)    (vpt_philox.cuh slot table)
 //   float4 C::jitter(const Rec &)                the pixel-jitter block (pseudo-bounce 0xffffffff)
-//   bool   C::scan(F3 o, F3 d, float &t, int &id)  nearest accepted hit (vpt_scan.cuh)
+//   bool   C::scan(F3 o, F3 d, float &t, int &id)  nearest accepted hit (vpt_scan.cuh); the stages count the scans of their active lanes
 //   void   C::add(const Rec &, F3 contribution)  radiance arriving at the record's pixel (rt.cpp:794: the sum over the path's vertices)
 //   void   C::last_step()                        called once per stage before its last block of work (the product kernel claims its next batch here)
 //   const SmScene &S;  const ConstsF &k;  unsigned events, scans;
@@ -58,6 +58,15 @@ __device__ __forceinline__ int roulette(C &c, bool act, Rec &r) {
     return alive ? SQ_PRIMARY : (act ? kDestFree : -1);
 }
 
+// camera ray of storage pixel `pixel` with jitter (j1, j2), rt.cpp:773,787 (storage row 0 is the top of the image)
+__device__ __forceinline__ F3 camera_dir(const ConstsF &k, uint32_t pixel, int width, int height, float j1, float j2) {
+    const int row = (int)(pixel / (unsigned)width), col = (int)pixel - row * width;
+    const float fx = (float)col, fy = (float)(height - 1 - row);
+    const float u = (fx + j1 - 0.5f) * k.inv_w - 0.5f, v = (fy + j2 - 0.5f) * k.inv_h - 0.5f;
+    return unit(mk(fmaf(k.cam_cx[0], u, fmaf(k.cam_cy[0], v, k.cam_d[0])), fmaf(k.cam_cx[1], u, fmaf(k.cam_cy[1], v, k.cam_d[1])),
+                   fmaf(k.cam_cx[2], u, fmaf(k.cam_cy[2], v, k.cam_d[2]))));
+}
+
 // ---- GEN: camera sample (pixel, sample) -> record at the camera, or nothing if the first roulette ends the path (rt.cpp:773-794) ---------
 template <class C>
 __device__ __forceinline__ bool stage_gen(C &c, bool mine, uint32_t pixel, uint32_t sample, int width, int height, Rec &r) {
@@ -68,11 +77,7 @@ __device__ __forceinline__ bool stage_gen(C &c, bool mine, uint32_t pixel, uint3
         alive = !(u.x < c.k.q);
         if (alive) {
             const float4 j = c.jitter(r);
-            const int row = (int)(pixel / (unsigned)width), col = (int)pixel - row * width;
-            const float fx = (float)col, fy = (float)(height - 1 - row); // rt.cpp:773: storage row 0 is the top of the image
-            const float uu = (fx + j.x - 0.5f) * c.k.inv_w - 0.5f, vv = (fy + j.y - 0.5f) * c.k.inv_h - 0.5f;
-            r.d = unit(mk(fmaf(c.k.cam_cx[0], uu, fmaf(c.k.cam_cy[0], vv, c.k.cam_d[0])), fmaf(c.k.cam_cx[1], uu, fmaf(c.k.cam_cy[1], vv, c.k.cam_d[1])),
-                          fmaf(c.k.cam_cx[2], uu, fmaf(c.k.cam_cy[2], vv, c.k.cam_d[2])))); // rt.cpp:787
+            r.d = camera_dir(c.k, pixel, width, height, j.x, j.y);
             r.o = mk(c.k.cam_o[0], c.k.cam_o[1], c.k.cam_o[2]);
             r.beta = mk(1.0f, 1.0f, 1.0f);
             r.src = (uint32_t)c.S.emitters[min((int)(u.y * c.k.n_emitters), c.S.n_emitters - 1)];
@@ -89,7 +94,7 @@ __device__ __forceinline__ int stage_primary(C &c, bool act, Rec &r) {
     const bool hit = c.scan(r.o, r.d, t, hid);
     int dest = -1;
     if (act) {
-        ++c.events;
+        ++c.events; ++c.scans;
         if (!hit) { t = kMaxFloat; hid = 0; } // :1287 (id stays 0)
         const MatF &sm = c.S.mats[r.src];
         bool surface; float dist, inv_pdf = 1.0f;
@@ -102,7 +107,7 @@ __device__ __forceinline__ int stage_primary(C &c, bool act, Rec &r) {
             const float Tr = transmit(c.k.sigma_t * t); // TrActual :1046 / psurf :1407 (0 on a miss)
             float D, dth, tl;
             dist = equiangular_sample(mk(sm.px, sm.py, sm.pz), r.o, r.d, t, r.xi_dist, D, dth, tl);
-            inv_pdf = dth * (tl * tl + D * D) / (D * (1.0f - Tr));
+            inv_pdf = dth * fmaf(tl, tl, D * D) / (D * (1.0f - Tr));
             surface = (METHOD == 1) ? (r.xi_decide <= Tr) : (r.xi_decide < Tr); // :1096 / :1426
         }
         const MatF &obj = c.S.mats[hid];
@@ -150,6 +155,7 @@ __device__ __forceinline__ int stage_med(C &c, bool act, Rec &r) {
     float t; int hid;
     const bool hit = c.scan(qo, qd, t, hid);
     if (act) {
+        ++c.scans;
         if (POINT) { if (!hit || t > lim) c.add(r, Cn); }
         else if (hit && hid == src) c.add(r, Cn * transmit(c.k.sigma_t * t));
     }
@@ -178,6 +184,7 @@ __device__ __forceinline__ int stage_surf_p(C &c, bool act, Rec &r) {
     const F3 Cn = had(had(mk(sm.lr, sm.lg, sm.lb), f), r.beta) * (dot(n_, wi) * transmit(c.k.sigma_t * dist) / d2 * c.k.n_emitters * c.k.inv_cp);
     float t; int hid;
     const bool hit = c.scan(light, lx * (-inv), t, hid);
+    c.scans += act ? 1u : 0u;
     if (act && (!hit || t > dist * (1.0f - 1e-4f))) c.add(r, Cn);
     return act ? (obj.material != 0 ? SQ_SURF_F : SQ_SURF_L) : -1;
 }
@@ -215,6 +222,7 @@ __device__ __forceinline__ int stage_surf(C &c, bool act, Rec &r) {
         const F3 wi = cone_sample(cx * inv_len, omc_max, xi1, xi2);
         float t; int hid;
         const bool hit = c.scan(o, wi, t, hid);
+        c.scans += act ? 1u : 0u;
         if (act && (hit ? hid : 0) == lid && !diel) { // id stays 0 on a miss, samplingFunctions.h:196
             const float cos_i = dot(n_, wi);
             F3 f = albedo * kInvPi;
@@ -245,6 +253,7 @@ __device__ __forceinline__ int stage_surf(C &c, bool act, Rec &r) {
         const F3 wi = unit(to_world(fr, wi_l));
         float t; int hid;
         const bool hit = c.scan(o, wi, t, hid);
+        c.scans += act ? 1u : 0u;
         if (act && hit && c.S.mats[hid].emits) {
             const MatF &em = c.S.mats[hid];
             const F3 cx = mk(em.px, em.py, em.pz) - o;

@@ -29,6 +29,28 @@ def test_ppm_bytes(vpt, tmp_path):
     assert text == want
 
 
+def test_ppm_is_byte_identical_to_a_file_written_by_the_reference_binary(vpt, tmp_path):
+    """`oracle/_ref/ref_rt 1` (the unmodified src/rt.cpp, rt.cpp:808-820) writes image.ppm; the 8-bit values it holds are mapped back to an HDR
+    frame that tonemaps to exactly those values, and vpt_write_ppm of that frame must reproduce the reference's file byte for byte:
+    header, separators, trailing blank, no newline after the header."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ref_rt")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_rt not built (reference tree absent)")
+    subprocess.run([exe, "1"], cwd=tmp_path, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=300,
+                   env=dict(os.environ, OMP_NUM_THREADS=str(min(os.cpu_count() or 1, 8))))
+    ref = (tmp_path / "image.ppm").read_bytes()
+    head, body = ref.split(b"\n", 3)[:3], ref.split(b"\n", 3)[3]
+    assert head == [b"P3", b"1024 768", b"255"] and b"\n" not in body and body.endswith(b" ")
+    v = np.array(body.split(), dtype=np.int64)
+    assert v.size == 1024 * 768 * 3 and v.min() >= 0 and v.max() <= 255 and len(set(v.tolist())) > 50   # a real image, not a constant
+    hdr = ((v / 255.0) ** 2.2).astype(np.float32).reshape(768, 1024, 3)      # toDisplayValue(hdr) == v (mathUtilities.h:34-45)
+    assert np.array_equal(vpt.tonemap(hdr).reshape(-1), v)
+    out = tmp_path / "ours.ppm"
+    vpt.write_ppm(hdr, str(out))
+    assert out.read_bytes() == ref
+
+
 def test_sample_shards_partition_the_range():
     from minimal_volumetric_path_tracer_b200 import distributed as d
     for spp in (1, 7, 64, 1024, 16384):

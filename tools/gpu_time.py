@@ -5,7 +5,7 @@ import minimal_volumetric_path_tracer_b200 as v
 if os.environ.get("VPT_LIB"):  # development only: time an experimental build of the library
     v.api.LIB_PATH = os.path.abspath(os.environ["VPT_LIB"])
 spp = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-kernels = {"mega": v.KERNEL_MEGA, "scan": v.KERNEL_MEGA_SCAN, "wave": v.KERNEL_WAVEFRONT, "smwave": v.KERNEL_WAVEFRONT_SM, "hbm": v.KERNEL_WAVEFRONT_HBM}
+kernels = {"mega": v.KERNEL_MEGA, "smwave": v.KERNEL_WAVEFRONT_SM, "hbm": v.KERNEL_WAVEFRONT_HBM}
 names = sys.argv[2].split(",") if len(sys.argv) > 2 else list(kernels)
 for kern, name in ((kernels[n], n) for n in names):
     for method in (0, 1, 2, 4):
