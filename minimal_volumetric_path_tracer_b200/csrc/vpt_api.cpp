@@ -86,7 +86,7 @@ int validate_params(const vpt_params *p, bool need_image) {
     if (p->precision == VPT_PRECISION_FP32 && p->quirks != 0) return VPT_ERR_UNSUPPORTED; // rounding-decided behaviours exist in FP64 only
     if (p->kernel < VPT_KERNEL_AUTO || p->kernel > VPT_KERNEL_WAVEFRONT_HBM) return VPT_ERR_INVALID_ARGUMENT;
     if (p->kernel == VPT_KERNEL_WAVEFRONT || p->kernel == VPT_KERNEL_MEGA_SCAN) return VPT_ERR_UNSUPPORTED; // superseded variants, no longer built (profiles/r1_summary.md has their measurements)
-    if ((p->kernel == VPT_KERNEL_WAVEFRONT_SM || p->kernel == VPT_KERNEL_WAVEFRONT_HBM) && p->precision != VPT_PRECISION_FP32) return VPT_ERR_UNSUPPORTED;
+    if (p->kernel == VPT_KERNEL_WAVEFRONT_HBM && p->precision != VPT_PRECISION_FP32) return VPT_ERR_UNSUPPORTED; // the multi-kernel wavefront is FP32 only
     return VPT_OK;
 }
 
@@ -243,7 +243,7 @@ int enqueue_render(const vpt_params *p, const vpt_sphere *spheres, int n_spheres
     } else {
         SceneD sc;
         build_scene_f64(spheres, n_spheres, sc);
-        rc = launch_render_f64(sc, lp, hdr_dev, counters_dev, stream, blocks);
+        rc = launch_render_f64(sc, lp, hdr_dev, counters_dev, stream, blocks, p->kernel);
     }
     if (rc != 0) return cuda_fail((cudaError_t)rc, "render kernel launch");
     if (launches) ++*launches;

@@ -420,10 +420,22 @@ __device__ __forceinline__ bool mis_distance(D3 light, D3 o, D3 d, double t, dou
 
 struct Path { D3 o, d, beta, L; int depth; };
 
-// one vertex after a successful roulette draw; vptShadeMethods.h:1263-1340 / :1014-1149 / :1345-1481 in throughput form
+// One path vertex after a successful roulette draw (vptShadeMethods.h:1263-1340 / :1014-1149 / :1345-1481 in throughput form), in three
+// PARTS -- the cut points of the wavefront kernel (vpt_smwave_f64.cuh), which re-queues a path between them; vertex() below runs them
+// back to back for the one-thread-per-pixel kernel and the unit kernels.  Same statements, same order, same roundings either way.
+enum : int { V_END = 0, V_SURFACE = 1, V_MEDIUM = 2 };
+struct VertexPlan { // what the first part hands to the second
+    int id, source;        // hit object, picked source
+    D3 x;                  // the vertex: surface point xs or medium point xt
+    double T, pdf_medium;  // medium vertex (equi-angular methods): transmittance origin -> xt, distance pdf
+};
+
+// part 1: scene scan, light pick, distance sampling, surface-or-medium decision.  Lc: radiance this part contributes (a directly seen
+// emitter at depth 0, :1308-1313), before it the caller's p.L is untouched.
 template <class RngT>
-__device__ __forceinline__ bool vertex(const Ctx &c, Path &p, RngT &rng, Tally &tl) {
+__device__ __forceinline__ int vertex_primary(const Ctx &c, const Path &p, RngT &rng, Tally &tl, VertexPlan &vp, D3 &Lc) {
     ++tl.events;
+    Lc = mk(0, 0, 0);
     double t;
     int id = 0;
     const bool hit = scan(c, p.o, p.d, t, id, tl);
@@ -431,9 +443,7 @@ __device__ __forceinline__ bool vertex(const Ctx &c, Path &p, RngT &rng, Tally &
     const D3 xs = p.o + p.d * t;
     double Tr = 0;
     if (c.method == 1 && hit) Tr = transmittance(p.o, xs, c.sigma_t);
-    const D3 n = unit(xs - pos(c.s[id]));
-    if (c.n_emitters == 0) return false;
-    const double prob_source = 1.0 / c.n_emitters;
+    if (c.n_emitters == 0) return V_END;
     const int source = c.emitters[static_cast<int>(rng.next_f64(S_SRC) * c.n_emitters)];
 
     bool surface;
@@ -459,42 +469,76 @@ __device__ __forceinline__ bool vertex(const Ctx &c, Path &p, RngT &rng, Tally &
         const double xs_ = rng.next_f64(S_DECIDE);
         surface = (c.method == 1) ? (xs_ <= Tr) : (xs_ < Tr);
     }
-
+    vp.id = id; vp.source = source; vp.pdf_medium = pdf_medium; vp.T = 0;
     if (surface) {
         const SphereD &obj = c.s[id];
         if (obj.emits) {
-            if (p.depth == 0) p.L = had(rad(obj), p.beta);
-            return false;
+            if (p.depth == 0) Lc = had(rad(obj), p.beta);
+            return V_END;
         }
-        const SphereD &src = c.s[source];
-        const double Trs = transmittance(xs, pos(src), c.sigma_t);
-        const D3 Ld_point = point_light_direct(c, obj, xs, n, p.d, rad(src), pos(src), obj.alpha, tl) * Trs * (1 / prob_source);
-        const D3 Ld = surface_direct_mis(c, obj, xs, n, p.d, obj.alpha, rng, tl);
-        D3 wi;
-        double pdf;
-        const D3 fs = bsdf_sample(obj, wi, p.d, n, pdf, rng);
-        wi = unit(wi);
-        const double cosine = dot(n, wi);
-        p.L = p.L + had(Ld_point + Ld, p.beta) * (1 / c.cp);
-        p.beta = had(p.beta, fs) * (1 / c.cp) * cosine * (1 / pdf);
-        p.o = xs; p.d = wi;
-    } else {
-        const D3 xt = p.o + p.d * dist;
-        if (c.method == 0) {
-            const D3 Ld = medium_direct(c, xt, source, prob_source, false, 0.0, rng, tl);
-            const double xi1 = rng.next_f64(S_PHASE), xi2 = rng.next_f64(S_PHASE + 1);
-            p.L = p.L + had(Ld, p.beta) * (c.sigma_s / c.sigma_t) * (1 / c.cp);
-            p.beta = p.beta * (c.sigma_s / c.sigma_t) * (1 / c.cp);
-            p.o = xt; p.d = phase_sample(xi1, xi2);
-        } else {
-            const double T = transmittance(p.o, xt, c.sigma_t);
-            const D3 Ld = medium_direct(c, xt, source, prob_source, true, T, rng, tl);
-            const double xi1 = rng.next_f64(S_PHASE), xi2 = rng.next_f64(S_PHASE + 1);
-            p.L = p.L + had(Ld * (1 / pdf_medium) * (1 / c.cp), p.beta);
-            p.beta = p.beta * c.sigma_s * T * (1 / c.cp) * (1 / pdf_medium);
-            p.o = xt; p.d = phase_sample(xi1, xi2);
-        }
+        vp.x = xs;
+        return V_SURFACE;
     }
+    vp.x = p.o + p.d * dist;
+    if (c.method != 0) vp.T = transmittance(p.o, vp.x, c.sigma_t);
+    return V_MEDIUM;
+}
+
+// part 2, surface vertex: pLight + MISv2 + bdsf (:1316-1327).  Lc: the vertex's direct light; p becomes the scattered ray.
+template <class RngT>
+__device__ __forceinline__ void vertex_surface(const Ctx &c, Path &p, const VertexPlan &vp, RngT &rng, Tally &tl, D3 &Lc) {
+    const SphereD &obj = c.s[vp.id];
+    const D3 xs = vp.x;
+    const D3 n = unit(xs - pos(obj));
+    const double prob_source = 1.0 / c.n_emitters;
+    const SphereD &src = c.s[vp.source];
+    const double Trs = transmittance(xs, pos(src), c.sigma_t);
+    const D3 Ld_point = point_light_direct(c, obj, xs, n, p.d, rad(src), pos(src), obj.alpha, tl) * Trs * (1 / prob_source);
+    const D3 Ld = surface_direct_mis(c, obj, xs, n, p.d, obj.alpha, rng, tl);
+    D3 wi;
+    double pdf;
+    const D3 fs = bsdf_sample(obj, wi, p.d, n, pdf, rng);
+    wi = unit(wi);
+    const double cosine = dot(n, wi);
+    Lc = had(Ld_point + Ld, p.beta) * (1 / c.cp);
+    p.beta = had(p.beta, fs) * (1 / c.cp) * cosine * (1 / pdf);
+    p.o = xs; p.d = wi;
+}
+
+// part 2, medium vertex: (free)SingleScattering + isotropicPhaseSample (:1330-1337 / :1120-1135)
+template <class RngT>
+__device__ __forceinline__ void vertex_medium(const Ctx &c, Path &p, const VertexPlan &vp, RngT &rng, Tally &tl, D3 &Lc) {
+    const D3 xt = vp.x;
+    const double prob_source = 1.0 / c.n_emitters;
+    if (c.method == 0) {
+        const D3 Ld = medium_direct(c, xt, vp.source, prob_source, false, 0.0, rng, tl);
+        const double xi1 = rng.next_f64(S_PHASE), xi2 = rng.next_f64(S_PHASE + 1);
+        Lc = had(Ld, p.beta) * (c.sigma_s / c.sigma_t) * (1 / c.cp);
+        p.beta = p.beta * (c.sigma_s / c.sigma_t) * (1 / c.cp);
+        p.o = xt; p.d = phase_sample(xi1, xi2);
+    } else {
+        const double T = vp.T;
+        const D3 Ld = medium_direct(c, xt, vp.source, prob_source, true, T, rng, tl);
+        const double xi1 = rng.next_f64(S_PHASE), xi2 = rng.next_f64(S_PHASE + 1);
+        Lc = had(Ld * (1 / vp.pdf_medium) * (1 / c.cp), p.beta);
+        p.beta = p.beta * c.sigma_s * T * (1 / c.cp) * (1 / vp.pdf_medium);
+        p.o = xt; p.d = phase_sample(xi1, xi2);
+    }
+}
+
+// the whole vertex; returns false when the path ends here
+template <class RngT>
+__device__ __forceinline__ bool vertex(const Ctx &c, Path &p, RngT &rng, Tally &tl) {
+    VertexPlan vp;
+    D3 Lc;
+    const int kind = vertex_primary(c, p, rng, tl, vp, Lc);
+    if (kind == V_END) {
+        if (Lc.x != 0 || Lc.y != 0 || Lc.z != 0) p.L = Lc; // (a directly seen emitter counts at depth 0 only: nothing collected before)
+        return false;
+    }
+    if (kind == V_SURFACE) vertex_surface(c, p, vp, rng, tl, Lc);
+    else vertex_medium(c, p, vp, rng, tl, Lc);
+    p.L = p.L + Lc;
     return true;
 }
 

@@ -11,6 +11,10 @@ constexpr int kMaxEmitters = VPT_MAX_EMITTERS;
 constexpr int kThreadsPerBlock = 128; // one pixel tile = kTile consecutive storage-order pixels
 constexpr int kTile = 128;
 
+// ---- stages of a path vertex (the queues of the wavefront kernels) -----------------------------------------------
+enum : int { SQ_PRIMARY = 0, SQ_MED_POINT, SQ_MED_AREA, SQ_SURF_P, SQ_SURF_L, SQ_SURF_F, SQ_COUNT };
+constexpr int kDestFree = SQ_COUNT; // the path ended: its record is free
+
 // ---- fp32 scene ----------------------------------------------------------------------------------------------
 // Ray/sphere record for the scan loop (lives in kernel-parameter constant memory; uniform index -> broadcast).
 // Re-anchored form (DESIGN.md "fp32 geometry"): for a sphere with centre p and radius r the
@@ -103,7 +107,7 @@ int scratch_alloc_(int device, void **ptr, size_t bytes, void *stream);
 void scratch_trim_(int device, size_t keep_bytes); // give the pool's unused memory above keep_bytes back to the driver
 int launch_march_f32(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks);
 int launch_render_f32(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks, int kernel);
-int launch_render_f64(const SceneD &scene, const LaunchParams &lp, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks);
+int launch_render_f64(const SceneD &scene, const LaunchParams &lp, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks, int kernel);
 int launch_unit_f32(int fn, const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, int n, const double *in_dev, int in_stride, double *out_dev, int out_stride, void *stream);
 int launch_unit_f64(int fn, const SceneD &scene, const LaunchParams &lp, int n, const double *in_dev, int in_stride, double *out_dev, int out_stride, void *stream);
 int launch_philox(int n, const uint32_t *ctr_dev, const uint32_t *key_dev, uint32_t *out_dev, void *stream);

@@ -70,25 +70,15 @@ __global__ void __launch_bounds__(kSmThreads, 1) render_f32_smwave_kernel(const 
     SmShared &M = sm_shared();
     const int tid = (int)threadIdx.x;
     stage_scene(M.scene, sc, tid, kSmThreads);
-    for (int i = tid; i < kSmPool; i += kSmThreads) { M.freelist[i] = (uint16_t)i; M.meta[i] = 0u; }
+    for (int i = tid; i < kSmPool; i += kSmThreads) M.meta[i] = 0u;
     if (tid < 32) { // record 0 backs the idle lanes of partial batches before it is first allocated: give it in-range values
         M.ox[0] = M.oy[0] = M.oz[0] = 0.0f; M.dx[0] = M.dy[0] = 0.0f; M.dz[0] = 1.0f; M.br[0] = M.bg[0] = M.bb[0] = 0.0f;
         M.sample[0] = 0u; M.xd[0] = M.xs[0] = 0.5f;
     }
-    for (int i = tid; i < 2 * kSmMaxItemPixels * 3; i += kSmThreads) (&M.acc[0][0][0])[i] = 0ull;
-    if (tid == 0) {
-        for (int q = 0; q < SQ_COUNT; ++q) { M.q_tail[q] = 0u; M.q_end[q] = 0u; }
-        M.free_head = 0u; M.free_tail = (unsigned)kSmPool;
-        for (int b = 0; b < 2; ++b) {
-            const int item = (int)blockIdx.x + b * (int)gridDim.x;
-            M.t_item[b] = item < n_items ? item : -1; M.t_cursor[b] = 0u; M.t_done[b] = 0u;
-        }
-        M.next_item = (int)blockIdx.x + 2 * (int)gridDim.x;
-        M.gen_slot = -1; M.tail_limit = 0u;
-    }
-    __syncthreads();
     SmWave<METHOD> wf(M, cf, lp, log_p, n_owned_tiles, zero);
-    wf.run(hdr, n_items);
+    wf.init(n_items);
+    __syncthreads();
+    wf.run(hdr, n_items, kSmFixInv);
     if (!counters) return;
     unsigned long long ev = wf.events, scn = wf.scans, nf = wf.nonfinite, np = wf.paths;
     for (int off = 16; off > 0; off >>= 1) {

@@ -3,6 +3,7 @@
 // megakernel (vpt_kernels_f32.cu); the scene lives in shared memory as the reference's own FP64 sphere records.
 #include <cuda_runtime.h>
 #include "vpt_f64.cuh"
+#include "vpt_smwave_f64.cuh"
 
 namespace vpt {
 
@@ -101,8 +102,54 @@ __global__ void __launch_bounds__(kThreadsPerBlock) render_f64_kernel(const __gr
     atomicAdd(&counters->paths, (unsigned long long)(lp.sample_end - lp.sample_begin));
 }
 
-int launch_render_f64(const SceneD &scene, const LaunchParams &lp, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks) {
-    render_f64_kernel<<<n_blocks, kThreadsPerBlock, 0, (cudaStream_t)stream>>>(scene, lp, hdr_dev, counters_dev);
+// ---- SM-wide wavefront, FP64 reference mode (vpt_smwave_f64.cuh) ------------------------------------------------------------------------
+extern __shared__ __align__(16) unsigned char smwave_f64_smem[];
+__global__ void __launch_bounds__(kSmdThreads, 1) render_f64_smwave_kernel(const __grid_constant__ SceneD sc, const __grid_constant__ LaunchParams lp,
+                                                                            float *__restrict__ hdr, Counters *__restrict__ counters,
+                                                                            int log_p, int n_owned_tiles, int n_items, int zero) {
+    SmSharedD &M = *reinterpret_cast<SmSharedD *>(smwave_f64_smem);
+    const int tid = (int)threadIdx.x;
+    for (int i = tid; i < kSmdPool; i += kSmdThreads) M.meta[i] = 0u;
+    if (tid == 0) { M.ox[0] = M.oy[0] = M.oz[0] = 0.0; M.dx[0] = M.dy[0] = 0.0; M.dz[0] = 1.0; M.br[0] = M.bg[0] = M.bb[0] = 0.0; M.sample[0] = 0u; }
+    stage_scene(sc, M.spheres); // (ends with __syncthreads)
+    const Ctx c = make_ctx(sc, M.spheres, lp);
+    SmWaveD wf(M, c, lp, log_p, n_owned_tiles, zero);
+    wf.init(n_items);
+    __syncthreads();
+    wf.run(hdr, n_items, kSmdFixInv);
+    if (!counters) return;
+    unsigned long long ev = wf.tally.events, scn = wf.tally.scans, nf = wf.nonfinite, np = wf.paths;
+    for (int off = 16; off > 0; off >>= 1) {
+        ev += __shfl_down_sync(0xffffffffu, ev, off); scn += __shfl_down_sync(0xffffffffu, scn, off);
+        nf += __shfl_down_sync(0xffffffffu, nf, off); np += __shfl_down_sync(0xffffffffu, np, off);
+    }
+    if ((tid & 31) == 0) {
+        atomicAdd(&counters->events, ev); atomicAdd(&counters->scans, scn); atomicAdd(&counters->paths, np);
+        if (nf) atomicAdd(&counters->nonfinite, nf);
+#ifdef VPT_SMWAVE_PROFILE
+        for (int i = 0; i < 24; ++i) if (wf.prof[i]) atomicAdd(&counters->dbg[i], wf.prof[i]);
+#endif
+    }
+}
+
+// kernel: VPT_KERNEL_MEGA = one thread per pixel (also the ray marcher's kernel), anything else = the SM-wide wavefront
+int launch_render_f64(const SceneD &scene, const LaunchParams &lp, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks, int kernel) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (kernel == VPT_KERNEL_MEGA || lp.method == VPT_METHOD_RAYMARCH) {
+        render_f64_kernel<<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, hdr_dev, counters_dev);
+        return (int)cudaGetLastError();
+    }
+    int dev = 0, n_sm = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
+    if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(render_f64_smwave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmSharedD))) != cudaSuccess) return (int)e;
+    // work item = 256 pixels when that still leaves every SM at least 8 items, else one 128-pixel tile (as the FP32 pipeline)
+    const int log_p = (n_blocks / 2 >= 8 * n_sm) ? 8 : 7;
+    const int tiles_per_item = 1 << (log_p - 7);
+    const int n_items = (n_blocks + tiles_per_item - 1) / tiles_per_item;
+    const int grid = n_items < n_sm ? n_items : n_sm;
+    render_f64_smwave_kernel<<<grid, kSmdThreads, sizeof(SmSharedD), st>>>(scene, lp, hdr_dev, counters_dev, log_p, n_blocks, n_items, 0);
     return (int)cudaGetLastError();
 }
 

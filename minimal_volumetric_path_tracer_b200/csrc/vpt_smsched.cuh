@@ -1,0 +1,362 @@
+// vpt_smsched.cuh -- the SM-wide wavefront SCHEDULER: one persistent CTA per SM, a pool of path records in shared memory, rounds of
+// 32-record stage batches claimed by warps.  Precision-agnostic: the FP32 product pipeline (vpt_smwave.cuh) and the FP64 reference-mode
+// pipeline (vpt_smwave_f64.cuh) plug their record layout and their stage functions into it (CRTP).
+//
+// Why (profiles/r1_summary.md): a per-warp wavefront fixed SIMT efficiency (28 of 32 lanes active) but used only 40 % of the issue slots --
+// 42 % of all stall samples were `no_inst`: sixteen warps per SM, each in a different stage of a 62 KB kernel, thrash the 32 KB L1.5 /
+// 6 KB L0 instruction caches.  Here the warps of an SM share ONE pool of path records and move through the stages together:
+//   * one CTA per SM, grid = number of SMs (persistent); work items = groups of pixel tiles x all samples, handed out statically
+//     (item j -> CTA j % gridDim.x), two items in flight per CTA so that a draining item overlaps the next one;
+//   * POOL path records in shared memory (layout: the pipeline's), one index queue (ring) per stage, one ring of free records.  A record
+//     carries NO radiance: every vertex's direct light goes straight into the pixel's fixed-point sum;
+//   * work proceeds in ROUNDS: at a barrier warp 0 snapshots every queue's tail (one load of the 20 control words, then shuffles) into a
+//     table of 32-record batches ordered longest stage first; every warp claims batches with ONE shared-memory atomic each, runs them
+//     and routes the survivors to the next stage's ring (match.any groups the lanes by destination: one atomic per group); what is
+//     pushed during a round is consumed in the next one.  Only full batches are handed out while samples remain.  A warp that finds
+//     the table used up generates new camera samples into the free records instead of idling at the barrier (tail fill).  The rank order
+//     also keeps the warps inside two or three stages at a time -- a barrier-free variant lost 40 % to instruction-cache misses;
+//   * queues are split by what diverges: medium vertex with a point / an area source, surface vertex needing the pLight shadow ray,
+//     Lambert / microfacet surface vertex.
+// Per-pixel sums are 64-bit fixed-point accumulators in shared memory, built from native 32-bit atomics: integer adds are order
+// independent, so images are bit-reproducible although the order in which paths finish is data dependent.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include "vpt_internal.h"
+
+namespace vpt {
+
+constexpr int kSmMaxItemPixels = 256; // pixels per work item (power of two multiple of kTile)
+// Claim order of a round's batches (one nibble per rank, SQ_COUNT = generation), longest stage first so that a round ends evenly:
+// SURF_F, SURF_L, PRIMARY, MED_AREA, MED_POINT, SURF_P, generation
+constexpr unsigned kRankStage = 0x6312045u;
+
+// meta word of a record: pixel-in-item (bits 0-8) | item slot (bit 9) | picked source (10-14) | hit object (15-19) | depth (20-31)
+static_assert(kMaxSpheres <= 32 && VPT_MAX_DEPTH <= 4095 && kSmMaxItemPixels <= 512, "meta word layout");
+__device__ __forceinline__ uint32_t meta_pack(uint32_t aux, uint32_t src, uint32_t hid, uint32_t depth) { return (aux & 0x3ffu) | (src << 10) | (hid << 15) | (depth << 20); }
+
+// queues, pixel sums and control words of one CTA (the pipeline's shared-memory struct holds one, next to its records and its scene)
+template <int POOL>
+struct SmCtl {
+    static_assert(POOL % 32 == 0 && POOL <= 65536, "queues hold 16-bit record indices, batches are 32 records");
+    uint16_t queue[SQ_COUNT][POOL];
+    uint16_t freelist[POOL];
+    unsigned long long acc[2][kSmMaxItemPixels][3];
+    // this round's batch table by rank (kRankStage): batch k belongs to the last rank with rb_first[rank] <= k and covers entries
+    // [rb_begin + 32 j, min(rb_end, +32)), j = k - rb_first
+    __align__(16) unsigned rb_first[8]; // [7] = number of batches of the round
+    unsigned rb_begin[8], rb_end[8];
+    unsigned round_claim;      // next unclaimed batch of the round: one atomicAdd per batch
+    unsigned tail_limit;       // camera-sample cursor up to which warps out of batches may generate in this round (tail fill)
+    // the 20 words the round plan reads, contiguous: warp 0 fetches them with ONE load (lane i reads word i, see plan_round)
+    __align__(16) unsigned q_tail[SQ_COUNT]; // [0..5]   push counters
+    unsigned q_end[SQ_COUNT];                // [6..11]  entries below it have been handed out
+    unsigned free_head, free_tail;           // [12,13]  the free-record ring: allocate at the head (only below the round's snapshot), release at the tail
+    int t_item[2];                           // [14,15]  work item of the slot, -1: slot idle
+    unsigned t_cursor[2], t_done[2];         // [16..19] camera samples generated / paths finished
+    unsigned ctl_pad[12];
+    int gen_slot, flush_slot, exit_flag;
+#ifdef VPT_SMWAVE_PROFILE
+    long long dbg_arrive[32];
+#endif
+    int next_item;
+};
+
+// shared-memory atomic add issued by ONE lane (the callers aggregate over the warp themselves): plain ATOMS.ADD, without the
+// compiler's own warp-aggregation wrapper around atomicAdd
+// `lane_zero` = laneid * (a kernel argument that is always 0): ptxas wraps an atomic on a provably warp-uniform address in its own
+// leader election (VOTEU / FLO / POPC / S2R / SHFL, ~13 instructions per site, 7 % of all executed instructions in the first
+// profile); the callers have already elected lane 0, so the address is made formally lane dependent.
+__device__ __forceinline__ unsigned smem_add(unsigned *p, unsigned v, unsigned lane_zero = 0u) {
+    unsigned old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(p) + lane_zero), "r"(v));
+    return old;
+}
+__device__ __forceinline__ void smem_red(unsigned *p, unsigned v, unsigned lane_zero = 0u) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p) + lane_zero), "r"(v));
+}
+
+// optional in-kernel timing (-DVPT_SMWAVE_PROFILE): per-warp cycle sums, added to Counters::dbg at the end
+//   dbg[0..7]  cycles inside batches of stage q (SQ_* order, 6 = generation, 7 = tail-fill generation)     dbg[8..15]  batches of stage q
+//   dbg[16] cycles waiting at barrier (A)   dbg[17] cycles from (A) to (B) (planning)   dbg[18] cycles in the claim loop outside batches
+//   dbg[19] total cycles of all warps   dbg[20] rounds (per CTA, summed)   dbg[21] cycles flushing
+#ifdef VPT_SMWAVE_PROFILE
+#define SMW_T(var) const long long var = clock64()
+#define SMW_ADD(i, v) prof[i] += (unsigned long long)(v)
+#else
+#define SMW_T(var)
+#define SMW_ADD(i, v)
+#endif
+
+// The pipeline D derives from SmSched<D, POOL, THREADS> and provides
+//   template <int STAGE> void run_stage(int slot)     one lane's record of a batch of stage STAGE (slot < 0: idle lane); loads the record, runs the
+//                                                     stage, stores what changed, calls route() / count_done() -- every lane of the warp must call both
+//   void run_gen(int item_slot, unsigned g0, int n)   n <= 32 new camera samples of the item in slot item_slot, lane i takes sample index g0 + i
+template <class D, int POOL, int THREADS>
+struct SmSched {
+    SmCtl<POOL> &Q;
+    const LaunchParams &lp;
+    const int tid, lane;
+    const unsigned lz; // lane * 0, opaque to the compiler (see smem_add)
+    const int log_p, item_pixels, n_owned_tiles;
+    unsigned next_raw = 0; // lane 0: the next batch of the round, claimed while the tail of the current one is still running (last_step)
+#ifdef VPT_SMWAVE_PROFILE
+    unsigned long long prof[24] = {};
+#endif
+    static constexpr bool kPow2 = (POOL & (POOL - 1)) == 0;
+    // ring counters only ever grow; once a queue's `handed out` mark passes this multiple of the pool size, both marks are pulled back by it
+    // (in the plan, single-threaded between two barriers), so that `counter % POOL` stays exact on 32-bit wrap-around
+    static constexpr unsigned kRebase = (unsigned)POOL * (0x40000000u / (unsigned)POOL);
+    static __device__ __forceinline__ unsigned ring_index(unsigned counter) { return kPow2 ? (counter & (unsigned)(POOL - 1)) : (counter % (unsigned)POOL); }
+
+    __device__ SmSched(SmCtl<POOL> &Q_, const LaunchParams &lp_, int log_p_, int n_owned_, int zero)
+        : Q(Q_), lp(lp_), tid((int)threadIdx.x), lane((int)threadIdx.x & 31), lz((threadIdx.x & 31u) * (unsigned)zero), log_p(log_p_),
+          item_pixels(1 << log_p_), n_owned_tiles(n_owned_) {}
+    __device__ __forceinline__ D &self() { return *static_cast<D *>(this); }
+
+    // cooperative initialisation by the whole block (then __syncthreads)
+    __device__ __forceinline__ void init(int n_items) {
+        for (int i = tid; i < POOL; i += THREADS) Q.freelist[i] = (uint16_t)i;
+        for (int i = tid; i < 2 * kSmMaxItemPixels * 3; i += THREADS) (&Q.acc[0][0][0])[i] = 0ull;
+        if (tid == 0) {
+            for (int q = 0; q < SQ_COUNT; ++q) { Q.q_tail[q] = 0u; Q.q_end[q] = 0u; }
+            Q.free_head = 0u; Q.free_tail = (unsigned)POOL;
+            for (int b = 0; b < 2; ++b) {
+                const int item = (int)blockIdx.x + b * (int)gridDim.x;
+                Q.t_item[b] = item < n_items ? item : -1; Q.t_cursor[b] = 0u; Q.t_done[b] = 0u;
+            }
+            Q.next_item = (int)blockIdx.x + 2 * (int)gridDim.x;
+            Q.gen_slot = -1; Q.tail_limit = 0u;
+        }
+    }
+
+    // The claim for the NEXT batch is issued a few hundred cycles before the current one ends (at the start of its last step: the roulette's
+    // Philox block or the final routing), so that the atomic's round trip is over when the claim loop needs it; early enough to hide the
+    // latency, late enough not to commit a warp to work while others idle (claiming at the START of a batch measured 15 % slower).
+    __device__ __forceinline__ void last_step() { if (lane == 0) next_raw = smem_add(&Q.round_claim, 1u, lz); }
+
+    // 64-bit two's-complement add from native 32-bit shared-memory atomics (a 64-bit atomicAdd on shared memory is a CAS loop):
+    // low word first, its carry goes into the high word; the sum modulo 2^64 does not depend on the order of the adds
+    static __device__ __forceinline__ void add_fixed(unsigned long long *acc, long long v) {
+        unsigned *w = reinterpret_cast<unsigned *>(acc);
+        const unsigned lo = (unsigned)v;
+        unsigned hi = (unsigned)((unsigned long long)v >> 32);
+        const unsigned old = smem_add(w, lo);
+        hi += (old + lo < old) ? 1u : 0u;
+        if (hi) smem_red(w + 1, hi);
+    }
+    // the fixed-point sums of the pixel a record belongs to (meta: pixel-in-item, item slot)
+    __device__ __forceinline__ unsigned long long *pixel_acc(uint32_t meta) { return Q.acc[(meta >> 9) & 1u][meta & 0x1ffu]; }
+
+    // ---- work items: item j = owned tiles [j * K, (j + 1) * K), K = item_pixels / kTile -----------------------------------------
+    // (32-bit arithmetic: n_pixels is an int32, so tile and pixel indices fit; -1 = outside the image / not this rank's tile)
+    __device__ __forceinline__ int item_pixel(int item, int pl) const {
+        const unsigned owned = ((unsigned)item << (log_p - 7)) + ((unsigned)pl >> 7);
+        if (owned >= (unsigned)n_owned_tiles) return -1;
+        const unsigned pixel = (owned * (unsigned)lp.tile_count + (unsigned)lp.tile_rank) * (unsigned)kTile + ((unsigned)pl & (unsigned)(kTile - 1));
+        return pixel < (unsigned)lp.n_pixels ? (int)pixel : -1;
+    }
+    __device__ __forceinline__ uint32_t pixel_of(uint32_t meta) const { return (uint32_t)item_pixel(Q.t_item[(meta >> 9) & 1u], (int)(meta & 0x1ffu)); }
+
+    // ---- queue / pool primitives (warp-aggregated shared-memory atomics) ------------------------------------------------------------
+    // Route every lane's record in ONE step: dest = a stage queue (SQ_*), kDestFree (the record goes back to the free ring) or -1 (nothing).
+    // Lanes with the same destination find each other with match.any; the lowest lane of each group reserves the group's entries
+    // with one atomic (all group leaders in the same instruction), the others take their rank behind it.
+    __device__ __forceinline__ void route(int dest, int slot) {
+        const unsigned grp = __match_any_sync(0xffffffffu, dest);
+        if (dest < 0) return;
+        const int leader = __ffs(grp) - 1;
+        unsigned base = 0;
+        // counters: q_tail[0..5] are words 0..5 of the control block, free_tail is word 13; rings: queue[0..5] and, right behind them, freelist
+        if (lane == leader) base = smem_add(&Q.q_tail[0] + (dest == kDestFree ? 13 : dest), (unsigned)__popc(grp), lz);
+        base = __shfl_sync(grp, base, leader);
+        (&Q.queue[0][0])[dest * POOL + (int)ring_index(base + __popc(grp & ((1u << lane) - 1u)))] = (uint16_t)slot;
+    }
+    __device__ __forceinline__ int alloc(bool flag) { // the round's snapshot guarantees enough free records below free_tail
+        const unsigned m = __ballot_sync(0xffffffffu, flag);
+        if (m == 0u) return -1;
+        unsigned base = 0;
+        if (lane == 0) base = smem_add(&Q.free_head, (unsigned)__popc(m), lz);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        return flag ? (int)Q.freelist[ring_index(base + __popc(m & ((1u << lane) - 1u)))] : -1;
+    }
+    __device__ __forceinline__ void count_done(bool ended, uint32_t meta) {
+        const unsigned m0 = __ballot_sync(0xffffffffu, ended && ((meta >> 9) & 1u) == 0u);
+        const unsigned m1 = __ballot_sync(0xffffffffu, ended && ((meta >> 9) & 1u) == 1u);
+        if (lane == 0) {
+            if (m0) smem_red(&Q.t_done[0], (unsigned)__popc(m0), lz);
+            if (m1) smem_red(&Q.t_done[1], (unsigned)__popc(m1), lz);
+        }
+    }
+    // generation bookkeeping: samples of pixels outside the image and paths killed by the first roulette are finished already
+    __device__ __forceinline__ void count_stillborn(int item_slot, bool mine, bool alive) {
+        const unsigned m = __ballot_sync(0xffffffffu, mine && !alive);
+        if (lane == 0 && m) smem_red(&Q.t_done[item_slot], (unsigned)__popc(m), lz);
+    }
+
+    // ---- item bookkeeping ---------------------------------------------------------------------------------------------------------------
+    // every thread: write the finished item's pixels and clear its accumulators; thread 0: load the next item into the slot
+    __device__ __forceinline__ void flush_item(int b, float *__restrict__ hdr, int n_items, double fix_inv) {
+        const int item = Q.t_item[b];
+        for (int pl = tid; pl < item_pixels; pl += THREADS) {
+            const int pixel = item_pixel(item, pl);
+            if (pixel >= 0) {
+                float *out = hdr + (size_t)pixel * 3;
+                for (int c = 0; c < 3; ++c) out[c] = (float)((double)(long long)Q.acc[b][pl][c] * fix_inv * lp.out_scale);
+            }
+            Q.acc[b][pl][0] = 0ull; Q.acc[b][pl][1] = 0ull; Q.acc[b][pl][2] = 0ull;
+        }
+        __syncthreads(); // everyone has read t_item[b]
+        if (tid == 0) {
+            const int next = Q.next_item;
+            if (next < n_items) { Q.t_item[b] = next; Q.next_item = next + (int)gridDim.x; Q.t_cursor[b] = 0u; Q.t_done[b] = 0u; }
+            else Q.t_item[b] = -1;
+        }
+    }
+
+    // ---- one round: warp 0 snapshots the queues (lane = claim rank) and plans the generation --------------------------------------
+    // Every other warp waits for this, so the dependent chain is kept short: ONE shared-memory load fetches all control words (lane i
+    // reads word i), everything else is register shuffles, and every lane computes the few scalar decisions redundantly.
+    __device__ __forceinline__ void plan_round(unsigned item_total) {
+        static_assert(offsetof(SmCtl<POOL>, t_done) - offsetof(SmCtl<POOL>, q_tail) == 18 * sizeof(unsigned), "plan_round reads the control words by index");
+        static_assert(offsetof(SmCtl<POOL>, free_tail) - offsetof(SmCtl<POOL>, q_tail) == 13 * sizeof(unsigned) &&
+                          offsetof(SmCtl<POOL>, freelist) - offsetof(SmCtl<POOL>, queue) == SQ_COUNT * POOL * sizeof(uint16_t),
+                      "route() addresses the free ring as queue number SQ_COUNT");
+        unsigned v = (&Q.q_tail[0])[lane]; // words 0..19 are the control block, the padding behind it is never used
+        { // keep the ring counters small: lanes 0..5 / 6..11 hold a queue's pushed / handed-out marks, 12 / 13 the free ring's head / tail
+            const unsigned low = __shfl_sync(0xffffffffu, v, lane < 6 ? lane + 6 : (lane == 13 ? 12 : lane)); // the smaller mark of the pair
+            if (lane < 14 && low >= kRebase) { v -= kRebase; (&Q.q_tail[0])[lane] = v; }
+        }
+        const int item0 = (int)__shfl_sync(0xffffffffu, v, 14), item1 = (int)__shfl_sync(0xffffffffu, v, 15);
+        unsigned cur0 = __shfl_sync(0xffffffffu, v, 16), cur1 = __shfl_sync(0xffffffffu, v, 17);
+        const unsigned done0 = __shfl_sync(0xffffffffu, v, 18), done1 = __shfl_sync(0xffffffffu, v, 19);
+        const unsigned n_free = __shfl_sync(0xffffffffu, v, 13) - __shfl_sync(0xffffffffu, v, 12);
+        const int prev_gen = Q.gen_slot;
+        const unsigned prev_limit = Q.tail_limit; // the tail fill overshoots its limit by the claims that found nothing
+        if (prev_gen == 0) cur0 = min(cur0, prev_limit);
+        if (prev_gen == 1) cur1 = min(cur1, prev_limit);
+        int flush = -1, gen = -1;
+        if (item1 >= 0) { if (cur1 == item_total) { if (done1 == item_total) flush = 1; } else gen = 1; }
+        if (item0 >= 0) { if (cur0 == item_total) { if (done0 == item_total) flush = 0; } else if (gen < 0 || item0 < item1) gen = 0; }
+        const unsigned gen_begin = gen == 0 ? cur0 : cur1;
+        const unsigned left = gen >= 0 ? item_total - gen_begin : 0u;
+        // while new samples keep coming only full 32-record batches are handed out (the remainder waits for the next round);
+        // once generation has stopped (an item drains) everything goes
+        const int q = (kRankStage >> (4 * min(lane, 6))) & 0xf; // lanes 0..5: the queue of that rank
+        const unsigned tail = __shfl_sync(0xffffffffu, v, q & 7), handed = __shfl_sync(0xffffffffu, v, 6 + (q & 7));
+        unsigned begin = 0, end = 0;
+        if (lane < SQ_COUNT) {
+            unsigned count = tail - handed;
+            if (left != 0u) count &= ~31u;
+            begin = handed; end = handed + count;
+            Q.q_end[q] = end;
+        }
+        unsigned queued = end - begin;
+#pragma unroll
+        for (int off = 1; off < 8; off <<= 1) queued += __shfl_xor_sync(0xffffffffu, queued, off);
+        // generation: normally left to the tail fill -- warps that find the round's batches all claimed generate camera samples instead
+        // of idling at the barrier -- and planned as batches of the round only when the queues cannot keep every warp busy
+        unsigned n_gen = 0;
+        if (queued < (unsigned)THREADS) {
+            n_gen = min(n_free, left);
+            if (n_gen < left) n_gen &= ~31u; // full warps only, except for the last samples of an item
+        }
+        if (lane == SQ_COUNT) { begin = gen_begin; end = gen_begin + n_gen; }
+        const unsigned nb = (end - begin + 31u) >> 5;
+        unsigned incl = nb;
+#pragma unroll
+        for (int off = 1; off < 8; off <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += u; }
+        if (lane < 8) { Q.rb_first[lane] = incl - nb; Q.rb_begin[lane] = begin; Q.rb_end[lane] = end; }
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 7);
+        if (lane == 0) {
+            const unsigned after = gen_begin + n_gen;                       // the cursor after the planned generation batches
+            const unsigned budget = (n_free - n_gen) & ~31u;                // free records the tail fill may use: one per sample, whole batches
+            const unsigned limit = min(after + budget, item_total);         // (a last, partial batch of the item needs fewer records than it claims)
+            Q.t_cursor[0] = gen == 0 ? after : cur0; Q.t_cursor[1] = gen == 1 ? after : cur1;
+            Q.tail_limit = gen >= 0 ? limit : 0u;
+            Q.flush_slot = flush; Q.gen_slot = gen; Q.round_claim = (unsigned)(THREADS / 32);
+            Q.exit_flag = (total == 0u && flush < 0 && gen < 0) ? 1 : 0; // nothing queued, nothing to generate, nothing to write out
+        }
+    }
+
+    __device__ __forceinline__ void run(float *__restrict__ hdr, int n_items, double fix_inv) {
+        const unsigned item_total = (unsigned)item_pixels * (unsigned)(lp.sample_end - lp.sample_begin);
+        SMW_T(t_start);
+        for (;;) {
+            SMW_T(t0);
+#ifdef VPT_SMWAVE_PROFILE
+            if (lane == 0) Q.dbg_arrive[tid >> 5] = t0;
+#endif
+            __syncthreads(); // (A) the previous round's pushes / releases / counters are visible
+            SMW_T(t1);
+            if (tid < 32) plan_round(item_total);
+            __syncthreads(); // (B) the plan is visible
+            SMW_T(t2);
+#ifdef VPT_SMWAVE_PROFILE
+            if (tid == 0) { // arrival spread at (A): last arrival minus mean arrival (x warps = idle warp-cycles), and last arrival -> (B) passed
+                long long last = 0, sum = 0;
+                for (int w = 0; w < THREADS / 32; ++w) { const long long a = Q.dbg_arrive[w]; last = a > last ? a : last; sum += a; }
+                prof[23] += (unsigned long long)(last * (THREADS / 32) - sum);
+                prof[22] += (unsigned long long)((t2 - last) * (THREADS / 32));
+            }
+#endif
+            SMW_ADD(16, t1 - t0); SMW_ADD(17, t2 - t1); SMW_ADD(20, tid == 0);
+            if (Q.exit_flag) break;
+            if (Q.flush_slot >= 0) flush_item(Q.flush_slot, hdr, n_items, fix_inv); // its records are all finished; the round below only touches the other item
+            SMW_T(t3);
+            SMW_ADD(21, t3 - t2);
+#ifdef VPT_SMWAVE_PROFILE
+            long long in_batches = 0;
+#define SMW_BATCH(q, call) { const long long b0 = clock64(); call; const long long b1 = clock64(); prof[q] += b1 - b0; prof[8 + q] += 1; in_batches += b1 - b0; }
+#else
+#define SMW_BATCH(q, call) { call; }
+#endif
+            const unsigned total = Q.rb_first[7];
+            const int gen_slot = Q.gen_slot;
+            // the first batch of a round needs no atomic: warp w takes batch w, the claim counter starts behind those (plan_round); the batch
+            // table does not change during a round: read it once
+            unsigned kb = (unsigned)tid >> 5;
+            const uint4 f0 = *reinterpret_cast<const uint4 *>(&Q.rb_first[0]), f1 = *reinterpret_cast<const uint4 *>(&Q.rb_first[4]);
+            while (kb < total) {
+                const int rank = (kb >= f0.y) + (kb >= f0.z) + (kb >= f0.w) + (kb >= f1.x) + (kb >= f1.y) + (kb >= f1.z);
+                const unsigned start = Q.rb_begin[rank] + ((kb - Q.rb_first[rank]) << 5);
+                const int n = (int)min(32u, Q.rb_end[rank] - start);
+                const unsigned e = ring_index(start + (unsigned)lane);
+                switch (rank) {
+                case 0: SMW_BATCH(SQ_SURF_F, self().template run_stage<SQ_SURF_F>(lane < n ? (int)Q.queue[SQ_SURF_F][e] : -1)); break;
+                case 1: SMW_BATCH(SQ_SURF_L, self().template run_stage<SQ_SURF_L>(lane < n ? (int)Q.queue[SQ_SURF_L][e] : -1)); break;
+                case 2: SMW_BATCH(SQ_PRIMARY, self().template run_stage<SQ_PRIMARY>(lane < n ? (int)Q.queue[SQ_PRIMARY][e] : -1)); break;
+                case 3: SMW_BATCH(SQ_MED_AREA, self().template run_stage<SQ_MED_AREA>(lane < n ? (int)Q.queue[SQ_MED_AREA][e] : -1)); break;
+                case 4: SMW_BATCH(SQ_MED_POINT, self().template run_stage<SQ_MED_POINT>(lane < n ? (int)Q.queue[SQ_MED_POINT][e] : -1)); break;
+                case 5: SMW_BATCH(SQ_SURF_P, self().template run_stage<SQ_SURF_P>(lane < n ? (int)Q.queue[SQ_SURF_P][e] : -1)); break;
+                default: SMW_BATCH(6, self().run_gen(gen_slot, start, n)); last_step(); break;
+                }
+                // (claiming the next batch before running this one hides the atomic's latency but commits warps too early: measured slower)
+                // (taking ALL batches round-robin without atomics: 6750 against 7340 -- the dynamic claim is what balances 12 000-cycle SURF_L batches
+                // against 4 000-cycle ones)
+                kb = __shfl_sync(0xffffffffu, next_raw, 0);
+            }
+            // tail fill: the round's batches are all claimed; instead of idling at the barrier generate camera samples up to the limit the
+            // plan set (one free record per sample is guaranteed), they are consumed in the next round.  One atomic per batch.
+            if (gen_slot >= 0) {
+                const unsigned limit = Q.tail_limit;
+                for (;;) {
+                    unsigned base = limit;
+                    if (lane == 0 && *(volatile unsigned *)&Q.t_cursor[gen_slot] < limit) base = smem_add(&Q.t_cursor[gen_slot], 32u, lz);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (base >= limit) break;
+                    SMW_BATCH(7, self().run_gen(gen_slot, base, (int)min(32u, limit - base)));
+                }
+            }
+#ifdef VPT_SMWAVE_PROFILE
+            prof[18] += clock64() - t3 - in_batches;
+#endif
+        }
+#ifdef VPT_SMWAVE_PROFILE
+        prof[19] += clock64() - t_start;
+#endif
+    }
+};
+
+} // namespace vpt

@@ -25,9 +25,6 @@
 namespace vpt {
 namespace f32 {
 
-enum : int { SQ_PRIMARY = 0, SQ_MED_POINT, SQ_MED_AREA, SQ_SURF_P, SQ_SURF_L, SQ_SURF_F, SQ_COUNT };
-constexpr int kDestFree = SQ_COUNT; // the path ended: its record is free
-
 struct Rec {
     F3 o, d, beta;             // ray origin (the current vertex once PRIMARY has placed it), direction, throughput
     uint32_t pixel, sample;    // Philox counter words 0, 1

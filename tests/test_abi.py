@@ -84,8 +84,8 @@ def test_argument_validation_precedes_device_work(vpt):
     assert _rc(vpt, P(), hdr=False) == INVALID
     assert _rc(vpt, P(quirks=vpt.QUIRKS_REFERENCE)) == UNSUPPORTED          # rounding-decided behaviours are FP64-only
     assert _rc(vpt, P(kernel=9)) == INVALID
-    for wave in (vpt.KERNEL_WAVEFRONT_SM, vpt.KERNEL_WAVEFRONT_HBM):      # the wavefront kernels are FP32 only
-        assert _rc(vpt, P(kernel=wave, precision=vpt.PRECISION_FP64_REF)) == UNSUPPORTED
+    assert _rc(vpt, P(kernel=vpt.KERNEL_WAVEFRONT_HBM, precision=vpt.PRECISION_FP64_REF)) == UNSUPPORTED   # the multi-kernel wavefront is FP32 only
+    assert _rc(vpt, P(kernel=vpt.KERNEL_WAVEFRONT_SM, precision=vpt.PRECISION_FP64_REF)) in (0, -4, -5)   # FP64 reference mode has its own SM-wide wavefront
     for gone in (vpt.KERNEL_WAVEFRONT, vpt.KERNEL_MEGA_SCAN):              # superseded variants: no longer built
         assert _rc(vpt, P(kernel=gone)) == UNSUPPORTED
     rows = DEFAULT_SCENE.copy(); rows[6, 10] = 3                             # volumetric sphere: undefined in the reference's active methods

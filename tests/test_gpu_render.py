@@ -346,6 +346,24 @@ def test_kernel_variants_agree(gpu, l1, method):
         assert err.value.status == -3
 
 
+@pytest.mark.parametrize("quirks", [0, 3])
+def test_fp64_wavefront_equals_the_fp64_megakernel(gpu, quirks):
+    """FP64 reference mode: the SM-wide wavefront (AUTO; csrc/vpt_smwave_f64.cuh) runs the same three vertex parts (csrc/vpt_f64.cuh
+    vertex_primary / vertex_medium / vertex_surface) as the one-thread-per-pixel kernel (VPT_KERNEL_MEGA) composes into vertex(): identical
+    decisions, identical scan and event counts, pixel sums equal to the 2^-34 fixed-point rounding; reruns bit-identical."""
+    w, h, spp = 160, 120, 8
+    for method in (0, 1, 2, 4):
+        p = gpu.default_params(width=w, height=h, spp=spp, method=method, seed=15, output=gpu.OUTPUT_SUM, precision=gpu.PRECISION_FP64_REF, quirks=quirks)
+        a, sa = gpu.render(p.copy(kernel=gpu.KERNEL_MEGA), stats=True)
+        b, sb = gpu.render(p, stats=True)
+        assert (sa.paths, sa.events, sa.scene_scans, sa.nonfinite) == (sb.paths, sb.events, sb.scene_scans, sb.nonfinite)
+        np.testing.assert_allclose(b, a, rtol=3e-7, atol=spp * 3 * 2.0 ** -34)
+        assert np.array_equal(b, gpu.render(p))
+        c = gpu.render(p.copy(tile_rank=1, tile_count=3))
+        owner = (np.arange(w * h) // 128) % 3
+        assert np.array_equal(c.reshape(-1, 3)[owner == 1], b.reshape(-1, 3)[owner == 1]) and not c.reshape(-1, 3)[owner != 1].any()
+
+
 @pytest.mark.parametrize("method", [0, 1, 2, 4])
 def test_auto_kernel_per_path_parity(gpu, l1, method):
     """spp = 1: every pixel of the product kernel (AUTO = the SM-wide wavefront) is ONE path; compare each with the FP64 oracle on the same

@@ -1,5 +1,6 @@
 """Build an experimental copy of the library with extra -D flags on the FP32 translation unit (development only):
     python tools/build_variant.py <name> -DVPT_SM_THREADS=896 ...      -> tools/_variants/<name>.so
+    (a name starting with "d_" applies the flags to the FP64 translation unit instead, e.g. d_t384 -DVPT_SMD_THREADS=384)
     VPT_LIB=tools/_variants/<name>.so python tools/gpu_time.py 1024 smwave        (on the GPU box)"""
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -10,8 +11,8 @@ b.build_library()
 out = os.path.join(ROOT, "tools", "_variants"); os.makedirs(out, exist_ok=True)
 objs = []
 for src, flags in b.UNITS:
-    if src == "vpt_kernels_f32.cu":
-        o = os.path.join(out, "vpt_kernels_f32.%s.o" % name)
+    if src == ("vpt_kernels_f64.cu" if name.startswith("d_") else "vpt_kernels_f32.cu"):
+        o = os.path.join(out, "%s.%s.o" % (os.path.splitext(src)[0], name))
         subprocess.run([b._nvcc()] + b.ARCH + b.COMMON + flags + defs + ["-Xptxas", "-v", "-x", "cu", "-c", os.path.join(b.CSRC, src), "-o", o], check=True,
                        stderr=open(os.path.join(out, name + ".ptxas.txt"), "w"))
     else:

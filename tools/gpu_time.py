@@ -1,3 +1,5 @@
+"""Device-timed Mpaths/s of the kernel variants on the C2 frame (1024x768, default scene), all four shade methods.
+usage: gpu_time.py [spp] [mega,smwave,hbm,f64,f64mega]      VPT_LIB=tools/_variants/<name>.so selects an experimental build"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -5,11 +7,13 @@ import minimal_volumetric_path_tracer_b200 as v
 if os.environ.get("VPT_LIB"):  # development only: time an experimental build of the library
     v.api.LIB_PATH = os.path.abspath(os.environ["VPT_LIB"])
 spp = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-kernels = {"mega": v.KERNEL_MEGA, "smwave": v.KERNEL_WAVEFRONT_SM, "hbm": v.KERNEL_WAVEFRONT_HBM}
-names = sys.argv[2].split(",") if len(sys.argv) > 2 else list(kernels)
-for kern, name in ((kernels[n], n) for n in names):
+kernels = {"mega": dict(kernel=v.KERNEL_MEGA), "smwave": dict(kernel=v.KERNEL_WAVEFRONT_SM), "hbm": dict(kernel=v.KERNEL_WAVEFRONT_HBM),
+           "f64": dict(kernel=v.KERNEL_AUTO, precision=v.PRECISION_FP64_REF, quirks=v.QUIRKS_REFERENCE),
+           "f64mega": dict(kernel=v.KERNEL_MEGA, precision=v.PRECISION_FP64_REF, quirks=v.QUIRKS_REFERENCE)}
+names = sys.argv[2].split(",") if len(sys.argv) > 2 else ["mega", "smwave", "hbm"]
+for name in names:
     for method in (0, 1, 2, 4):
-        p = v.default_params(spp=spp, method=method, kernel=kern)
+        p = v.default_params(spp=spp, method=method, **kernels[name])
         v.render(p)
         best = 0
         for _ in range(3):
