@@ -33,7 +33,8 @@ typedef enum {
     VPT_OK = 0,
     VPT_ERR_INVALID_ARGUMENT = -1, /* null pointer, non-positive size, bad enum, sample range outside [0, spp] ... */
     VPT_ERR_SCENE = -2,            /* n_spheres out of range, too many emitters, negative radius, non-finite field */
-    VPT_ERR_UNSUPPORTED = -3,      /* material 3; material 2 with the superseded MEGA_SCAN / WAVEFRONT kernels; quirks requested in fp32 precision */
+    VPT_ERR_UNSUPPORTED = -3,      /* material 3 outside VPT_METHOD_VOLUME_SPHERES; that method in fp32 precision; the superseded MEGA_SCAN / WAVEFRONT kernels;
+                                      the HBM wavefront in fp64; quirks requested in fp32 precision */
     VPT_ERR_NO_DEVICE = -4,        /* no CUDA device / bad ordinal */
     VPT_ERR_CUDA = -5,             /* a CUDA runtime call failed; vpt_last_cuda_error() has the text */
     VPT_ERR_IO = -6                /* vpt_write_ppm could not write */
@@ -47,7 +48,8 @@ typedef struct {
     double radiance[3]; /* > 0 in any channel = emitter (vptShadeMethods.h:1296) */
     int32_t material;   /* 0 Lambert, 1 Beckmann conductor microfacet, 2 dielectric exactly as the reference writes it (bdsf vptShadeMethods.h:26-46,
                            softDielectric samplingFunctions.h:209, refraxDielectric microFacetUtilities.h:122 -- not Snell's law; used by no scene of
-                           Sphere.cpp); 3 volumetric sphere: unsupported (undefined in the reference's active methods) */
+                           Sphere.cpp); 3 volumetric sphere: only with VPT_METHOD_VOLUME_SPHERES (in the reference's three active methods bdsf leaves
+                           its pdf and direction unset for it: VPT_ERR_UNSUPPORTED there) */
     int32_t _pad;
     double eta[3], kappa[3];
     double alpha; /* Beckmann roughness */
@@ -61,8 +63,14 @@ typedef struct {
  * (freeFlightSample, vptSamplingFunctions.h:11) or equi-angular towards the picked source (equiAngularParams2, volumetricBasicFunctions.h:209) --
  * is chosen with probability 1/2 and weighted with the balance heuristic (the sample is divided by the mean of the two densities); everything
  * else (roulette, surface shading, next-event estimation, random-number slots) is method 1's.  Same expectation as methods 0-2, lower variance
- * than either. */
-enum { VPT_METHOD_FREE_FLIGHT = 0, VPT_METHOD_EQUIANGULAR = 1, VPT_METHOD_MIS = 2, VPT_METHOD_RAYMARCH = 3, VPT_METHOD_MIS_DISTANCE = 4 };
+ * than either.
+ * VOLUME_SPHERES = explicitPathRecursive2 (vptShadeMethods.h:398-497), the reference's only estimator that handles material 3 (volumetric
+ * spheres): a legacy surface path tracer in VACUUM -- the global medium (sigma_a, sigma_s, continue_prob of vpt_params) is not
+ * used; sigma_a = 0.05, sigma_s = 0.009 and the roulette q = 0.1 are the function's own literals.  A material-3 sphere is ray-marched in 100
+ * steps with single scattering from the point lights (punctualVolumetric rayMarchingMethods.h:12, multipleT volumetricBasicFunctions.h:26,
+ * Sphere::intersectVPT Sphere.h:39) and the ray continues behind it; spheres are hit from OUTSIDE only (intersectV2 :109 keeps the near
+ * root), so it needs a scene without an enclosing room (scenes/scene_volume_spheres.txt).  FP64_REF precision only. */
+enum { VPT_METHOD_FREE_FLIGHT = 0, VPT_METHOD_EQUIANGULAR = 1, VPT_METHOD_MIS = 2, VPT_METHOD_RAYMARCH = 3, VPT_METHOD_MIS_DISTANCE = 4, VPT_METHOD_VOLUME_SPHERES = 5 };
 enum { VPT_PRECISION_FP32 = 0, VPT_PRECISION_FP64_REF = 1 };
 enum { VPT_OUTPUT_SUM = 0, VPT_OUTPUT_MEAN = 1 };
 /* FP32 kernel variants (DESIGN.md "Kernels"), same results to fp32 rounding, AUTO = the fastest by measurement (profiles/):

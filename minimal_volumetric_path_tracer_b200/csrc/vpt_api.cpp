@@ -44,14 +44,14 @@ V3 v3(const double *p) { return {p[0], p[1], p[2]}; }
 bool finite3(const double *p) { return std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]); }
 bool emits(const vpt_sphere &s) { return s.radiance[0] > 0 || s.radiance[1] > 0 || s.radiance[2] > 0; } // vptShadeMethods.h:1296
 
-int validate_scene(const vpt_sphere *s, int n) {
+int validate_scene(const vpt_sphere *s, int n, int method = VPT_METHOD_FREE_FLIGHT) {
     if (!s) return VPT_ERR_INVALID_ARGUMENT;
     if (n <= 0 || n > kMaxSpheres) return VPT_ERR_SCENE;
     int n_emit = 0;
     for (int i = 0; i < n; ++i) {
         if (!(s[i].r >= 0) || !std::isfinite(s[i].r) || !finite3(s[i].p) || !finite3(s[i].c) || !finite3(s[i].radiance)) return VPT_ERR_SCENE;
-        if (s[i].material == 3) return VPT_ERR_UNSUPPORTED; // volumetric spheres: bdsf leaves pdf and direction unset for them in the active methods
-        if (s[i].material != 0 && s[i].material != 1 && s[i].material != 2) return VPT_ERR_SCENE;
+        if (s[i].material == 3 && method != VPT_METHOD_VOLUME_SPHERES) return VPT_ERR_UNSUPPORTED; // volumetric spheres: bdsf leaves pdf and direction unset for them in the active methods
+        if (s[i].material < 0 || s[i].material > 3) return VPT_ERR_SCENE;
         if (s[i].material == 1 && (!(s[i].alpha > 0) || !finite3(s[i].eta) || !finite3(s[i].kappa))) return VPT_ERR_SCENE;
         if (emits(s[i])) ++n_emit;
     }
@@ -71,7 +71,8 @@ int validate_params(const vpt_params *p, bool need_image) {
         if (!all_tiles && (p->tile_count <= 0 || p->tile_rank < 0 || p->tile_rank >= p->tile_count)) return VPT_ERR_INVALID_ARGUMENT;
         if (p->output != VPT_OUTPUT_SUM && p->output != VPT_OUTPUT_MEAN) return VPT_ERR_INVALID_ARGUMENT;
     }
-    if (p->method < 0 || p->method > VPT_METHOD_MIS_DISTANCE) return VPT_ERR_INVALID_ARGUMENT;
+    if (p->method < 0 || p->method > VPT_METHOD_VOLUME_SPHERES) return VPT_ERR_INVALID_ARGUMENT;
+    if (p->method == VPT_METHOD_VOLUME_SPHERES && p->precision != VPT_PRECISION_FP64_REF) return VPT_ERR_UNSUPPORTED; // the legacy estimator exists in reference precision only
     if (p->method == VPT_METHOD_RAYMARCH && (!(p->march_step > 0) || !std::isfinite(p->march_step) || p->march_source < 0 || p->march_source >= kMaxSpheres)) return VPT_ERR_INVALID_ARGUMENT;
     if (p->precision != VPT_PRECISION_FP32 && p->precision != VPT_PRECISION_FP64_REF) return VPT_ERR_INVALID_ARGUMENT;
     if (!(p->sigma_a >= 0) || !(p->sigma_s >= 0) || !(p->sigma_a + p->sigma_s > 0) || !std::isfinite(p->sigma_a + p->sigma_s)) return VPT_ERR_INVALID_ARGUMENT;
@@ -409,7 +410,7 @@ int vpt_render_device(const vpt_params *p, const vpt_sphere *spheres, int32_t n_
     const double t0 = now_ms();
     int rc = validate_params(p, true);
     if (rc) return rc;
-    rc = validate_scene(spheres, n_spheres);
+    rc = validate_scene(spheres, n_spheres, p->method);
     if (rc) return rc;
     if (!hdr_dev) return VPT_ERR_INVALID_ARGUMENT;
     DeviceGuard guard(p->device);
@@ -456,7 +457,7 @@ int vpt_render(const vpt_params *p, const vpt_sphere *spheres, int32_t n_spheres
     const double t0 = now_ms();
     int rc = validate_params(p, true);
     if (rc) return rc;
-    rc = validate_scene(spheres, n_spheres);
+    rc = validate_scene(spheres, n_spheres, p->method);
     if (rc) return rc;
     if (!hdr_rgb) return VPT_ERR_INVALID_ARGUMENT;
     DeviceGuard guard(p->device);
@@ -491,7 +492,7 @@ int vpt_render_multi(const vpt_params *p, const vpt_sphere *spheres, int32_t n_s
     const double t0 = now_ms();
     int rc = validate_params(p, true);
     if (rc) return rc;
-    rc = validate_scene(spheres, n_spheres);
+    rc = validate_scene(spheres, n_spheres, p->method);
     if (rc) return rc;
     if (!hdr_rgb || !devices || n_devices <= 0) return VPT_ERR_INVALID_ARGUMENT;
     if (p->tile_count > 1) return VPT_ERR_INVALID_ARGUMENT; // the tile split is chosen here
@@ -591,7 +592,7 @@ int vpt_unit(int32_t fn, const vpt_params *p, const vpt_sphere *spheres, int32_t
     if (in_stride < kUnitStrides[fn][0] || out_stride < kUnitStrides[fn][1]) return VPT_ERR_INVALID_ARGUMENT;
     int rc = validate_params(p, fn == VPT_UNIT_CAMERA_RAY);
     if (rc) return rc;
-    rc = validate_scene(spheres, n_spheres);
+    rc = validate_scene(spheres, n_spheres, p->method);
     if (rc) return rc;
     DeviceGuard guard(p->device);
     if (guard.rc) return guard.rc;

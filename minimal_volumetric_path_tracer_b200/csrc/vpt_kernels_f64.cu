@@ -14,6 +14,8 @@ __device__ __forceinline__ Ctx make_ctx(const SceneD &sc, const SphereD *shared_
     c.s = shared_spheres;
     c.n_spheres = sc.n_spheres;
     c.n_emitters = sc.n_emitters;
+    c.n_volumes = 0;
+    for (int i = 0; i < sc.n_spheres; ++i) c.n_volumes += sc.s[i].material == 3;
     c.emitters = sc.emitters;
     c.quirks = lp.quirks;
     c.sigma_a = lp.sigma_a; c.sigma_s = lp.sigma_s; c.sigma_t = lp.sigma_a + lp.sigma_s;
@@ -58,6 +60,15 @@ __global__ void __launch_bounds__(kThreadsPerBlock) render_f64_kernel(const __gr
             rng.jitter_f64(j1, j2);
             const D3 L = ray_march3(c, v3(lp.cam_o), camera_dir(lp, col, cam_y, j1, j2), lp.march_step, lp.march_source, tally);
             ++tally.events;
+            if (isfinite(L.x + L.y + L.z)) { acc_r += L.x; acc_g += L.y; acc_b += L.z; } else ++nonfinite;
+        }
+    }
+    if (c.method == VPT_METHOD_VOLUME_SPHERES) { // explicitPathRecursive2 (vptShadeMethods.h:398): one legacy path per jittered camera ray
+        for (; s < lp.sample_end; ++s) {
+            rng.start((uint32_t)pixel, (uint32_t)s, lp.key0, lp.key1);
+            double j1, j2;
+            rng.jitter_f64(j1, j2);
+            const D3 L = volume_spheres_radiance(c, v3(lp.cam_o), camera_dir(lp, col, cam_y, j1, j2), rng, tally);
             if (isfinite(L.x + L.y + L.z)) { acc_r += L.x; acc_g += L.y; acc_b += L.z; } else ++nonfinite;
         }
     }
@@ -135,7 +146,7 @@ __global__ void __launch_bounds__(kSmdThreads, 1) render_f64_smwave_kernel(const
 // kernel: VPT_KERNEL_MEGA = one thread per pixel (also the ray marcher's kernel), anything else = the SM-wide wavefront
 int launch_render_f64(const SceneD &scene, const LaunchParams &lp, float *hdr_dev, Counters *counters_dev, void *stream, int n_blocks, int kernel) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (kernel == VPT_KERNEL_MEGA || lp.method == VPT_METHOD_RAYMARCH) {
+    if (kernel == VPT_KERNEL_MEGA || lp.method == VPT_METHOD_RAYMARCH || lp.method == VPT_METHOD_VOLUME_SPHERES) {
         render_f64_kernel<<<n_blocks, kThreadsPerBlock, 0, st>>>(scene, lp, hdr_dev, counters_dev);
         return (int)cudaGetLastError();
     }
@@ -251,6 +262,7 @@ __global__ void unit_f64_kernel(int fn, const __grid_constant__ SceneD sc, const
     case VPT_UNIT_RADIANCE: {
         Path p; p.o = v3(a); p.d = v3(a + 3); p.beta = mk(1, 1, 1); p.L = mk(0, 0, 0); p.depth = 0;
         Rng rng; rng.start((uint32_t)a[6], (uint32_t)a[7], lp.key0, lp.key1);
+        if (c.method == VPT_METHOD_VOLUME_SPHERES) { st3(o, volume_spheres_radiance(c, p.o, p.d, rng, tl)); o[3] = tl.events; break; }
         for (;;) {
             rng.begin_bounce((uint32_t)p.depth);
             if ((c.max_depth > 0 && p.depth >= c.max_depth) || rng.next_f64(S_RR) < c.q) break;
@@ -262,6 +274,7 @@ __global__ void unit_f64_kernel(int fn, const __grid_constant__ SceneD sc, const
     case VPT_UNIT_RADIANCE_LIST: {
         Path p; p.o = v3(a); p.d = v3(a + 3); p.beta = mk(1, 1, 1); p.L = mk(0, 0, 0); p.depth = 0;
         ListRng rng{a + 7, 0, min((int)a[6], 120)};
+        if (c.method == VPT_METHOD_VOLUME_SPHERES) { st3(o, volume_spheres_radiance(c, p.o, p.d, rng, tl)); o[3] = rng.overrun ? -1.0 : (double)rng.i; break; }
         for (;;) {
             if ((c.max_depth > 0 && p.depth >= c.max_depth) || rng.next_f64(S_RR) < c.q) break;
             if (!vertex(c, p, rng, tl)) break;

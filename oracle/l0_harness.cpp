@@ -192,6 +192,7 @@ static inline Color radiance(int method, const Ray &r, double sa, double ss) {
     case 0: return iterativeVPTracerFree(r, sa, ss);
     case 1: return explicitVPTracerRecursive(r, sa, ss, 0);
     case 2: return MISVPTTracerRecursive(r, sa, ss, 0);
+    case 5: return explicitPathRecursive2(r, 0); /* vptShadeMethods.h:398: the legacy estimator with volumetric (material 3) spheres */
     default: return explicitVPTracerRecursiveFree(r, sa, ss, 0);
     }
 }

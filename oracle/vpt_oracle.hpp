@@ -447,13 +447,67 @@ static inline Vec surface_direct_mis(Rng &rng, Scene &sc, const Sphere &obj, con
     }
     return total + g * wg;
 }
-/* pLight, vptShadeMethods.h:62-91.  Without material-3 spheres visibilityVPT == visibility and multipleT == 1,
- * so the second branch (:70-74) cannot fire. */
+/* Sphere::intersectVPT, Sphere.h:39-45: both roots as they are (0, 0 on a miss) */
+static inline void sphere_t2(const Sphere &s, const Ray &ray, double &t1, double &t2) {
+    const Vec op = ray.o - s.p;
+    const double b = dot(op, ray.d);
+    const double det = b * b - dot(op, op) + s.r * s.r;
+    if (det < 0) { t1 = 0.0; t2 = 0.0; return; }
+    t2 = -b + std::sqrt(det);
+    t1 = -b - std::sqrt(det);
+}
+/* intersectVPT, volumetricBasicFunctions.h:64-91: intersect() that ignores material-3 (volumetric) spheres */
+static inline bool scan_vpt(Scene &sc, const Ray &ray, double &t, int &id) {
+    double best = __DBL_MAX__;
+    bool any = false;
+    ++sc.scans;
+    const bool skip_r0 = !(sc.quirks & QUIRK_R0_FALLTHROUGH);
+    for (size_t i = 0; i < sc.s.size(); ++i) {
+        if (sc.s[i].material == 3 || (skip_r0 && sc.s[i].r == 0)) continue;
+        const double ti = sphere_t(sc.s[i], ray);
+        if (ti > 0 && std::fabs(ti) > 0.0001) {
+            any = true;
+            if (ti < best) { best = ti; id = (int)i; }
+        }
+    }
+    t = any ? best : 0;
+    return any;
+}
+/* visibilityVPT, volumetricBasicFunctions.h:94-106 */
+static inline bool visible_vpt(Scene &sc, const Vec &light, const Vec &x) {
+    Vec lx = light - x;
+    const double distance = std::sqrt(dot(lx, lx));
+    lx = unit(lx);
+    lx = lx * -1;
+    int id = 0;
+    double t;
+    scan_vpt(sc, Ray{light, lx}, t, id);
+    if (sc.quirks & QUIRK_EXACT_VISIBILITY) return t > distance || t == 0;
+    return t == 0 || t > distance * (1.0 - 1e-4);
+}
+/* multipleT, volumetricBasicFunctions.h:26-58, as written: every material-3 sphere on the LINE through x1 towards x2 (the segment's end
+ * is not checked) attenuates by its full chord; a sphere wholly behind x1 multiplies by exp(-sigma_t * t_near) with t_near < 0 */
+static inline double multiple_t(const Scene &sc, const Vec &x1, const Vec &x2, double sigma_t) {
+    double T = 1;
+    const Ray r{x1, unit(x2 - x1)};
+    for (size_t i = 0; i < sc.s.size(); ++i) {
+        if (sc.s[i].material != 3) continue;
+        double t1, t2;
+        sphere_t2(sc.s[i], r, t1, t2);
+        if (t2 < 0) T = T * std::exp(-sigma_t * t1);
+        if (t2 - t1 > 0) T = T * std::exp(-sigma_t * (t2 - t1));
+    }
+    return T;
+}
+
+/* pLight, vptShadeMethods.h:62-91.  Without material-3 spheres visibilityVPT == visibility: the second branch (:70-74) repeats the
+ * scan and cannot fire. */
 static inline Vec point_light_direct(Scene &sc, const Sphere &obj, const Vec &x, const Vec &n, const Vec &wray, const Vec &I, const Vec &light, double alpha) {
     Vec Le;
     if (visible(sc, light, x)) Le = I * (1 / dot(light - x, light - x));
-    else {
-        ++sc.scans; /* the reference repeats the scan through visibilityVPT (:70); same answer */
+    else if (visible_vpt(sc, light, x)) {
+        Le = I * (1 / dot(light - x, light - x));
+        Le = Le * multiple_t(sc, x, light, 0.05 + 0.009);
     }
     Vec wi = unit(light - x);
     Vec wo = wray * -1;
@@ -602,6 +656,108 @@ static inline MisDistance mis_distance(const Scene &sc, int source, double t, co
     return m;
 }
 
+struct PathStats { uint64_t events = 0; };
+
+/* punctualVolumetric, rayMarchingMethods.h:12-32 */
+static inline Vec punctual_volumetric(Scene &sc, int source, const Vec &x, double phase, double sigma_t, double sigma_s) {
+    const Vec light = sc.s[source].p;
+    if (!visible_vpt(sc, light, x)) return Vec();
+    Vec Le = sc.s[source].radiance;
+    const double d2 = dot(light - x, light - x);
+    Le = Le * (1 / d2);
+    const Vec Ls = Le * phase * multiple_t(sc, x, light, sigma_t);
+    return Ls * sigma_s;
+}
+/* intersectV2, volumetricBasicFunctions.h:109-134: the nearest sphere by its NEAR root only -- a sphere the ray starts inside (near root
+ * negative) is never hit -- with both of its roots */
+static inline bool scan_v2(Scene &sc, const Ray &ray, double &t1, double &t2, int &id) {
+    double best = __DBL_MAX__;
+    bool any = false;
+    ++sc.scans;
+    const bool skip_r0 = !(sc.quirks & QUIRK_R0_FALLTHROUGH);
+    for (size_t i = 0; i < sc.s.size(); ++i) {
+        if (skip_r0 && sc.s[i].r == 0) continue;
+        double a, b;
+        sphere_t2(sc.s[i], ray, a, b);
+        if (a > 0 && std::fabs(a) > 0.0001) {
+            any = true;
+            if (a < best) { best = a; t1 = a; t2 = b; id = (int)i; }
+        }
+    }
+    if (!any) { t1 = 0; t2 = 0; }
+    return any;
+}
+/* VPT_METHOD_VOLUME_SPHERES = explicitPathRecursive2, vptShadeMethods.h:398-497 (the reference's only estimator that
+ * handles material 3): a surface path tracer in VACUUM -- no global medium; sigma_a = 0.05, sigma_s = 0.009 are its own literals for the
+ * inside of volumetric spheres -- in throughput form.  A material-3 sphere is ray-marched in 100 steps (single scattering from the point
+ * lights, punctualVolumetric) and the ray goes on from the LAST SAMPLE POINT (not the exit point) with the chord's transmittance; surface
+ * vertices take pLight for every point light + the legacy MIS (= MISv2 without transmittance) and roulette with q = 0.1 AFTER the direct
+ * light; an emitter that is hit returns black at any depth (`radiance.x > 0` only); materials 1 and 2 both scatter as a microfacet with the
+ * literal alpha = 0.001.  `events` counts surface vertices and marched spheres. */
+template <class Rng>
+static inline Vec volume_spheres_radiance(Rng &rng, Scene &sc, Ray ray, PathStats *stats = nullptr) {
+    const double sigma_a = 0.05, sigma_s = 0.009;
+    const double sigma_t = sigma_a + sigma_s;
+    Vec L, beta(1, 1, 1);
+    const int n_spheres = (int)sc.s.size();
+    for (int bounce = 0, guard = 0; guard < 100000; ++guard) {
+        double t, t2;
+        int id = 0;
+        if (!scan_v2(sc, ray, t, t2, id)) break;
+        if (sc.s[id].radiance.x > 0) break;
+        if (stats) ++stats->events;
+        const Vec x = ray.o + ray.d * t;
+        if (sc.s[id].material == 3) {
+            const int steps = 100;
+            const double distance = t2 - t;
+            const double step = distance / steps;
+            Vec Ls, xt;
+            for (int i = 0; i < steps; i++) {
+                xt = x + ray.d * step * i;
+                for (int light = 0; light < n_spheres; light++)
+                    if (sc.s[light].r == 0)
+                        Ls = punctual_volumetric(sc, light, xt, phase_value(), sigma_t, sigma_s) * step * transmittance(x, xt, sigma_t) + Ls;
+            }
+            L = L + had(Ls, beta);
+            beta = beta * transmittance(x, xt, sigma_t);
+            ray = Ray{xt, ray.d};
+            continue;
+        }
+        rng.begin_bounce(bounce);
+        const Sphere &obj = sc.s[id];
+        const Vec n = unit(x - obj.p);
+        const Vec wo = ray.d * -1;
+        Vec Ld;
+        for (int light = 0; light < n_spheres; light++)
+            if (sc.s[light].r == 0) Ld = point_light_direct(sc, obj, x, n, ray.d, sc.s[light].radiance, sc.s[light].p, obj.alpha) + Ld;
+        Ld = surface_direct_mis(rng, sc, obj, x, n, ray.d, obj.alpha, 0.0) + Ld; /* MIS (misSamplingFunctions.h:19-93) = MISv2 with transmittance 1 */
+        L = L + had(Ld, beta);
+        const double q = 0.1, continueprob = 1.0 - q;
+        if (rng.next(S_RR) < q) break;
+        Vec wi, fs;
+        double prob;
+        if (obj.material == 0) {
+            wi = cosine_hemisphere(rng, n, S_BSDF);
+            fs = obj.c * (1 / kPi);
+            prob = cosine_pdf(dot(n, wi));
+        } else {
+            const double alpha = 0.001;
+            Vec wh = facet_normal(rng, alpha, S_BSDF);
+            Vec s_, t_;
+            frame(n, s_, t_);
+            wh = s_ * wh.x + t_ * wh.y + n * wh.z;
+            wi = wo * (-1) + wh * 2 * (dot(wh, wo));
+            fs = facet_brdf(obj.eta, obj.kappa, wi, wh, wo, alpha, n);
+            prob = facet_pdf(wo, wh, alpha, n);
+        }
+        const double cosine = dot(n, wi);
+        beta = had(beta, fs) * std::fabs(cosine) * (1 / (prob * continueprob));
+        ray = Ray{x, wi};
+        ++bounce;
+    }
+    return L;
+}
+
 struct Settings {
     int method = 0;              /* 0 free-flight (vptShadeMethods.h:1263), 1 equi-angular (:1014), 2 "MIS" (:1345),
                                     4 distance-sampling MIS (not in the reference, SURVEY.md 8f-4: see mis_distance below) */
@@ -609,12 +765,12 @@ struct Settings {
     double continue_prob = 0.6;  /* vptShadeMethods.h:1275 */
     int max_depth = 0;           /* <= 0: unlimited (reference) */
 };
-struct PathStats { uint64_t events = 0; };
 
 /* One camera path.  The reference's recursion (methods 1, 2) is unrolled into throughput form
  * (L += beta * A ; beta *= B): identical up to the rounding of the re-associated sum. */
 template <class Rng>
 static inline Vec radiance(Rng &rng, Scene &sc, Ray ray, const Settings &cfg, PathStats *stats = nullptr) {
+    if (cfg.method == 5) return volume_spheres_radiance(rng, sc, ray, stats); /* explicitPathRecursive2: its own literals, no global medium */
     Vec L, beta(1, 1, 1);
     const double sigma_t = cfg.sigma_a + cfg.sigma_s;
     const double cp = cfg.continue_prob, q = 1 - cp;
