@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvpt_b200.so")
 
-METHOD_FREE_FLIGHT, METHOD_EQUIANGULAR, METHOD_MIS, METHOD_RAYMARCH, METHOD_MIS_DISTANCE = 0, 1, 2, 3, 4
+METHOD_FREE_FLIGHT, METHOD_EQUIANGULAR, METHOD_MIS, METHOD_RAYMARCH, METHOD_MIS_DISTANCE, METHOD_VOLUME_SPHERES = 0, 1, 2, 3, 4, 5
 PRECISION_FP32, PRECISION_FP64_REF = 0, 1
 OUTPUT_SUM, OUTPUT_MEAN = 0, 1
 KERNEL_AUTO, KERNEL_MEGA, KERNEL_WAVEFRONT, KERNEL_MEGA_SCAN, KERNEL_WAVEFRONT_SM, KERNEL_WAVEFRONT_HBM = 0, 1, 2, 3, 4, 5

@@ -63,7 +63,8 @@ def test_argument_validation_precedes_device_work(vpt):
     INVALID, SCENE, UNSUPPORTED = -1, -2, -3
     assert _rc(vpt, P(spp=0)) == INVALID
     assert _rc(vpt, P(width=0)) == INVALID
-    assert _rc(vpt, P(method=5)) == INVALID
+    assert _rc(vpt, P(method=6)) == INVALID
+    assert _rc(vpt, P(method=5)) == UNSUPPORTED                              # VPT_METHOD_VOLUME_SPHERES: FP64_REF precision only
     assert _rc(vpt, P(sample_begin=1, sample_end=1)) == INVALID
     assert _rc(vpt, P(sample_begin=0, sample_end=3)) == INVALID
     assert _rc(vpt, P(tile_rank=2, tile_count=2)) == INVALID

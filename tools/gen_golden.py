@@ -7,6 +7,7 @@ oracle/Makefile).  Run in the build container only (the reference tree does not 
   python tools/gen_golden.py scenes    -> tests/golden/scenes.npz     per-path radiance on the reference's commented alternate scenes (scenes/*.txt)
   python tools/gen_golden.py march     -> tests/golden/march.npz      rayMarching3 (rayMarchingMethods.h:330) on fixed rays
   python tools/gen_golden.py dielectric -> tests/golden/dielectric.npz per-path radiance with material-2 (dielectric) spheres in the scene
+  python tools/gen_golden.py volume    -> tests/golden/volume_spheres.npz explicitPathRecursive2 (vptShadeMethods.h:398) with material-3 spheres
 """
 import os
 import sys
@@ -276,6 +277,38 @@ def gen_dielectric():
     print("dielectric.npz written:", len(out), "arrays")
 
 
+def gen_volume():
+    """explicitPathRecursive2 of the UNMODIFIED reference (vptShadeMethods.h:398-497, as shipped: quirks 3) on scenes/scene_volume_spheres.txt:
+    320 seeded camera paths, a third of them aimed at the two volumetric (material 3) spheres, with the number of erand48 draws; plus the
+    16x16-block statistics of a 256x192 render at 64 spp (the legacy estimator takes no medium parameters: its sigma_a = 0.05, sigma_s = 0.009
+    and roulette q = 0.1 are literals)"""
+    l0 = L0(); l1 = L1(); rng = np.random.default_rng(777)
+    rows = np.loadtxt(os.path.join(ROOT, "scenes", "scene_volume_spheres.txt"), comments="#")
+    N = 320
+    o = np.tile(np.array(CAM_O), (N, 1)); d = np.zeros((N, 3))
+    vols = rows[rows[:, 10] == 3]
+    for i in range(N):
+        if i % 3 == 0:
+            v = vols[(i // 3) % len(vols)]
+            aim = v[1:4] + rng.normal(size=3) * 0.5 * v[0] - o[i]; d[i] = aim / np.linalg.norm(aim)
+        else:
+            d[i] = l1.camera_ray(1024, 768, int(rng.integers(1024)), int(rng.integers(768)), rng.random(), rng.random())
+    seeds = rng.integers(0, 65536, (N, 3))
+    l0.set_scene(rows); l0.set_quirks(3)
+    res = np.zeros((N, 4))
+    for i in range(N):
+        L, nd = l0.radiance(5, o[i], d[i], SA, SS, seed3=tuple(int(s) for s in seeds[i]))
+        res[i, :3] = L; res[i, 3] = nd
+    w, h, spp = 256, 192, 64
+    t0 = time.time()
+    total, sq, draws = l0.render(w, h, spp, 5, SA, SS, seed=31, want_sumsq=True)
+    mean, var = block_stats(total, sq, spp)
+    l0.reset_scene(); l0.set_quirks(3)
+    np.savez_compressed(os.path.join(GOLD, "volume_spheres.npz"), rows=rows, o=o, d=d, seeds=seeds, q3=res, block_mean=mean.astype(np.float32),
+                        block_var=var.astype(np.float32), width=w, height=h, spp=spp, image_mean=(total / spp).mean(axis=(0, 1)))
+    print("volume_spheres.npz: %d paths, %d with light, render %.1fs, image mean %s" % (N, int((res[:, :3].max(axis=1) > 0).sum()), time.time() - t0, (total / spp).mean(axis=(0, 1))))
+
+
 def gen_march():
     """rayMarching3 of the UNMODIFIED reference (as shipped: quirks 3) and with the robust hooks (quirks 0) on 96 rays: the literals of the
     commented call rt.cpp:791 (sigma 0.001 / 0.0125, step 0.1, source 7), the point light (source 8) and a coarser step"""
@@ -339,5 +372,7 @@ if __name__ == "__main__":
         gen_dielectric()
     if what in ("march", "all"):
         gen_march()
+    if what in ("volume", "all"):
+        gen_volume()
     if what in ("images", "all"):
         gen_images(sys.argv[2:] or None)
