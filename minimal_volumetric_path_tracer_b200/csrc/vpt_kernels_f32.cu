@@ -2,6 +2,8 @@
 // megakernel kept as the measured alternative, the ray marcher, the unit kernels behind vpt_unit(), the Philox test kernel and the FFMA
 // peak probe.  Every estimator evaluated here is vpt_stages.cuh -- the same functions the product kernel runs.
 #include <cuda_runtime.h>
+#include <mutex>
+#include <vector>
 #include "vpt_smwave.cuh"
 #include "vpt_march.cuh"
 
@@ -94,6 +96,52 @@ __global__ void __launch_bounds__(kSmThreads, 1) render_f32_smwave_kernel(const 
     }
 }
 
+// ---- Philox round keys of the product kernel in constant memory (vpt_philox.cuh philox_block_ck) ------------------------------------------
+// One schedule per device at a time.  Launches with the same seed share it (each waits for the copy that set it); a launch with another
+// seed first waits -- on the device, through events -- for every launch that may still read the old one.  Nothing here blocks the host.
+namespace {
+struct KeySlot {
+    std::mutex m;
+    bool valid = false;
+    uint32_t k0 = 0, k1 = 0;
+    cudaEvent_t set_ev = nullptr;
+    std::vector<cudaEvent_t> users, spare;
+};
+KeySlot g_key_slots[64];
+
+cudaError_t philox_keys_begin(KeySlot &K, cudaStream_t st, uint32_t k0, uint32_t k1) { // K.m is held until philox_keys_end
+    cudaError_t e;
+    if (!K.set_ev && (e = cudaEventCreateWithFlags(&K.set_ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if (K.valid && K.k0 == k0 && K.k1 == k1) return cudaStreamWaitEvent(st, K.set_ev, 0);
+    for (cudaEvent_t ev : K.users) {
+        if ((e = cudaStreamWaitEvent(st, ev, 0)) != cudaSuccess) return e;
+        K.spare.push_back(ev);
+    }
+    K.users.clear();
+    uint32_t ks[20];
+    for (uint32_t i = 0; i < 10; ++i) { ks[2 * i] = k0 + i * 0x9E3779B9u; ks[2 * i + 1] = k1 + i * 0xBB67AE85u; }
+    K.valid = false;
+    if ((e = cudaMemcpyToSymbolAsync(c_philox_ks, ks, sizeof(ks), 0, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(K.set_ev, st)) != cudaSuccess) return e;
+    K.valid = true; K.k0 = k0; K.k1 = k1;
+    return cudaSuccess;
+}
+cudaError_t philox_keys_end(KeySlot &K, cudaStream_t st) { // after the launch: remember it as a reader of the current schedule
+    if (K.users.size() >= 16) { // forget the readers that have finished
+        std::vector<cudaEvent_t> busy;
+        for (cudaEvent_t ev : K.users) (cudaEventQuery(ev) == cudaSuccess ? K.spare : busy).push_back(ev);
+        cudaGetLastError(); // (cudaErrorNotReady is not an error)
+        K.users.swap(busy);
+    }
+    cudaEvent_t ev = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (!K.spare.empty()) { ev = K.spare.back(); K.spare.pop_back(); }
+    else e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e == cudaSuccess && (e = cudaEventRecord(ev, st)) == cudaSuccess) K.users.push_back(ev);
+    return e;
+}
+} // namespace
+
 template <int METHOD>
 static int launch_smwave(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, cudaStream_t st, int n_owned_tiles) {
     int dev = 0, n_sm = 0;
@@ -106,8 +154,18 @@ static int launch_smwave(const SceneF &scene, const LaunchParams &lp, const Cons
     const int tiles_per_item = 1 << (log_p - 7);
     const int n_items = (n_owned_tiles + tiles_per_item - 1) / tiles_per_item;
     const int grid = n_items < n_sm ? n_items : n_sm;
+#ifdef VPT_PHILOX_ARG_KEYS
     render_f32_smwave_kernel<METHOD><<<grid, kSmThreads, sizeof(SmShared), st>>>(scene, lp, cf, hdr_dev, counters_dev, log_p, n_owned_tiles, n_items, 0);
     return (int)cudaGetLastError();
+#else
+    if (dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
+    KeySlot &K = g_key_slots[dev];
+    std::lock_guard<std::mutex> lock(K.m);
+    if ((e = philox_keys_begin(K, st, lp.key0, lp.key1)) != cudaSuccess) return (int)e;
+    render_f32_smwave_kernel<METHOD><<<grid, kSmThreads, sizeof(SmShared), st>>>(scene, lp, cf, hdr_dev, counters_dev, log_p, n_owned_tiles, n_items, 0);
+    if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+    return (int)philox_keys_end(K, st);
+#endif
 }
 
 // ---- ray-marching reference solver (vpt_march.cuh): one thread per pixel ---------------------------------------------------------

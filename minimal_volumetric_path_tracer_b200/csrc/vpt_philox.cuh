@@ -37,6 +37,21 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1
 static __device__ __noinline__ uint4 philox_block(uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t block, uint32_t k0, uint32_t k1) {
     return philox4x32_10(make_uint4(pixel, sample, bounce, block), k0, k1);
 }
+// The same block with the ten round keys (key + round * Weyl constant) read from constant memory: `hi ^ c ^ c[bank][imm]` is ONE LOP3 with a
+// constant-bank operand, where the version above spends two more instructions per round bumping the keys (UIADD3: 3.4 % of the product
+// kernel's executed instructions, profiles/r2_summary.md).  The host sets the schedule of the render's seed before the launch
+// (vpt_kernels_f32.cu philox_keys_begin); used by the product kernel only.
+static __constant__ uint32_t c_philox_ks[20];
+static __device__ __noinline__ uint4 philox_block_ck(uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t block) {
+    uint4 c = make_uint4(pixel, sample, bounce, block);
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ c_philox_ks[2 * round], lo1, hi0 ^ c.w ^ c_philox_ks[2 * round + 1], lo0);
+    }
+    return c;
+}
 // (2k + 1) 2^-24 with k = w >> 9, without the integer-to-float conversion: 1.k (k in the mantissa) minus (1 - 2^-24) is exactly that value
 __device__ __forceinline__ float u32_to_unit_f32(uint32_t w) { return __uint_as_float(0x3f800000u | (w >> 9)) - 0.99999994039535522461f; }
 __device__ __forceinline__ double u32_to_unit_f64(uint32_t w) { return (double)(2u * (w >> 9) + 1u) * 5.9604644775390625e-8; }

@@ -55,11 +55,19 @@ struct SmWave : SmSched<SmWave<METHOD>, kSmPool, kSmThreads> {
 
     // ---- the stages' context ------------------------------------------------------------------------------------------------------
     __device__ __forceinline__ float4 rnd(const Rec &r, uint32_t block) const {
+#ifdef VPT_PHILOX_ARG_KEYS
         const uint4 b = philox_block(r.pixel, r.sample, r.depth, block, lp.key0, lp.key1);
+#else
+        const uint4 b = philox_block_ck(r.pixel, r.sample, r.depth, block);
+#endif
         return make_float4(u32_to_unit_f32(b.x), u32_to_unit_f32(b.y), u32_to_unit_f32(b.z), u32_to_unit_f32(b.w));
     }
     __device__ __forceinline__ float4 jitter(const Rec &r) const {
+#ifdef VPT_PHILOX_ARG_KEYS
         const uint4 b = philox_block(r.pixel, r.sample, kJitterBounce, 0, lp.key0, lp.key1);
+#else
+        const uint4 b = philox_block_ck(r.pixel, r.sample, kJitterBounce, 0);
+#endif
         return make_float4(u32_to_unit_f32(b.x), u32_to_unit_f32(b.y), 0.0f, 0.0f);
     }
     __device__ __forceinline__ bool scan(F3 o, F3 d, float &t, int &id) { return scan_sm(S, o, d, t, id); }

@@ -93,8 +93,32 @@ def erand48_stream(seed3, n):
     return out
 
 
+def test_the_estimator_has_a_rounding_decided_branch_of_its_own(l1, gold):
+    """Hazard C (as hazards A and B of the active methods): the first march point of a volumetric sphere lies ON the
+    sphere, so in multipleT (volumetricBasicFunctions.h:42-49) the far root of that very sphere is 0 up to rounding -- `t_aux2 < 0` then
+    multiplies the step's transmittance by exp(+sigma_t chord) instead of exp(-sigma_t chord).  A 1e-13 change of the camera direction flips
+    it: per-path agreement between two correct FP64 implementations (glibc / CUDA libm) can only be asked of the paths that are not affected."""
+    rows = gold["rows"]
+    o = np.tile(np.array(CAM_O), (60, 1))
+    d = gold["d"][:180:3][:60]                                                     # the rays aimed at the volumetric spheres
+    pix = np.arange(60, dtype=np.uint32); smp = np.zeros(60, dtype=np.uint32)
+    a, _ = l1.radiance_philox(rows, 0, M, 0.001, 0.009, 5, o, d, pix, smp)
+    d2 = d + 1e-13; d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
+    b, _ = l1.radiance_philox(rows, 0, M, 0.001, 0.009, 5, o, d2, pix, smp)
+    e = np.abs(a - b).max(axis=1) / np.maximum(np.abs(a).max(axis=1), 1e-30)
+    assert np.median(e) < 1e-9                                                     # smooth for most rays ...
+    assert 1e-6 < e.max() < 0.05                                                   # ... and a jump of the size of one march step for some
+
+
+def _per_path(got, want):
+    den = np.maximum(np.abs(want).max(axis=1), 1e-30)
+    return np.abs(got - want).max(axis=1) / den
+
+
 @pytest.mark.gpu
 def test_gpu_fp64_reproduces_the_reference_vectors(gpu, gold):
+    """the reference's own erand48 sequences (as shipped: quirks 3) through VPT_UNIT_RADIANCE_LIST: same number of draws; identical radiance
+    except where one of the rounding-decided branches (hazards A, B: point-light visibility; C: above) falls differently with CUDA's libm"""
     n = len(gold["o"])
     rows = np.zeros((n, 127))
     rows[:, 0:3] = gold["o"]; rows[:, 3:6] = gold["d"]; rows[:, 6] = 120
@@ -106,23 +130,44 @@ def test_gpu_fp64_reproduces_the_reference_vectors(gpu, gold):
     ok = got[:, 3] >= 0
     assert ok.mean() > 0.9                                                        # roulette q = 0.1: a few paths need more than 120 draws
     same = got[ok, 3] == want[ok, 3]
-    assert same.mean() > 0.97                                                     # (a rounding-decided hit of an r = 0 sphere may flip with CUDA's libm)
-    den = np.maximum(np.abs(want[ok, :3]).max(axis=1), 1e-30)
-    e = (np.abs(got[ok, :3] - want[ok, :3]).max(axis=1) / den)[same]
-    assert np.mean(e > 1e-9) < 0.03 and np.median(e) < 1e-12
+    assert same.mean() > 0.97
+    e = _per_path(got[ok, :3], want[ok, :3])[same]
+    assert np.median(e) < 1e-12 and np.mean(e > 1e-9) < 0.2, (float(np.median(e)), float(np.mean(e > 1e-9)))
+
+
+@pytest.mark.gpu
+def test_gpu_fp64_paths_equal_the_oracle_on_philox_streams(gpu, l1, gold):
+    """robust semantics (quirks 0): only hazard C is left -- at most 1 % of the paths, by at most a march step's worth"""
+    rows = gold["rows"]
+    n = 6000
+    rng = np.random.default_rng(1)
+    o = np.tile(np.array(CAM_O), (n, 1))
+    d = np.array([l1.camera_ray(256, 192, int(rng.integers(256)), int(rng.integers(192)), rng.random(), rng.random()) for _ in range(n)])
+    pix = rng.integers(0, 2 ** 20, n).astype(np.uint32); smp = rng.integers(0, 2 ** 14, n).astype(np.uint32)
+    inp = np.concatenate([o, d, pix[:, None].astype(float), smp[:, None].astype(float)], axis=1)
+    want, ev = l1.radiance_philox(rows, 0, M, 0.001, 0.009, 42, o, d, pix, smp)
+    got = gpu.unit(gpu.UNIT.RADIANCE, inp, gpu.default_params(method=M, precision=gpu.PRECISION_FP64_REF, quirks=0, seed=42), gpu.scene_from_rows(rows))
+    assert np.array_equal(got[:, 3], ev)
+    e = _per_path(got[:, :3], want)
+    assert np.mean(e > 1e-9) < 0.01 and e.max() < 0.05 and np.median(e) < 1e-12, (float(np.mean(e > 1e-9)), float(e.max()))
 
 
 @pytest.mark.gpu
 def test_gpu_fp64_render_equals_the_oracle_on_philox_streams(gpu, l1, gold):
     w, h, spp = 96, 72, 4
     scene = gpu.scene_from_rows(gold["rows"])
-    for quirks in (0, 3):
-        p = gpu.default_params(width=w, height=h, spp=spp, method=M, precision=gpu.PRECISION_FP64_REF, quirks=quirks, seed=6, output=gpu.OUTPUT_SUM)
-        img, st = gpu.render(p, scene, stats=True)
-        ref, _, rst = l1.render(gold["rows"], quirks, M, 0.001, 0.009, w, h, 6, spp, want_sumsq=False)
-        assert st.paths == w * h * spp and st.nonfinite == 0 and st.events == rst["events"]
-        np.testing.assert_allclose(img, ref, rtol=3e-6, atol=1e-7)
-        assert np.array_equal(img, gpu.render(p, scene))
+    p = gpu.default_params(width=w, height=h, spp=spp, method=M, precision=gpu.PRECISION_FP64_REF, quirks=0, seed=6, output=gpu.OUTPUT_SUM)
+    img, st = gpu.render(p, scene, stats=True)
+    ref, _, rst = l1.render(gold["rows"], 0, M, 0.001, 0.009, w, h, 6, spp, want_sumsq=False)
+    assert st.paths == w * h * spp and st.nonfinite == 0 and st.events == rst["events"]
+    e = np.abs(img - ref).max(axis=2) / np.maximum(np.abs(ref).max(axis=2), 1e-6)
+    assert np.mean(e > 3e-6) < 0.03 and e.max() < 0.05                            # (hazard C pixels)
+    np.testing.assert_allclose(img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=1e-4)
+    assert np.array_equal(img, gpu.render(p, scene))
+    img3, st3 = gpu.render(p.copy(quirks=3), scene, stats=True)                   # as shipped: hazards A and B on top (point-light visibility)
+    ref3, _, rst3 = l1.render(gold["rows"], 3, M, 0.001, 0.009, w, h, 6, spp, want_sumsq=False)
+    assert abs(int(st3.events) - rst3["events"]) <= 0.01 * rst3["events"]
+    np.testing.assert_allclose(img3.mean(axis=(0, 1)), ref3.mean(axis=(0, 1)), rtol=0.05)
 
 
 @pytest.mark.gpu
