@@ -47,6 +47,9 @@ struct SmCtl {
     // [rb_begin + 32 j, min(rb_end, +32)), j = k - rb_first
     __align__(16) unsigned rb_first[8]; // [7] = number of batches of the round
     unsigned rb_begin[8], rb_end[8];
+    // ... and spelled out per batch by the plan, so that a claim costs ONE load: rank (bits 0-2) | records in the batch (3-8) | bits 16-31: ring
+    // index of the batch's first queue entry, or, for a generation batch (rank 6), its number j (samples [rb_begin[6] + 32 j, + 32))
+    unsigned desc[2 * (POOL / 32) + 16];
     unsigned round_claim;      // next unclaimed batch of the round: one atomicAdd per batch
     unsigned tail_limit;       // camera-sample cursor up to which warps out of batches may generate in this round (tail fill)
     // the 20 words the round plan reads, contiguous: warp 0 fetches them with ONE load (lane i reads word i, see plan_round)
@@ -267,8 +270,21 @@ struct SmSched {
         unsigned incl = nb;
 #pragma unroll
         for (int off = 1; off < 8; off <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += u; }
-        if (lane < 8) { Q.rb_first[lane] = incl - nb; Q.rb_begin[lane] = begin; Q.rb_end[lane] = end; }
+        const unsigned first = incl - nb;
+        if (lane < 8) { Q.rb_first[lane] = first; Q.rb_begin[lane] = begin; Q.rb_end[lane] = end; }
         const unsigned total = __shfl_sync(0xffffffffu, incl, 7);
+        { // the batch descriptors: lane i writes batches i, i + 32, ...; lane r < 7 holds rank r's first batch / begin / end
+            const unsigned f1 = __shfl_sync(0xffffffffu, first, 1), f2 = __shfl_sync(0xffffffffu, first, 2), f3 = __shfl_sync(0xffffffffu, first, 3);
+            const unsigned f4 = __shfl_sync(0xffffffffu, first, 4), f5 = __shfl_sync(0xffffffffu, first, 5), f6 = __shfl_sync(0xffffffffu, first, 6);
+            for (unsigned k0 = 0; k0 < total; k0 += 32u) { // (warp-uniform trip count: the shuffles below are executed by every lane)
+                const unsigned kk = k0 + (unsigned)lane;
+                const int rank = (kk >= f1) + (kk >= f2) + (kk >= f3) + (kk >= f4) + (kk >= f5) + (kk >= f6);
+                const unsigned rf = __shfl_sync(0xffffffffu, first, rank), rbeg = __shfl_sync(0xffffffffu, begin, rank), rend = __shfl_sync(0xffffffffu, end, rank);
+                const unsigned j = kk - rf, start = rbeg + (j << 5);
+                const unsigned n = min(32u, rend - start);
+                if (kk < total) Q.desc[kk] = (unsigned)rank | (n << 3) | ((rank == SQ_COUNT ? j : ring_index(start)) << 16);
+            }
+        }
         if (lane == 0) {
             const unsigned after = gen_begin + n_gen;                       // the cursor after the planned generation batches
             const unsigned budget = (n_free - n_gen) & ~31u;                // free records the tail fill may use: one per sample, whole batches
@@ -314,15 +330,15 @@ struct SmSched {
 #endif
             const unsigned total = Q.rb_first[7];
             const int gen_slot = Q.gen_slot;
-            // the first batch of a round needs no atomic: warp w takes batch w, the claim counter starts behind those (plan_round); the batch
-            // table does not change during a round: read it once
+            const unsigned gen_begin = Q.rb_begin[SQ_COUNT];
+            // the first batch of a round needs no atomic: warp w takes batch w, the claim counter starts behind those (plan_round)
             unsigned kb = (unsigned)tid >> 5;
-            const uint4 f0 = *reinterpret_cast<const uint4 *>(&Q.rb_first[0]), f1 = *reinterpret_cast<const uint4 *>(&Q.rb_first[4]);
             while (kb < total) {
-                const int rank = (kb >= f0.y) + (kb >= f0.z) + (kb >= f0.w) + (kb >= f1.x) + (kb >= f1.y) + (kb >= f1.z);
-                const unsigned start = Q.rb_begin[rank] + ((kb - Q.rb_first[rank]) << 5);
-                const int n = (int)min(32u, Q.rb_end[rank] - start);
-                const unsigned e = ring_index(start + (unsigned)lane);
+                const unsigned dsc = Q.desc[kb];
+                const int rank = (int)(dsc & 7u), n = (int)((dsc >> 3) & 63u);
+                const unsigned start = gen_begin + ((dsc >> 16) << 5); // (generation batches only)
+                unsigned e = (dsc >> 16) + (unsigned)lane;             // ring index of this lane's queue entry
+                if (e >= (unsigned)POOL) e -= (unsigned)POOL;
                 switch (rank) {
                 case 0: SMW_BATCH(SQ_SURF_F, self().template run_stage<SQ_SURF_F>(lane < n ? (int)Q.queue[SQ_SURF_F][e] : -1)); break;
                 case 1: SMW_BATCH(SQ_SURF_L, self().template run_stage<SQ_SURF_L>(lane < n ? (int)Q.queue[SQ_SURF_L][e] : -1)); break;
