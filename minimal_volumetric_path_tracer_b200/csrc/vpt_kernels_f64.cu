@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock) render_f64_kernel(const __gr
                 active = true; ++s;
             }
             rng.begin_bounce((uint32_t)p.depth);
-            const bool too_deep = c.max_depth > 0 && p.depth >= c.max_depth;
+            const bool too_deep = (c.max_depth > 0 && p.depth >= c.max_depth) || p.depth >= VPT_MAX_DEPTH;
             if (too_deep || rng.next_f64(S_RR) < c.q) {
                 if (isfinite(p.L.x + p.L.y + p.L.z)) { acc_r += p.L.x; acc_g += p.L.y; acc_b += p.L.z; } else ++nonfinite;
                 active = false;
@@ -265,7 +265,7 @@ __global__ void unit_f64_kernel(int fn, const __grid_constant__ SceneD sc, const
         if (c.method == VPT_METHOD_VOLUME_SPHERES) { st3(o, volume_spheres_radiance(c, p.o, p.d, rng, tl)); o[3] = tl.events; break; }
         for (;;) {
             rng.begin_bounce((uint32_t)p.depth);
-            if ((c.max_depth > 0 && p.depth >= c.max_depth) || rng.next_f64(S_RR) < c.q) break;
+            if ((c.max_depth > 0 && p.depth >= c.max_depth) || p.depth >= VPT_MAX_DEPTH || rng.next_f64(S_RR) < c.q) break;
             if (!vertex(c, p, rng, tl)) break;
             ++p.depth;
         }

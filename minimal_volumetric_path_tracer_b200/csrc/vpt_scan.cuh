@@ -122,7 +122,12 @@ __device__ __forceinline__ void pair_direct(const float4 *__restrict__ rec, cons
 // exactly the positive floats, whose bit patterns order like unsigned integers, while negative values (sign bit) and the NaN of a
 // negative discriminant (0x7fffffff) compare above +inf: ONE three-input unsigned minimum per sphere replaces four compares and
 // selects on the half-rate ALU pipe; the index follows with one compare and one select.
-static __device__ __noinline__ ScanHit scan_sm_call(float ox, float oy, float oz, float dx, float dy, float dz) {
+#ifdef VPT_SCAN_INLINE // experiment (tools/build_variant.py): one copy per call site instead of one per kernel
+#define VPT_SCAN_LINKAGE __forceinline__
+#else
+#define VPT_SCAN_LINKAGE __noinline__
+#endif
+static __device__ VPT_SCAN_LINKAGE ScanHit scan_sm_call(float ox, float oy, float oz, float dx, float dy, float dz) {
     const SmScene &S = *reinterpret_cast<const SmScene *>(smwave_smem);
     unsigned best = 0x7f800000u; // +inf
     int bi = -1;

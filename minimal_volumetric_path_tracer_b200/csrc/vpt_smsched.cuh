@@ -107,11 +107,10 @@ struct SmSched {
 #ifdef VPT_SMWAVE_PROFILE
     unsigned long long prof[24] = {};
 #endif
-    static constexpr bool kPow2 = (POOL & (POOL - 1)) == 0;
-    // ring counters only ever grow; once a queue's `handed out` mark passes this multiple of the pool size, both marks are pulled back by it
-    // (in the plan, single-threaded between two barriers), so that `counter % POOL` stays exact on 32-bit wrap-around
-    static constexpr unsigned kRebase = (unsigned)POOL * (0x40000000u / (unsigned)POOL);
-    static __device__ __forceinline__ unsigned ring_index(unsigned counter) { return kPow2 ? (counter & (unsigned)(POOL - 1)) : (counter % (unsigned)POOL); }
+    // Ring counters only grow between plans; every plan pulls a ring's two marks (pushed / handed out, free head / tail) back by the pool size
+    // once the smaller one has passed it.  A ring never holds more than POOL entries and a round hands out at most POOL, so every counter a
+    // round sees is below 2 * POOL and `counter mod POOL` is one compare and one subtract (POOL need not be a power of two).
+    static __device__ __forceinline__ unsigned ring_index(unsigned counter) { return counter >= (unsigned)POOL ? counter - (unsigned)POOL : counter; }
 
     __device__ SmSched(SmCtl<POOL> &Q_, const LaunchParams &lp_, int log_p_, int n_owned_, int zero)
         : Q(Q_), lp(lp_), tid((int)threadIdx.x), lane((int)threadIdx.x & 31), lz((threadIdx.x & 31u) * (unsigned)zero), log_p(log_p_),
@@ -227,9 +226,9 @@ struct SmSched {
                           offsetof(SmCtl<POOL>, freelist) - offsetof(SmCtl<POOL>, queue) == SQ_COUNT * POOL * sizeof(uint16_t),
                       "route() addresses the free ring as queue number SQ_COUNT");
         unsigned v = (&Q.q_tail[0])[lane]; // words 0..19 are the control block, the padding behind it is never used
-        { // keep the ring counters small: lanes 0..5 / 6..11 hold a queue's pushed / handed-out marks, 12 / 13 the free ring's head / tail
+        { // keep the ring counters below 2 * POOL: lanes 0..5 / 6..11 hold a queue's pushed / handed-out marks, 12 / 13 the free ring's head / tail
             const unsigned low = __shfl_sync(0xffffffffu, v, lane < 6 ? lane + 6 : (lane == 13 ? 12 : lane)); // the smaller mark of the pair
-            if (lane < 14 && low >= kRebase) { v -= kRebase; (&Q.q_tail[0])[lane] = v; }
+            if (lane < 14 && low >= (unsigned)POOL) { v -= (unsigned)POOL; (&Q.q_tail[0])[lane] = v; }
         }
         const int item0 = (int)__shfl_sync(0xffffffffu, v, 14), item1 = (int)__shfl_sync(0xffffffffu, v, 15);
         unsigned cur0 = __shfl_sync(0xffffffffu, v, 16), cur1 = __shfl_sync(0xffffffffu, v, 17);
@@ -337,8 +336,7 @@ struct SmSched {
                 const unsigned dsc = Q.desc[kb];
                 const int rank = (int)(dsc & 7u), n = (int)((dsc >> 3) & 63u);
                 const unsigned start = gen_begin + ((dsc >> 16) << 5); // (generation batches only)
-                unsigned e = (dsc >> 16) + (unsigned)lane;             // ring index of this lane's queue entry
-                if (e >= (unsigned)POOL) e -= (unsigned)POOL;
+                const unsigned e = ring_index((dsc >> 16) + (unsigned)lane); // this lane's queue entry
                 switch (rank) {
                 case 0: SMW_BATCH(SQ_SURF_F, self().template run_stage<SQ_SURF_F>(lane < n ? (int)Q.queue[SQ_SURF_F][e] : -1)); break;
                 case 1: SMW_BATCH(SQ_SURF_L, self().template run_stage<SQ_SURF_L>(lane < n ? (int)Q.queue[SQ_SURF_L][e] : -1)); break;

@@ -39,6 +39,11 @@ def shard_params(params, mode, rank, world):
 
 
 def _render_cuda(params, scene, torch):
+    if torch.cuda.current_device() != params.device:
+        # one rank per GPU: the frame is reduced by NCCL on torch's current device; a rank that leaves params.device at its default 0 would
+        # render on GPU 0 next to rank 0 and hand NCCL a buffer of another device
+        raise ValueError("params.device = %d but this process's current CUDA device is %d: pass device=local_rank (and torch.cuda.set_device(local_rank))"
+                         % (params.device, torch.cuda.current_device()))
     dev = torch.device("cuda", params.device)
     hdr = torch.empty((params.height, params.width, 3), dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
