@@ -16,7 +16,8 @@ last timed step is compared with the reference's own render of this configuratio
 reference-facing call with HOST buffers (vpt_render() at N = 1; distributed.render_sharded() + the D2H of the reduced frame
 at N > 1), copies inside the timed region.  `roofline` is FP32 CUDA-core throughput: algorithmic FLOP per camera path
 (1700 canonical for C1/C2/C3/C5, W = 18*S*T + 460*E from vpt_stats for C4) against the FFMA peak measured live.
-`extras` carries the other BASELINE.json configurations measured with the same build (N = 1 only).  `cpu_baseline` /
+`extras` carries the other BASELINE.json configurations measured with the same build (N = 1; at N > 1 one frame of config 5 as written,
+3840x2160 at 16384 spp sharded over the N GPUs).  `cpu_baseline` /
 `--impl reference` time the reference's own CPU code (oracle/_ref, compiled from the unmodified sources) on the host cores."""
 import argparse
 import ctypes as C
@@ -299,6 +300,31 @@ def main():
     h2d = C.sizeof(v.Params) + len(scene) * C.sizeof(v.Sphere)
     d2h = W * H * 3 * 4
 
+    # ---- N > 1: BASELINE.json config 5 as written (3840x2160 @ 16384 spp sharded over the N GPUs, one NCCL reduce), one warm-up + one timed frame
+    c5_sharded = None
+    if world > 1 and args.config != "c5" and args.precision == "fp32" and not args.no_extras:
+        c5 = CONFIGS["c5"]
+        whole5 = v.default_params(width=c5["width"], height=c5["height"], spp=c5["spp"], method=c5["method"], seed=1, device=local)
+        mine5, _ = vdist.shard_params(whole5, "samples", rank, world)
+        hdr5 = torch.zeros((c5["height"], c5["width"], 3), dtype=torch.float32, device=dev)
+        ev5 = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+        for timed in (False, True):
+            sync()
+            if timed:
+                ev5[0].record(stream)
+            v.render_device(mine5, scene, hdr5.data_ptr(), stream.cuda_stream)
+            dist.reduce(hdr5, dst=0, op=dist.ReduceOp.SUM)
+            if timed:
+                ev5[1].record(stream)
+            sync()
+        ms5 = torch.tensor([ev5[0].elapsed_time(ev5[1])], dtype=torch.float64, device=dev)
+        dist.all_reduce(ms5, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            paths5 = c5["width"] * c5["height"] * c5["spp"]
+            c5_sharded = {"workload": c5["name"] + ", sharded by samples over %d GPUs, one NCCL reduce" % world, "mpaths_s": paths5 / float(ms5.item()) / 1e3,
+                          "ms_per_frame": float(ms5.item()), "frame_check": golden_check(c5, hdr5.cpu().numpy(), c5["spp"])}
+        del hdr5
+
     if rank != 0:
         if world > 1:
             dist.barrier(); dist.destroy_process_group()
@@ -370,6 +396,8 @@ def main():
             v.render_device(q, scene, hdr.data_ptr(), stream.cuda_stream, s)
             v.render_device(q, scene, hdr.data_ptr(), stream.cuda_stream, s)
             extras[name] = s.paths / s.kernel_ms / 1e3
+    if c5_sharded is not None:
+        extras["c5_sharded"] = c5_sharded
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

@@ -42,7 +42,12 @@ static __device__ __noinline__ uint4 philox_block(uint32_t pixel, uint32_t sampl
 // kernel's executed instructions, profiles/r2_summary.md).  The host sets the schedule of the render's seed before the launch
 // (vpt_kernels_f32.cu philox_keys_begin); used by the product kernel only.
 static __constant__ uint32_t c_philox_ks[20];
-static __device__ __noinline__ uint4 philox_block_ck(uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t block) {
+#ifdef VPT_PHILOX_INLINE // experiment (tools/build_variant.py)
+static __device__ __forceinline__ uint4 philox_block_ck(
+#else
+static __device__ __noinline__ uint4 philox_block_ck(
+#endif
+    uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t block) {
     uint4 c = make_uint4(pixel, sample, bounce, block);
 #pragma unroll
     for (int round = 0; round < 10; ++round) {

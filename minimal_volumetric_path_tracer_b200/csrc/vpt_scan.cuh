@@ -122,10 +122,14 @@ __device__ __forceinline__ void pair_direct(const float4 *__restrict__ rec, cons
 // exactly the positive floats, whose bit patterns order like unsigned integers, while negative values (sign bit) and the NaN of a
 // negative discriminant (0x7fffffff) compare above +inf: ONE three-input unsigned minimum per sphere replaces four compares and
 // selects on the half-rate ALU pipe; the index follows with one compare and one select.
-#ifdef VPT_SCAN_INLINE // experiment (tools/build_variant.py): one copy per call site instead of one per kernel
-#define VPT_SCAN_LINKAGE __forceinline__
-#else
+// One copy per call site.  Round 1 kept the scan out of line (its megakernels had it at eight divergent sites of one loop body); in the
+// staged kernels a stage has one or two scan sites and every warp of the SM is in the same stage, so the copies cost little instruction
+// cache and save the call (argument / return moves were 4 % of the executed instructions) and let the loads of the first pair overlap the
+// stage's own arithmetic: +2.6 % (equi-angular) / +3.7 % (free flight), profiles/r2_summary.md.  -DVPT_SCAN_OUTLINE restores the call.
+#ifdef VPT_SCAN_OUTLINE
 #define VPT_SCAN_LINKAGE __noinline__
+#else
+#define VPT_SCAN_LINKAGE __forceinline__
 #endif
 static __device__ VPT_SCAN_LINKAGE ScanHit scan_sm_call(float ox, float oy, float oz, float dx, float dy, float dz) {
     const SmScene &S = *reinterpret_cast<const SmScene *>(smwave_smem);
