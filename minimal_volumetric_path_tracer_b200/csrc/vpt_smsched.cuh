@@ -47,9 +47,13 @@ struct SmCtl {
     // [rb_begin + 32 j, min(rb_end, +32)), j = k - rb_first
     __align__(16) unsigned rb_first[8]; // [7] = number of batches of the round
     unsigned rb_begin[8], rb_end[8];
-    // ... and spelled out per batch by the plan, so that a claim costs ONE load: rank (bits 0-2) | records in the batch (3-8) | bits 16-31: ring
-    // index of the batch's first queue entry, or, for a generation batch (rank 6), its number j (samples [rb_begin[6] + 32 j, + 32))
-    unsigned desc[2 * (POOL / 32) + 16];
+    // ... and spelled out per batch, so that a claim costs ONE load: rank (bits 0-2) | records in the batch (3-8) | bits 9-20: ring index of the
+    // batch's first queue entry or, for a generation batch (rank 6), its number j (samples [rb_begin[6] + 32 j, + 32)) | bits 21-31: the round
+    // (mod 2048).  Written right after the plan by ALL warps (a few entries each: SmSched::run), so that the plan itself stays short.
+    static constexpr int kDescMax = 2 * (POOL / 32) + 16;
+    static_assert(POOL <= 4096, "batch descriptors keep a ring index in 12 bits");
+    unsigned desc[kDescMax];
+    unsigned round_no;
     unsigned round_claim;      // next unclaimed batch of the round: one atomicAdd per batch
     unsigned tail_limit;       // camera-sample cursor up to which warps out of batches may generate in this round (tail fill)
     // the 20 words the round plan reads, contiguous: warp 0 fetches them with ONE load (lane i reads word i, see plan_round)
@@ -129,8 +133,9 @@ struct SmSched {
                 Q.t_item[b] = item < n_items ? item : -1; Q.t_cursor[b] = 0u; Q.t_done[b] = 0u;
             }
             Q.next_item = (int)blockIdx.x + 2 * (int)gridDim.x;
-            Q.gen_slot = -1; Q.tail_limit = 0u;
+            Q.gen_slot = -1; Q.tail_limit = 0u; Q.round_no = 0u;
         }
+        for (int i = tid; i < SmCtl<POOL>::kDescMax; i += THREADS) Q.desc[i] = 0xffffffffu; // (no round carries the tag 2047 before the 2047th)
     }
 
     // The claim for the NEXT batch is issued a few hundred cycles before the current one ends (at the start of its last step: the roulette's
@@ -272,25 +277,13 @@ struct SmSched {
         const unsigned first = incl - nb;
         if (lane < 8) { Q.rb_first[lane] = first; Q.rb_begin[lane] = begin; Q.rb_end[lane] = end; }
         const unsigned total = __shfl_sync(0xffffffffu, incl, 7);
-        { // the batch descriptors: lane i writes batches i, i + 32, ...; lane r < 7 holds rank r's first batch / begin / end
-            const unsigned f1 = __shfl_sync(0xffffffffu, first, 1), f2 = __shfl_sync(0xffffffffu, first, 2), f3 = __shfl_sync(0xffffffffu, first, 3);
-            const unsigned f4 = __shfl_sync(0xffffffffu, first, 4), f5 = __shfl_sync(0xffffffffu, first, 5), f6 = __shfl_sync(0xffffffffu, first, 6);
-            for (unsigned k0 = 0; k0 < total; k0 += 32u) { // (warp-uniform trip count: the shuffles below are executed by every lane)
-                const unsigned kk = k0 + (unsigned)lane;
-                const int rank = (kk >= f1) + (kk >= f2) + (kk >= f3) + (kk >= f4) + (kk >= f5) + (kk >= f6);
-                const unsigned rf = __shfl_sync(0xffffffffu, first, rank), rbeg = __shfl_sync(0xffffffffu, begin, rank), rend = __shfl_sync(0xffffffffu, end, rank);
-                const unsigned j = kk - rf, start = rbeg + (j << 5);
-                const unsigned n = min(32u, rend - start);
-                if (kk < total) Q.desc[kk] = (unsigned)rank | (n << 3) | ((rank == SQ_COUNT ? j : ring_index(start)) << 16);
-            }
-        }
         if (lane == 0) {
             const unsigned after = gen_begin + n_gen;                       // the cursor after the planned generation batches
             const unsigned budget = (n_free - n_gen) & ~31u;                // free records the tail fill may use: one per sample, whole batches
             const unsigned limit = min(after + budget, item_total);         // (a last, partial batch of the item needs fewer records than it claims)
             Q.t_cursor[0] = gen == 0 ? after : cur0; Q.t_cursor[1] = gen == 1 ? after : cur1;
             Q.tail_limit = gen >= 0 ? limit : 0u;
-            Q.flush_slot = flush; Q.gen_slot = gen; Q.round_claim = (unsigned)(THREADS / 32);
+            Q.flush_slot = flush; Q.gen_slot = gen; Q.round_claim = (unsigned)(THREADS / 32); Q.round_no = Q.round_no + 1u;
             Q.exit_flag = (total == 0u && flush < 0 && gen < 0) ? 1 : 0; // nothing queued, nothing to generate, nothing to write out
         }
     }
@@ -330,13 +323,28 @@ struct SmSched {
             const unsigned total = Q.rb_first[7];
             const int gen_slot = Q.gen_slot;
             const unsigned gen_begin = Q.rb_begin[SQ_COUNT];
-            // the first batch of a round needs no atomic: warp w takes batch w, the claim counter starts behind those (plan_round)
+            const unsigned tag = (Q.round_no & 0x7ffu) << 21;
+            // the batch table (rb_first / rb_begin / rb_end by rank) -> one descriptor per batch
+            const uint4 f0 = *reinterpret_cast<const uint4 *>(&Q.rb_first[0]), f1 = *reinterpret_cast<const uint4 *>(&Q.rb_first[4]);
+            auto make_desc = [&](unsigned k) -> unsigned {
+                const int rank = (k >= f0.y) + (k >= f0.z) + (k >= f0.w) + (k >= f1.x) + (k >= f1.y) + (k >= f1.z);
+                const unsigned j = k - Q.rb_first[rank], start = Q.rb_begin[rank] + (j << 5);
+                const unsigned n = min(32u, Q.rb_end[rank] - start);
+                return (unsigned)rank | (n << 3) | ((rank == SQ_COUNT ? j : ring_index(start)) << 9) | tag;
+            };
+            { // every warp spells out its share of the table (the plan, on which all warps wait, stays short); a reader checks the round tag
+                constexpr int kPer = (SmCtl<POOL>::kDescMax + THREADS / 32 - 1) / (THREADS / 32);
+                const unsigned k = (unsigned)(tid >> 5) * (unsigned)kPer + (unsigned)lane;
+                if (lane < kPer && k < total) Q.desc[k] = make_desc(k);
+            }
+            // the first batch of a round needs no atomic and no table: warp w takes batch w, the claim counter starts behind those (plan_round)
             unsigned kb = (unsigned)tid >> 5;
+            unsigned dsc = kb < total ? make_desc(kb) : 0u;
             while (kb < total) {
-                const unsigned dsc = Q.desc[kb];
                 const int rank = (int)(dsc & 7u), n = (int)((dsc >> 3) & 63u);
-                const unsigned start = gen_begin + ((dsc >> 16) << 5); // (generation batches only)
-                const unsigned e = ring_index((dsc >> 16) + (unsigned)lane); // this lane's queue entry
+                const unsigned idx = (dsc >> 9) & 0xfffu;
+                const unsigned start = gen_begin + (idx << 5);             // (generation batches only)
+                const unsigned e = ring_index(idx + (unsigned)lane);       // this lane's queue entry
                 switch (rank) {
                 case 0: SMW_BATCH(SQ_SURF_F, self().template run_stage<SQ_SURF_F>(lane < n ? (int)Q.queue[SQ_SURF_F][e] : -1)); break;
                 case 1: SMW_BATCH(SQ_SURF_L, self().template run_stage<SQ_SURF_L>(lane < n ? (int)Q.queue[SQ_SURF_L][e] : -1)); break;
@@ -350,6 +358,7 @@ struct SmSched {
                 // (taking ALL batches round-robin without atomics: 6750 against 7340 -- the dynamic claim is what balances 12 000-cycle SURF_L batches
                 // against 4 000-cycle ones)
                 kb = __shfl_sync(0xffffffffu, next_raw, 0);
+                if (kb < total) do { dsc = *(volatile unsigned *)&Q.desc[kb]; } while ((dsc ^ tag) >> 21); // (written thousands of cycles ago: never loops)
             }
             // tail fill: the round's batches are all claimed; instead of idling at the barrier generate camera samples up to the limit the
             // plan set (one free record per sample is guaranteed), they are consumed in the next round.  One atomic per batch.
