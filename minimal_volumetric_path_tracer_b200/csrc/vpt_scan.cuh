@@ -2,7 +2,7 @@
 //
 // intersect (pathTracingUtilities.h:12-36) over Sphere::intersect (Sphere.h:27-37), FP32 semantics (include/vpt.h): r == 0 spheres have no
 // scan record.  One out-of-line copy (scan_sm_call) serves the product wavefront, the HBM wavefront, the megakernel, the ray marcher and
-// the unit kernels; the per-pair root arithmetic lives in pair_general / pair_direct, which VPT_UNIT_SPHERE_INTERSECT evaluates directly.
+// the unit kernels; the per-pair root arithmetic lives in pair_general_* / pair_direct_*, which VPT_UNIT_SPHERE_INTERSECT evaluates directly.
 //   * scan records are staged in shared memory as float4 and read with broadcast LDS.128;
 //   * ordinary spheres (r < 64) take the roots directly as -b -+ sqrt(det) with det = r^2 - |op - (op.d)d|^2 (no cancellation for small
 //     far-away spheres); spheres with r >= 64 (the r = 1e5 walls of Sphere.cpp:11-15 above all) use the re-anchored cancellation-free
@@ -82,38 +82,57 @@ __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(neg_fold(a
 __device__ __forceinline__ float2 lo2(float4 v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 hi2(float4 v) { return make_float2(v.z, v.w); }
 
-struct Ray2 { float2 ox, oy, oz, dx, dy, dz; }; // the ray with every component broadcast to both packed lanes
-__device__ __forceinline__ Ray2 ray2(float ox, float oy, float oz, float dx, float dy, float dz) {
-    return Ray2{make_float2(ox, ox), make_float2(oy, oy), make_float2(oz, oz), make_float2(dx, dx), make_float2(dy, dy), make_float2(dz, dz)};
+// The pair arithmetic in two parts: what depends on the ray's ORIGIN only (shared by all rays that start at the same point -- the three
+// next-event rays of a surface vertex, scan_sm_n) and what depends on its direction.  Every add / multiply / fma is one packed instruction for
+// both spheres of the pair (same IEEE roundings as a scalar, one-sphere-at-a-time form); the ray's components are broadcast operands.
+struct Org2 { float2 x, y, z; };  // origin, each component broadcast to both packed lanes
+struct Dir2 { float2 x, y, z; };
+__device__ __forceinline__ Org2 org2(F3 o) { return Org2{make_float2(o.x, o.x), make_float2(o.y, o.y), make_float2(o.z, o.z)}; }
+__device__ __forceinline__ Dir2 dir2(F3 d) { return Dir2{make_float2(d.x, d.x), make_float2(d.y, d.y), make_float2(d.z, d.z)}; }
+struct PairG { float2 opx, opy, opz, c; }; // general form: o - p and |o - p|^2 - r^2 (without cancellation)
+struct PairD { float2 oqx, oqy, oqz, r2; }; // direct-root form: o - p and r^2
+__device__ __forceinline__ PairG pair_general_origin(const float4 *__restrict__ rec, const Org2 &o) {
+    const float4 A = rec[0], B = rec[1], C = rec[2], E = rec[3];
+    const float2 mx = lo2(C), my = hi2(C), mz = lo2(E);
+    const float2 oqx = __fadd2_rn(o.x, neg2(lo2(A))), oqy = __fadd2_rn(o.y, neg2(hi2(A))), oqz = __fadd2_rn(o.z, neg2(lo2(B)));
+    PairG g;
+    g.opx = __fadd2_rn(oqx, mx); g.opy = __fadd2_rn(oqy, my); g.opz = __fadd2_rn(oqz, mz);
+    g.c = __ffma2_rn(oqx, __fadd2_rn(g.opx, mx), __ffma2_rn(oqy, __fadd2_rn(g.opy, my), __ffma2_rn(oqz, __fadd2_rn(g.opz, mz), hi2(B))));
+    return g;
 }
 // The two roots of both spheres of a pair, each MINUS 1e-4 (w = root - eps: see scan_sm_call).  NaN when the ray misses (det < 0).
-// Every add / multiply / fma is one packed instruction for both spheres (same IEEE roundings as a scalar, one-sphere-at-a-time form).
-__device__ __forceinline__ void pair_general(const float4 *__restrict__ rec, const Ray2 &r, float2 &w1, float2 &w2) {
-    const float4 A = rec[0], B = rec[1], C = rec[2], E = rec[3];
+__device__ __forceinline__ void pair_general_dir(const PairG &g, const Dir2 &d, float2 &w1, float2 &w2) {
     const float2 meps = make_float2(-kEps, -kEps);
-    const float2 mx = lo2(C), my = hi2(C), mz = lo2(E);
-    const float2 oqx = __fadd2_rn(r.ox, neg2(lo2(A))), oqy = __fadd2_rn(r.oy, neg2(hi2(A))), oqz = __fadd2_rn(r.oz, neg2(lo2(B)));
-    const float2 opx = __fadd2_rn(oqx, mx), opy = __fadd2_rn(oqy, my), opz = __fadd2_rn(oqz, mz);
-    const float2 b = __ffma2_rn(opx, r.dx, __ffma2_rn(opy, r.dy, __fmul2_rn(opz, r.dz)));
-    const float2 c = __ffma2_rn(oqx, __fadd2_rn(opx, mx), __ffma2_rn(oqy, __fadd2_rn(opy, my), __ffma2_rn(oqz, __fadd2_rn(opz, mz), hi2(B)))); // |op|^2 - r^2 without cancellation
-    const float2 det = __ffma2_rn(b, b, neg2(c));
+    const float2 b = __ffma2_rn(g.opx, d.x, __ffma2_rn(g.opy, d.y, __fmul2_rn(g.opz, d.z)));
+    const float2 det = __ffma2_rn(b, b, neg2(g.c));
     const float2 sq = __fmul2_rn(det, make_float2(rsqrtf(det.x), rsqrtf(det.y))); // NaN when det <= 0
     const float2 q = __fadd2_rn(neg2(b), neg2(make_float2(copysignf(sq.x, b.x), copysignf(sq.y, b.y)))); // the root without cancellation; the other one is c / q
     w1 = __fadd2_rn(q, meps);
-    w2 = __ffma2_rn(c, make_float2(rcp_approx(q.x), rcp_approx(q.y)), meps);
+    w2 = __ffma2_rn(g.c, make_float2(rcp_approx(q.x), rcp_approx(q.y)), meps);
 }
-__device__ __forceinline__ void pair_direct(const float4 *__restrict__ rec, const Ray2 &r, float2 &w1, float2 &w2) {
+__device__ __forceinline__ PairD pair_direct_origin(const float4 *__restrict__ rec, const Org2 &o) {
     const float4 A = rec[0], B = rec[1];
+    return PairD{__fadd2_rn(o.x, neg2(lo2(A))), __fadd2_rn(o.y, neg2(hi2(A))), __fadd2_rn(o.z, neg2(lo2(B))), hi2(B)};
+}
+__device__ __forceinline__ void pair_direct_dir(const PairD &g, const Dir2 &d, float2 &w1, float2 &w2) {
     const float2 meps = make_float2(-kEps, -kEps);
-    const float2 oqx = __fadd2_rn(r.ox, neg2(lo2(A))), oqy = __fadd2_rn(r.oy, neg2(hi2(A))), oqz = __fadd2_rn(r.oz, neg2(lo2(B)));
-    const float2 b = __ffma2_rn(oqx, r.dx, __ffma2_rn(oqy, r.dy, __fmul2_rn(oqz, r.dz)));
+    const float2 b = __ffma2_rn(g.oqx, d.x, __ffma2_rn(g.oqy, d.y, __fmul2_rn(g.oqz, d.z)));
     const float2 nb2 = neg2(b);
-    const float2 lx = __ffma2_rn(r.dx, nb2, oqx), ly = __ffma2_rn(r.dy, nb2, oqy), lz = __ffma2_rn(r.dz, nb2, oqz);
-    const float2 det = __ffma2_rn(neg2(lx), lx, __ffma2_rn(neg2(ly), ly, __ffma2_rn(neg2(lz), lz, hi2(B))));
+    const float2 lx = __ffma2_rn(d.x, nb2, g.oqx), ly = __ffma2_rn(d.y, nb2, g.oqy), lz = __ffma2_rn(d.z, nb2, g.oqz);
+    const float2 det = __ffma2_rn(neg2(lx), lx, __ffma2_rn(neg2(ly), ly, __ffma2_rn(neg2(lz), lz, g.r2)));
     const float2 sq = __fmul2_rn(det, make_float2(rsqrtf(det.x), rsqrtf(det.y)));
     const float2 nbe = __fadd2_rn(nb2, meps);
     w1 = __fadd2_rn(nbe, neg2(sq));
     w2 = __fadd2_rn(nbe, sq);
+}
+// the smaller accepted root of the pair's two spheres against the best so far (see scan_sm_call), slot = the pair's first scan slot
+__device__ __forceinline__ void pair_select(unsigned &best, int &bi, int slot, float2 w1, float2 w2) {
+    unsigned k = __vimin3_u32(best, __float_as_uint(w1.x), __float_as_uint(w2.x));
+    if (k != best) bi = slot;
+    best = k;
+    k = __vimin3_u32(best, __float_as_uint(w1.y), __float_as_uint(w2.y));
+    if (k != best) bi = slot + 1;
+    best = k;
 }
 
 // nearest accepted hit over all spheres: distance (+inf: none) and scan index.
@@ -136,28 +155,58 @@ static __device__ VPT_SCAN_LINKAGE ScanHit scan_sm_call(float ox, float oy, floa
     unsigned best = 0x7f800000u; // +inf
     int bi = -1;
     const int na = S.n_pa, nb = S.n_pb;
-    const Ray2 r = ray2(ox, oy, oz, dx, dy, dz);
+    const Org2 o = org2(mk(ox, oy, oz));
+    const Dir2 d = dir2(mk(dx, dy, dz));
     for (int j = 0; j < na; ++j) {
         float2 w1, w2;
-        pair_general(&S.ga[4 * j], r, w1, w2);
-        unsigned k = __vimin3_u32(best, __float_as_uint(w1.x), __float_as_uint(w2.x));
-        if (k != best) bi = 2 * j;
-        best = k;
-        k = __vimin3_u32(best, __float_as_uint(w1.y), __float_as_uint(w2.y));
-        if (k != best) bi = 2 * j + 1;
-        best = k;
+        pair_general_dir(pair_general_origin(&S.ga[4 * j], o), d, w1, w2);
+        pair_select(best, bi, 2 * j, w1, w2);
     }
     for (int j = 0; j < nb; ++j) {
         float2 w1, w2;
-        pair_direct(&S.gb[2 * j], r, w1, w2);
-        unsigned k = __vimin3_u32(best, __float_as_uint(w1.x), __float_as_uint(w2.x));
-        if (k != best) bi = 2 * (na + j);
-        best = k;
-        k = __vimin3_u32(best, __float_as_uint(w1.y), __float_as_uint(w2.y));
-        if (k != best) bi = 2 * (na + j) + 1;
-        best = k;
+        pair_direct_dir(pair_direct_origin(&S.gb[2 * j], o), d, w1, w2);
+        pair_select(best, bi, 2 * (na + j), w1, w2);
     }
     return ScanHit{__uint_as_float(best) + kEps, bi};
+}
+// N rays from ONE origin in one pass over the spheres: the records are loaded once and the origin part of every pair (o - p, and for the
+// general form |o - p|^2 - r^2: 28 of its 46 instructions) is computed once; the N direction parts are independent chains (instruction-
+// level parallelism for a kernel that is latency bound at six warps per scheduler).  Per ray the same operations on the same values as
+// scan_sm: identical results.  Used by the surface stages, whose next-event rays (one per area light + the BSDF-sampled one) share the
+// vertex (vpt_stages.cuh stage_surf).
+template <int N>
+__device__ __forceinline__ void scan_sm_n(const SmScene &S, F3 o, const F3 *d, bool *hit, float *t, int *id) {
+    unsigned best[N];
+    int bi[N];
+    Dir2 dd[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) { best[n] = 0x7f800000u; bi[n] = -1; dd[n] = dir2(d[n]); }
+    const int na = S.n_pa, nb = S.n_pb;
+    const Org2 oo = org2(o);
+    for (int j = 0; j < na; ++j) {
+        const PairG g = pair_general_origin(&S.ga[4 * j], oo);
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+            float2 w1, w2;
+            pair_general_dir(g, dd[n], w1, w2);
+            pair_select(best[n], bi[n], 2 * j, w1, w2);
+        }
+    }
+    for (int j = 0; j < nb; ++j) {
+        const PairD g = pair_direct_origin(&S.gb[2 * j], oo);
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+            float2 w1, w2;
+            pair_direct_dir(g, dd[n], w1, w2);
+            pair_select(best[n], bi[n], 2 * (na + j), w1, w2);
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        t[n] = __uint_as_float(best[n]) + kEps;
+        hit[n] = bi[n] >= 0;
+        id[n] = bi[n] >= 0 ? S.gid[bi[n]] : -1;
+    }
 }
 __device__ __forceinline__ bool scan_sm(const SmScene &S, F3 o, F3 d, float &t, int &id) {
     const ScanHit h = scan_sm_call(o.x, o.y, o.z, d.x, d.y, d.z);
@@ -169,13 +218,14 @@ __device__ __forceinline__ bool scan_sm(const SmScene &S, F3 o, F3 d, float &t, 
 // Sphere::intersect (Sphere.h:27-37) for ONE sphere through the scan's own pair arithmetic: the near root unless it is negative or within
 // 1e-4 of the origin, else the far one (which may be negative); 0 when the ray misses or the sphere has no scan record (r == 0).
 __device__ __forceinline__ float sphere_t_sm(const SmScene &S, int sphere, F3 o, F3 d) {
-    const Ray2 r = ray2(o.x, o.y, o.z, d.x, d.y, d.z);
+    const Org2 oo = org2(o);
+    const Dir2 dd = dir2(d);
     const int n_slots = 2 * (S.n_pa + S.n_pb);
     for (int slot = 0; slot < n_slots; ++slot) {
         if (S.gid[slot] != sphere) continue;
         float2 w1, w2;
-        if (slot < 2 * S.n_pa) pair_general(&S.ga[4 * (slot >> 1)], r, w1, w2);
-        else pair_direct(&S.gb[2 * ((slot - 2 * S.n_pa) >> 1)], r, w1, w2);
+        if (slot < 2 * S.n_pa) pair_general_dir(pair_general_origin(&S.ga[4 * (slot >> 1)], oo), dd, w1, w2);
+        else pair_direct_dir(pair_direct_origin(&S.gb[2 * ((slot - 2 * S.n_pa) >> 1)], oo), dd, w1, w2);
         const float a = ((slot & 1) ? w1.y : w1.x) + kEps, b = ((slot & 1) ? w2.y : w2.x) + kEps;
         if (!(a == a) || !(b == b)) return 0.0f;
         const float t_near = fminf(a, b), t_far = fmaxf(a, b);

@@ -193,7 +193,11 @@ __device__ __forceinline__ int stage_surf_p(C &c, bool act, Rec &r) {
 }
 
 // ---- SURF: MISv2 (misSamplingFunctions.h:96-170) + bdsf (vptShadeMethods.h:16-59) + roulette ----------------------------------------------
-// FACET = false: Lambert (material 0); true: Beckmann conductor (1) and the dielectric as written in the reference (2)
+// FACET = false: Lambert (material 0); true: Beckmann conductor (1) and the dielectric as written in the reference (2).
+// The vertex's next-event rays -- one cone-sampled ray per area light (muestreoSA) and the BSDF-sampled ray -- all start at the vertex:
+// they are scanned together, two area lights per pass and the last one or two together with the BSDF-sampled ray (scan_sm_n: one pass
+// over the spheres, origin part of every sphere test shared).  The terms are added in the reference's order (lights, then the BSDF term).
+struct LightRay { F3 wi; float omc_max, len2, inv_len; int lid; };
 template <bool FACET, class C>
 __device__ __forceinline__ int stage_surf(C &c, bool act, Rec &r) {
     const F3 o = r.o, d = r.d, beta = r.beta;
@@ -203,74 +207,123 @@ __device__ __forceinline__ int stage_surf(C &c, bool act, Rec &r) {
     const F3 wo_l = FACET ? unit(to_local(fr, -d)) : mk(0, 0, 1);
     const F3 albedo = mk(obj.cr, obj.cg, obj.cb);
     F3 L = mk(0.0f, 0.0f, 0.0f); // this vertex's direct light, before throughput and 1 / cp
-    float omc_last = 1.0f;
-    // material 2 shares this stage with the microfacet: its light-sampled terms are zero (samplingFunctions.h:190), the loop below only runs
-    // its scans in step with the other lanes
+    // material 2 shares this stage with the microfacet: its light-sampled terms are zero (samplingFunctions.h:190), its lanes only run the
+    // light scans in step with the others
     const bool diel = FACET && obj.material == 2;
     DielF di; di.F = 0.0f; di.wr = di.wt = mk(0, 0, 1);
     if (diel) di = dielectric_setup(wo_l);
-    float gpdf_loop = 0.0f; // the pdf the reference's light loop leaves behind for the dielectric's BSDF term (misSamplingFunctions.h:110-118,148)
-    bool refracted = false;
-    float4 ra = make_float4(0, 0, 0, 0);
     const int n_area = c.S.n_area;
-    for (int a = 0; a < n_area; ++a) { // muestreoSA for every area light (misSamplingFunctions.h:105-118)
-        if ((a & 1) == 0) ra = c.rnd(r, 2 + (a >> 1));
-        const float xi1 = (a & 1) ? ra.z : ra.x, xi2 = (a & 1) ? ra.w : ra.y;
-        const int lid = c.S.area[a];
-        const MatF &sm = c.S.mats[lid];
+    float omc_tail = 1.0f; // (FACET: 1 - costhetaMax of the last light of the ray-by-ray loop)
+
+    // muestreoSA (misSamplingFunctions.h:105-118): aim at area light a, and what a hit of it contributes
+    auto aim = [&](int a, float xi1, float xi2) -> LightRay {
+        LightRay q;
+        q.lid = c.S.area[a];
+        const MatF &sm = c.S.mats[q.lid];
         const F3 cx = mk(sm.px, sm.py, sm.pz) - o;
-        const float len2 = dot(cx, cx), inv_len = rsqrtf(len2);
-        const float omc_max = one_minus_cos_max(sm.r * sm.r / len2);
-        omc_last = omc_max;
-        const F3 wi = cone_sample(cx * inv_len, omc_max, xi1, xi2);
-        float t; int hid;
-        const bool hit = c.scan(o, wi, t, hid);
+        q.len2 = dot(cx, cx); q.inv_len = rsqrtf(q.len2);
+        q.omc_max = one_minus_cos_max(sm.r * sm.r / q.len2);
+        q.wi = cone_sample(cx * q.inv_len, q.omc_max, xi1, xi2);
+        return q;
+    };
+    auto shade_light = [&](const LightRay &q, bool hit, int hid) {
         c.scans += act ? 1u : 0u;
-        if (act && (hit ? hid : 0) == lid && !diel) { // id stays 0 on a miss, samplingFunctions.h:196
-            const float cos_i = dot(n_, wi);
+        if (act && (hit ? hid : 0) == q.lid && !diel) { // id stays 0 on a miss, samplingFunctions.h:196
+            const MatF &sm = c.S.mats[q.lid];
+            const float cos_i = dot(n_, q.wi);
             F3 f = albedo * kInvPi;
             float gpdf = cos_i * kInvPi;
-            if (FACET) { const F3 wi_l = unit(to_local(fr, wi)); const F3 wh = unit(wi_l + wo_l); f = facet_brdf(obj, wi_l, wh, wo_l); gpdf = facet_pdf(wo_l, wh, obj.alpha); }
-            const float inv_fpdf = kTwoPi * omc_max;
+            if (FACET) { const F3 wi_l = unit(to_local(fr, q.wi)); const F3 wh = unit(wi_l + wo_l); f = facet_brdf(obj, wi_l, wh, wo_l); gpdf = facet_pdf(wo_l, wh, obj.alpha); }
+            const float inv_fpdf = kTwoPi * q.omc_max;
             const float wmis = power_heuristic(1.0f / inv_fpdf, gpdf);
-            L = L + had(mk(sm.lr, sm.lg, sm.lb), f) * (cos_i * inv_fpdf * transmit(c.k.sigma_t * len2 * inv_len) * wmis);
+            L = L + had(mk(sm.lr, sm.lg, sm.lb), f) * (cos_i * inv_fpdf * transmit(c.k.sigma_t * q.len2 * q.inv_len) * wmis);
+        }
+    };
+
+    // (the rare microfacet / dielectric stage scans ray by ray: one copy of the scan instead of four keeps its code small)
+    constexpr bool kFuse = !FACET;
+    int a = 0;
+    if (!kFuse) {
+        float4 ra = make_float4(0, 0, 0, 0);
+        for (; a < n_area; ++a) {
+            if ((a & 1) == 0) ra = c.rnd(r, 2 + (a >> 1));
+            const LightRay q = aim(a, (a & 1) ? ra.z : ra.x, (a & 1) ? ra.w : ra.y);
+            float t; int hid;
+            const bool hit = c.scan(o, q.wi, t, hid);
+            shade_light(q, hit, hid);
+            if (a == n_area - 1) omc_tail = q.omc_max;
         }
     }
+    while (kFuse && n_area - a > 2) { // two area lights per pass while more than two are left (their cone numbers share one Philox block)
+        const float4 ra = c.rnd(r, 2 + (a >> 1));
+        const LightRay q0 = aim(a, ra.x, ra.y), q1 = aim(a + 1, ra.z, ra.w);
+        const F3 dirs[2] = {q0.wi, q1.wi};
+        bool hit[2]; float t[2]; int hid[2];
+        scan_sm_n<2>(c.S, o, dirs, hit, t, hid);
+        shade_light(q0, hit[0], hid[0]);
+        shade_light(q1, hit[1], hid[1]);
+        a += 2;
+    }
+    // the last pass: the remaining 0, 1 or 2 area lights and the BSDF-sampled ray of MISv2 (:124-167)
+    const int left = n_area - a;
+    LightRay q0, q1;
+    q0.wi = q1.wi = mk(0, 0, 1); q0.omc_max = q1.omc_max = 1.0f; q0.len2 = q1.len2 = q0.inv_len = q1.inv_len = 1.0f; q0.lid = q1.lid = -1;
+    if (left > 0) {
+        const float4 ra = c.rnd(r, 2 + (a >> 1));
+        q0 = aim(a, ra.x, ra.y);
+        if (left > 1) q1 = aim(a + 1, ra.z, ra.w);
+    }
+    const float omc_last = n_area == 0 ? 1.0f : (left > 1 ? q1.omc_max : (left > 0 ? q0.omc_max : omc_tail)); // 1 - costhetaMax of the last light visited (:162); 1 = "cos 0"
     const float4 b1 = c.rnd(r, 1);
-    { // the BSDF-sampled term of MISv2 (:124-167): slots S_MIS = lanes 2,3 of block 1
-        const float xi1 = b1.z, xi2 = b1.w;
-        F3 wi_l, wh = mk(0, 0, 1);
-        if (FACET) {
-            wh = facet_normal(obj.alpha, xi1, xi2); wi_l = unit(fma3(wh, 2.0f * dot(wh, wo_l), -wo_l));
-            if (diel) { // softDielectric (samplingFunctions.h:209-235): reflect with probability F, else the reference's refraction
-                if (n_area > 0) {
-                    const uint32_t slot = S_DIEL + (uint32_t)n_area - 1u;
-                    const float4 bd = c.rnd(r, slot >> 2);
-                    const float xg = (slot & 3u) == 0u ? bd.x : (slot & 3u) == 1u ? bd.y : (slot & 3u) == 2u ? bd.z : bd.w;
-                    gpdf_loop = xg > di.F ? 1.0f - di.F : di.F;
-                }
-                refracted = !(xi1 < di.F);
-                wi_l = refracted ? di.wt : di.wr;
+    // slots S_MIS = lanes 2, 3 of block 1
+    const float xi1 = b1.z, xi2 = b1.w;
+    F3 wi_l, wh = mk(0, 0, 1);
+    float gpdf_loop = 0.0f; // the pdf the reference's light loop leaves behind for the dielectric's BSDF term (misSamplingFunctions.h:110-118,148)
+    bool refracted = false;
+    if (FACET) {
+        wh = facet_normal(obj.alpha, xi1, xi2); wi_l = unit(fma3(wh, 2.0f * dot(wh, wo_l), -wo_l));
+        if (diel) { // softDielectric (samplingFunctions.h:209-235): reflect with probability F, else the reference's refraction
+            if (n_area > 0) {
+                const uint32_t slot = S_DIEL + (uint32_t)n_area - 1u;
+                const float4 bd = c.rnd(r, slot >> 2);
+                const float xg = (slot & 3u) == 0u ? bd.x : (slot & 3u) == 1u ? bd.y : (slot & 3u) == 2u ? bd.z : bd.w;
+                gpdf_loop = xg > di.F ? 1.0f - di.F : di.F;
             }
-        } else wi_l = cosine_local(xi1, xi2);
-        const F3 wi = unit(to_world(fr, wi_l));
-        float t; int hid;
-        const bool hit = c.scan(o, wi, t, hid);
-        c.scans += act ? 1u : 0u;
-        if (act && hit && c.S.mats[hid].emits) {
-            const MatF &em = c.S.mats[hid];
-            const F3 cx = mk(em.px, em.py, em.pz) - o;
-            float omc = one_minus_cos_max(em.r * em.r / dot(cx, cx));
-            if (diel) L = L + dielectric_direct(em, o, wi_l.z, refracted, gpdf_loop);
-            else if (FACET) {
-                const float gpdf = facet_pdf(wo_l, wh, obj.alpha);
-                const F3 g = had(mk(em.lr, em.lg, em.lb), facet_brdf(obj, wi_l, wh, wo_l)) * (wi_l.z / gpdf);
-                if (!(g.x > 0.0f)) omc = omc_last; // the reference's stale costhetaMax (:162)
-                L = L + g * power_heuristic(gpdf, 1.0f / (kTwoPi * omc));
-            } else {
-                const F3 g = had(mk(em.lr, em.lg, em.lb), albedo); // Le c/pi cos / (cos/pi)
-                if (g.x > 0.0f && g.y > 0.0f && g.z > 0.0f) L = L + g * power_heuristic(dot(n_, wi) * kInvPi, 1.0f / (kTwoPi * omc));
-            }
+            refracted = !(xi1 < di.F);
+            wi_l = refracted ? di.wt : di.wr;
+        }
+    } else wi_l = cosine_local(xi1, xi2);
+    const F3 wi_b = unit(to_world(fr, wi_l));
+    bool hit_b; float t_b; int hid_b;
+    if (kFuse && left == 2) {
+        const F3 dirs[3] = {q0.wi, q1.wi, wi_b};
+        bool hit[3]; float t[3]; int hid[3];
+        scan_sm_n<3>(c.S, o, dirs, hit, t, hid);
+        shade_light(q0, hit[0], hid[0]);
+        shade_light(q1, hit[1], hid[1]);
+        hit_b = hit[2]; t_b = t[2]; hid_b = hid[2];
+    } else if (kFuse && left == 1) {
+        const F3 dirs[2] = {q0.wi, wi_b};
+        bool hit[2]; float t[2]; int hid[2];
+        scan_sm_n<2>(c.S, o, dirs, hit, t, hid);
+        shade_light(q0, hit[0], hid[0]);
+        hit_b = hit[1]; t_b = t[1]; hid_b = hid[1];
+    } else hit_b = c.scan(o, wi_b, t_b, hid_b);
+    (void)t_b;
+    c.scans += act ? 1u : 0u;
+    if (act && hit_b && c.S.mats[hid_b].emits) {
+        const MatF &em = c.S.mats[hid_b];
+        const F3 cx = mk(em.px, em.py, em.pz) - o;
+        float omc = one_minus_cos_max(em.r * em.r / dot(cx, cx));
+        if (diel) L = L + dielectric_direct(em, o, wi_l.z, refracted, gpdf_loop);
+        else if (FACET) {
+            const float gpdf = facet_pdf(wo_l, wh, obj.alpha);
+            const F3 g = had(mk(em.lr, em.lg, em.lb), facet_brdf(obj, wi_l, wh, wo_l)) * (wi_l.z / gpdf);
+            if (!(g.x > 0.0f)) omc = omc_last; // the reference's stale costhetaMax (:162)
+            L = L + g * power_heuristic(gpdf, 1.0f / (kTwoPi * omc));
+        } else {
+            const F3 g = had(mk(em.lr, em.lg, em.lb), albedo); // Le c/pi cos / (cos/pi)
+            if (g.x > 0.0f && g.y > 0.0f && g.z > 0.0f) L = L + g * power_heuristic(dot(n_, wi_b) * kInvPi, 1.0f / (kTwoPi * omc));
         }
     }
     if (act) c.add(r, had(L, beta) * c.k.inv_cp); // :1321

@@ -446,3 +446,37 @@ def test_auto_kernel_per_path_parity_on_a_scene_not_in_the_reference(gpu, l1, me
     ref8, _, _ = l1.render(sc, 0, method, SA, SS, w, h, 31, 8, want_sumsq=False)
     e8 = np.abs(img8 - ref8) / np.maximum(np.abs(ref8), 1e-3)
     assert np.median(e8) < 2e-6 and np.mean(e8 > 1e-3) < 0.03
+
+
+def test_concurrent_renders_with_different_seeds(gpu):
+    """the product kernel reads its Philox round keys from constant memory, one schedule per device at a time (csrc/vpt_kernels_f32.cu
+    philox_keys_begin): launches of different seeds from different host threads / streams must order themselves on the device.  Four threads
+    with four seeds (and two frame sizes, so that launches overlap differently) render concurrently; every frame must equal the frame the
+    same parameters give alone."""
+    import threading
+    jobs = [gpu.default_params(width=w, height=h, spp=spp, method=m, seed=s, output=gpu.OUTPUT_SUM)
+            for (w, h, spp, m, s) in ((320, 240, 24, 1, 11), (256, 192, 40, 0, 12), (320, 240, 24, 2, 13), (192, 144, 64, 4, 14))]
+    want = [gpu.render(p) for p in jobs]
+    errors = []
+
+    def work(i):
+        try:
+            for _ in range(12):
+                if not np.array_equal(gpu.render(jobs[i]), want[i]):
+                    errors.append("job %d: frame differs under concurrency" % i)
+                    return
+        except Exception as e:  # noqa: BLE001
+            errors.append("job %d: %r" % (i, e))
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    # same seed on two threads: both share the schedule, nothing waits
+    same = [threading.Thread(target=work, args=(0,)) for _ in range(3)]
+    for t in same:
+        t.start()
+    for t in same:
+        t.join()
+    assert not errors, errors
