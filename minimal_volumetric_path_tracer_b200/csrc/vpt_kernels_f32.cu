@@ -45,6 +45,8 @@ __global__ void __launch_bounds__(kThreadsPerBlock) render_f32_kernel(const __gr
     SmScene &S = *reinterpret_cast<SmScene *>(smwave_smem);
     stage_scene(S, sc, (int)threadIdx.x, (int)blockDim.x);
     __syncthreads();
+    stage_scene_tables(S, (int)threadIdx.x, (int)blockDim.x);
+    __syncthreads();
     const long long tile = (long long)blockIdx.x * lp.tile_count + lp.tile_rank;
     const long long pixel = tile * kTile + threadIdx.x;
     if (pixel >= lp.n_pixels) return;
@@ -77,6 +79,8 @@ __global__ void __launch_bounds__(kSmThreads, 1) render_f32_smwave_kernel(const 
         M.ox[0] = M.oy[0] = M.oz[0] = 0.0f; M.dx[0] = M.dy[0] = 0.0f; M.dz[0] = 1.0f; M.br[0] = M.bg[0] = M.bb[0] = 0.0f;
         M.sample[0] = 0u; M.xd[0] = M.xs[0] = 0.5f;
     }
+    __syncthreads();
+    stage_scene_tables(M.scene, tid, kSmThreads);
     SmWave<METHOD> wf(M, cf, lp, log_p, n_owned_tiles, zero);
     wf.init(n_items);
     __syncthreads();
@@ -279,6 +283,8 @@ __global__ void unit_f32_kernel(int fn, const __grid_constant__ SceneF sc, const
                                 int in_stride, double *__restrict__ out, int out_stride) {
     SmScene &PS = *reinterpret_cast<SmScene *>(smwave_smem); // the product kernel's scene (dynamic shared memory): same staging, same scan
     stage_scene(PS, sc, (int)threadIdx.x, (int)blockDim.x);
+    __syncthreads();
+    stage_scene_tables(PS, (int)threadIdx.x, (int)blockDim.x);
     __syncthreads();
     const MatF *mats = PS.mats;
     const int row = blockIdx.x * blockDim.x + threadIdx.x;

@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(kHbmThreads) hbm_stage_kernel(const __grid_con
     stage_scene(S, sc, (int)threadIdx.x, (int)blockDim.x);
     if (threadIdx.x < 8) blk_cnt[threadIdx.x] = 0u;
     __syncthreads();
+    if (STAGE == SQ_MED_POINT || STAGE == SQ_SURF_P) { stage_scene_tables(S, (int)threadIdx.x, (int)blockDim.x); __syncthreads(); }
     HbmCtx C(S, cf, lp, H);
     const unsigned lane = threadIdx.x & 31u;
     for (unsigned first = blockIdx.x * blockDim.x; first < n; first += per_pass) { // block-uniform trip count

@@ -28,7 +28,13 @@ struct SmScene {
     int n_emitters, n_area;
     int emitters[kMaxEmitters]; // spheres with any radiance channel > 0 (vptShadeMethods.h:1296), in index order
     int area[kMaxEmitters];     // spheres with r > 0 && radiance.x > 0 (misSamplingFunctions.h:106), in index order
+    // Shadow rays of a point light start AT the light (visibility, pathTracingUtilities.h:39-53): the origin part of every sphere test is
+    // the same for all of them.  Tables of it for the first kLightTables point lights (stage_scene_tables), used by scan_sm_light.
+    int light_slot[kMaxSpheres];                           // sphere index -> table, -1: none
+    float4 lg[4][kMaxSpheres / 2][2];                      // general-form pair j seen from the light: PairG (opx opy) (opz c)
+    float4 ld[4][kMaxSpheres / 2][2];                      // direct-root pair j: PairD (oqx oqy) (oqz r2)
 };
+constexpr int kLightTables = 4;
 // cooperative staging by the whole block (call, then __syncthreads).  Scan order: general-form spheres first, in scene order, then the
 // direct-root ones; every scan record finds its place with one pass over its predecessors.  An odd class is padded with a record that no
 // ray can hit (negative discriminant for every ray).
@@ -36,6 +42,15 @@ __device__ __forceinline__ void stage_scene(SmScene &S, const SceneF &sc, int ti
     for (int i = tid; i < sc.n_spheres * (int)(sizeof(MatF) / 4); i += n_threads)
         reinterpret_cast<uint32_t *>(S.mats)[i] = reinterpret_cast<const uint32_t *>(sc.mat)[i];
     for (int i = tid; i < kMaxEmitters; i += n_threads) { S.emitters[i] = sc.emitters[i]; S.area[i] = sc.area[i]; }
+    for (int i = tid; i < kMaxSpheres; i += n_threads) { // the first kLightTables point lights (r == 0 emitters), in index order, get a table
+        int slot = -1;
+        if (i < sc.n_spheres && sc.mat[i].emits && sc.mat[i].r == 0.0f) {
+            slot = 0;
+            for (int j = 0; j < i; ++j) slot += (sc.mat[j].emits && sc.mat[j].r == 0.0f);
+            if (slot >= kLightTables) slot = -1;
+        }
+        S.light_slot[i] = slot;
+    }
     int n_general = 0;
     for (int g = 0; g < sc.n_geom; ++g) n_general += (sc.geom[g].big || sc.geom[g].r2 >= kSimpleRootMaxR2);
     const int n_direct = sc.n_geom - n_general, n_pa = (n_general + 1) >> 1, n_pb = (n_direct + 1) >> 1;
@@ -213,6 +228,49 @@ __device__ __forceinline__ bool scan_sm(const SmScene &S, F3 o, F3 d, float &t, 
     t = h.t;
     id = h.index >= 0 ? S.gid[h.index] : -1;
     return h.index >= 0;
+}
+
+// second staging phase (after the __syncthreads that follows stage_scene; then __syncthreads again): the per-light origin tables
+__device__ __forceinline__ void stage_scene_tables(SmScene &S, int tid, int n_threads) {
+    const int n_pairs = S.n_pa + S.n_pb;
+    for (int w = tid; w < kMaxSpheres * n_pairs; w += n_threads) {
+        const int i = w / n_pairs, j = w - i * n_pairs, k = S.light_slot[i];
+        if (k < 0) continue;
+        const Org2 o = org2(mk(S.mats[i].px, S.mats[i].py, S.mats[i].pz));
+        if (j < S.n_pa) {
+            const PairG g = pair_general_origin(&S.ga[4 * j], o);
+            S.lg[k][j][0] = make_float4(g.opx.x, g.opx.y, g.opy.x, g.opy.y); S.lg[k][j][1] = make_float4(g.opz.x, g.opz.y, g.c.x, g.c.y);
+        } else {
+            const PairD g = pair_direct_origin(&S.gb[2 * (j - S.n_pa)], o);
+            S.ld[k][j - S.n_pa][0] = make_float4(g.oqx.x, g.oqx.y, g.oqy.x, g.oqy.y); S.ld[k][j - S.n_pa][1] = make_float4(g.oqz.x, g.oqz.y, g.r2.x, g.r2.y);
+        }
+    }
+}
+// scan of a ray that starts at the centre of emitter `src` (a point light's shadow ray): the origin part of every pair comes from the light's
+// table -- same values as scan_sm computes, 28 of a general pair's 46 instructions less.  Lights without a table (more than kLightTables
+// point lights, area sources) take scan_sm; the choice is made per warp.
+__device__ __forceinline__ bool scan_sm_light(const SmScene &S, int src, F3 light, F3 d, float &t, int &id) {
+    const int k = S.light_slot[src];
+    if (__any_sync(0xffffffffu, k < 0)) return scan_sm(S, light, d, t, id);
+    unsigned best = 0x7f800000u; // +inf
+    int bi = -1;
+    const int na = S.n_pa, nb = S.n_pb;
+    const Dir2 dd = dir2(d);
+    for (int j = 0; j < na; ++j) {
+        const float4 a = S.lg[k][j][0], b = S.lg[k][j][1];
+        float2 w1, w2;
+        pair_general_dir(PairG{lo2(a), hi2(a), lo2(b), hi2(b)}, dd, w1, w2);
+        pair_select(best, bi, 2 * j, w1, w2);
+    }
+    for (int j = 0; j < nb; ++j) {
+        const float4 a = S.ld[k][j][0], b = S.ld[k][j][1];
+        float2 w1, w2;
+        pair_direct_dir(PairD{lo2(a), hi2(a), lo2(b), hi2(b)}, dd, w1, w2);
+        pair_select(best, bi, 2 * (na + j), w1, w2);
+    }
+    t = __uint_as_float(best) + kEps;
+    id = bi >= 0 ? S.gid[bi] : -1;
+    return bi >= 0;
 }
 
 // Sphere::intersect (Sphere.h:27-37) for ONE sphere through the scan's own pair arithmetic: the near root unless it is negative or within

@@ -156,7 +156,7 @@ __device__ __forceinline__ int stage_med(C &c, bool act, Rec &r) {
         Cn = had(mk(sm.lr, sm.lg, sm.lb), r.beta) * (kInv4Pi * kTwoPi * omc_max * c.k.n_emitters);
     }
     float t; int hid;
-    const bool hit = c.scan(qo, qd, t, hid);
+    const bool hit = POINT ? scan_sm_light(c.S, src, qo, qd, t, hid) : c.scan(qo, qd, t, hid);
     if (act) {
         ++c.scans;
         if (POINT) { if (!hit || t > lim) c.add(r, Cn); }
@@ -186,7 +186,7 @@ __device__ __forceinline__ int stage_surf_p(C &c, bool act, Rec &r) {
     if (obj.material == 1) f = facet_eval_world(obj, n_, wi, r.d);
     const F3 Cn = had(had(mk(sm.lr, sm.lg, sm.lb), f), r.beta) * (dot(n_, wi) * transmit(c.k.sigma_t * dist) / d2 * c.k.n_emitters * c.k.inv_cp);
     float t; int hid;
-    const bool hit = c.scan(light, lx * (-inv), t, hid);
+    const bool hit = scan_sm_light(c.S, (int)r.src, light, lx * (-inv), t, hid);
     c.scans += act ? 1u : 0u;
     if (act && (!hit || t > dist * (1.0f - 1e-4f))) c.add(r, Cn);
     return act ? (obj.material != 0 ? SQ_SURF_F : SQ_SURF_L) : -1;
