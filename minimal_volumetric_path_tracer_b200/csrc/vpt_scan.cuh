@@ -165,6 +165,13 @@ __device__ __forceinline__ void pair_select(unsigned &best, int &bi, int slot, f
 #else
 #define VPT_SCAN_LINKAGE __forceinline__
 #endif
+#ifdef VPT_SCAN_UNROLL // experiment (tools/build_variant.py -DVPT_SCAN_UNROLL=2): pairs per loop iteration
+#define VPT_SCAN_STR(x) #x
+#define VPT_SCAN_UNROLL_N(n) _Pragma(VPT_SCAN_STR(unroll n))
+#define VPT_SCAN_UNROLL_PRAGMA VPT_SCAN_UNROLL_N(VPT_SCAN_UNROLL)
+#else
+#define VPT_SCAN_UNROLL_PRAGMA
+#endif
 static __device__ VPT_SCAN_LINKAGE ScanHit scan_sm_call(float ox, float oy, float oz, float dx, float dy, float dz) {
     const SmScene &S = *reinterpret_cast<const SmScene *>(smwave_smem);
     unsigned best = 0x7f800000u; // +inf
@@ -172,11 +179,13 @@ static __device__ VPT_SCAN_LINKAGE ScanHit scan_sm_call(float ox, float oy, floa
     const int na = S.n_pa, nb = S.n_pb;
     const Org2 o = org2(mk(ox, oy, oz));
     const Dir2 d = dir2(mk(dx, dy, dz));
+    VPT_SCAN_UNROLL_PRAGMA
     for (int j = 0; j < na; ++j) {
         float2 w1, w2;
         pair_general_dir(pair_general_origin(&S.ga[4 * j], o), d, w1, w2);
         pair_select(best, bi, 2 * j, w1, w2);
     }
+    VPT_SCAN_UNROLL_PRAGMA
     for (int j = 0; j < nb; ++j) {
         float2 w1, w2;
         pair_direct_dir(pair_direct_origin(&S.gb[2 * j], o), d, w1, w2);
