@@ -116,6 +116,40 @@ struct SmWave : SmSched<SmWave<METHOD>, kSmPool, kSmThreads> {
         Base::count_stillborn(b, mine, alive);
     }
 
+    // n <= 64 samples, two per lane (g0 + lane, g0 + 32 + lane), straight-line: the tail fill's batches
+    __device__ __forceinline__ void run_gen2(int b, unsigned g0, int n) {
+        bool mine[2], alive[2];
+        uint32_t pixel[2], sample[2];
+        Rec r[2];
+        const int item = Q.t_item[b];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const unsigned g = g0 + (unsigned)(lane + 32 * h);
+            const int pl = (int)(g & (unsigned)(item_pixels - 1));
+            sample[h] = (uint32_t)lp.sample_begin + (g >> log_p);
+            const int px = lane + 32 * h < n ? item_pixel(item, pl) : -1;
+            mine[h] = px >= 0; pixel[h] = mine[h] ? (uint32_t)px : 0u;
+            if (mine[h]) ++paths;
+            r[h].aux = (uint32_t)pl | ((uint32_t)b << 9);
+        }
+        stage_gen2(*this, mine, pixel, sample, lp.width, lp.height, r, alive);
+        int slot[2];
+        Base::alloc_push2(SQ_PRIMARY, alive[0], alive[1], slot[0], slot[1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            if (alive[h]) {
+                const int s = slot[h];
+                M.ox[s] = r[h].o.x; M.oy[s] = r[h].o.y; M.oz[s] = r[h].o.z;
+                M.dx[s] = r[h].d.x; M.dy[s] = r[h].d.y; M.dz[s] = r[h].d.z;
+                M.br[s] = 1.0f; M.bg[s] = 1.0f; M.bb[s] = 1.0f;
+                M.sample[s] = sample[h];
+                M.xd[s] = r[h].xi_dist; M.xs[s] = r[h].xi_decide;
+                M.meta[s] = meta_pack(r[h].aux, r[h].src, 0u, 0u);
+            }
+        const unsigned dead = __ballot_sync(0xffffffffu, lane < n && !alive[0]), dead1 = __ballot_sync(0xffffffffu, lane + 32 < n && !alive[1]);
+        if (lane == 0 && (dead | dead1)) smem_red(&Q.t_done[b], (unsigned)(__popc(dead) + __popc(dead1)), Base::lz);
+    }
+
     // ---- the stage batches: load the fields the stage reads, run it (vpt_stages.cuh), store what it changed, route ---------------------
     // (idle lanes of a partial batch run on record 0's values: in range, never stored)
     template <int STAGE>

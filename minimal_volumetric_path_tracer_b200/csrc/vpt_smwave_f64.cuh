@@ -98,6 +98,11 @@ struct SmWaveD : SmSched<SmWaveD, kSmdPool, kSmdThreads> {
         count_stillborn(b, mine, alive);
     }
 
+    __device__ __forceinline__ void run_gen2(int b, unsigned g0, int n) { // (no two-per-lane form in FP64: registers)
+        run_gen(b, g0, min(n, 32));
+        if (n > 32) run_gen(b, g0 + 32u, n - 32);
+    }
+
     template <int STAGE>
     __device__ __forceinline__ void run_stage(int slot) {
         if (STAGE == SQ_SURF_P) { last_step(); route(-1, slot); return; } // never queued in this pipeline

@@ -90,6 +90,29 @@ __device__ __forceinline__ bool stage_gen(C &c, bool mine, uint32_t pixel, uint3
     return alive;
 }
 
+// Two camera samples per lane as straight-line code: the same operations on the same values as stage_gen, per sample, but nothing is
+// branched around -- the two Philox / camera chains are independent and interleave (the kernel is latency bound), and a lane whose sample
+// dies at the roulette (40 % at the default continue probability) would idle through its neighbours' work anyway.
+template <class C>
+__device__ __forceinline__ void stage_gen2(C &c, const bool *mine, const uint32_t *pixel, const uint32_t *sample, int width, int height, Rec *r, bool *alive) {
+    float4 u[2], j[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) { r[h].pixel = pixel[h]; r[h].sample = sample[h]; r[h].depth = 0u; }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) u[h] = c.rnd(r[h], 0);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) j[h] = c.jitter(r[h]);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        alive[h] = mine[h] && !(u[h].x < c.k.q);
+        r[h].d = camera_dir(c.k, pixel[h], width, height, j[h].x, j[h].y);
+        r[h].o = mk(c.k.cam_o[0], c.k.cam_o[1], c.k.cam_o[2]);
+        r[h].beta = mk(1.0f, 1.0f, 1.0f);
+        r[h].src = (uint32_t)c.S.emitters[min((int)(u[h].y * c.k.n_emitters), c.S.n_emitters - 1)];
+        r[h].xi_dist = u[h].z; r[h].xi_decide = u[h].w; r[h].hid = 0u;
+    }
+}
+
 // ---- PRIMARY: scan of the path ray, distance sampling, surface-or-medium decision --------------------------------------------------------
 template <int METHOD, class C>
 __device__ __forceinline__ int stage_primary(C &c, bool act, Rec &r) {
