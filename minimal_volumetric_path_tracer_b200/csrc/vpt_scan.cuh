@@ -199,38 +199,41 @@ static __device__ VPT_SCAN_LINKAGE ScanHit scan_sm_call(float ox, float oy, floa
 // scan_sm: identical results.  Used by the surface stages, whose next-event rays (one per area light + the BSDF-sampled one) share the
 // vertex (vpt_stages.cuh stage_surf).
 template <int N>
-__device__ __forceinline__ void scan_sm_n(const SmScene &S, F3 o, const F3 *d, bool *hit, float *t, int *id) {
-    unsigned best[N];
-    int bi[N];
-    Dir2 dd[N];
-#pragma unroll
-    for (int n = 0; n < N; ++n) { best[n] = 0x7f800000u; bi[n] = -1; dd[n] = dir2(d[n]); }
+struct RaysN { F3 d[N]; bool hit[N]; int id[N]; }; // in: directions; out: hit and sphere index per ray
+struct RayBest { Dir2 d; unsigned best; int bi; };
+__device__ __forceinline__ RayBest ray_best(F3 d) { return RayBest{dir2(d), 0x7f800000u, -1}; }
+__device__ __forceinline__ void ray_general(RayBest &r, const PairG &g, int slot) {
+    float2 w1, w2;
+    pair_general_dir(g, r.d, w1, w2);
+    pair_select(r.best, r.bi, slot, w1, w2);
+}
+__device__ __forceinline__ void ray_direct(RayBest &r, const PairD &g, int slot) {
+    float2 w1, w2;
+    pair_direct_dir(g, r.d, w1, w2);
+    pair_select(r.best, r.bi, slot, w1, w2);
+}
+// (scalars, not arrays indexed in unrolled loops: that form crashed the compiler's front end now and then)
+template <int N>
+__device__ __forceinline__ void scan_sm_n(const SmScene &S, F3 o, RaysN<N> &q) {
+    static_assert(N == 2 || N == 3, "two or three rays");
+    RayBest r0 = ray_best(q.d[0]), r1 = ray_best(q.d[1]), r2 = ray_best(q.d[N - 1]);
     const int na = S.n_pa, nb = S.n_pb;
     const Org2 oo = org2(o);
     for (int j = 0; j < na; ++j) {
         const PairG g = pair_general_origin(&S.ga[4 * j], oo);
-#pragma unroll
-        for (int n = 0; n < N; ++n) {
-            float2 w1, w2;
-            pair_general_dir(g, dd[n], w1, w2);
-            pair_select(best[n], bi[n], 2 * j, w1, w2);
-        }
+        ray_general(r0, g, 2 * j);
+        ray_general(r1, g, 2 * j);
+        if (N > 2) ray_general(r2, g, 2 * j);
     }
     for (int j = 0; j < nb; ++j) {
         const PairD g = pair_direct_origin(&S.gb[2 * j], oo);
-#pragma unroll
-        for (int n = 0; n < N; ++n) {
-            float2 w1, w2;
-            pair_direct_dir(g, dd[n], w1, w2);
-            pair_select(best[n], bi[n], 2 * (na + j), w1, w2);
-        }
+        ray_direct(r0, g, 2 * (na + j));
+        ray_direct(r1, g, 2 * (na + j));
+        if (N > 2) ray_direct(r2, g, 2 * (na + j));
     }
-#pragma unroll
-    for (int n = 0; n < N; ++n) {
-        t[n] = __uint_as_float(best[n]) + kEps;
-        hit[n] = bi[n] >= 0;
-        id[n] = bi[n] >= 0 ? S.gid[bi[n]] : -1;
-    }
+    q.hit[0] = r0.bi >= 0; q.id[0] = r0.bi >= 0 ? S.gid[r0.bi] : -1;
+    q.hit[1] = r1.bi >= 0; q.id[1] = r1.bi >= 0 ? S.gid[r1.bi] : -1;
+    if (N > 2) { q.hit[N - 1] = r2.bi >= 0; q.id[N - 1] = r2.bi >= 0 ? S.gid[r2.bi] : -1; }
 }
 __device__ __forceinline__ bool scan_sm(const SmScene &S, F3 o, F3 d, float &t, int &id) {
     const ScanHit h = scan_sm_call(o.x, o.y, o.z, d.x, d.y, d.z);

@@ -28,7 +28,7 @@
 namespace vpt {
 
 #ifndef VPT_TAIL_GEN
-#define VPT_TAIL_GEN 64 // camera samples per tail-fill batch: 64 = two per lane (run_gen2), 32 = one per lane
+#define VPT_TAIL_GEN 64 // camera samples per tail-fill batch: 64 = two per lane (run_gen_wide), 32 = one per lane
 #endif
 constexpr int kTailGen = VPT_TAIL_GEN;
 constexpr int kSmMaxItemPixels = 256; // pixels per work item (power of two multiple of kTile)
@@ -104,7 +104,7 @@ __device__ __forceinline__ void smem_red(unsigned *p, unsigned v, unsigned lane_
 //   template <int STAGE> void run_stage(int slot)     one lane's record of a batch of stage STAGE (slot < 0: idle lane); loads the record, runs the
 //                                                     stage, stores what changed, calls route() / count_done() -- every lane of the warp must call both
 //   void run_gen(int item_slot, unsigned g0, int n)   n <= 32 new camera samples of the item in slot item_slot, lane i takes sample index g0 + i
-//   void run_gen2(int item_slot, unsigned g0, int n)  the same for n <= 64, lane i takes g0 + i and g0 + 32 + i (the tail fill's batches)
+//   void run_gen_wide(int item_slot, unsigned g0, int n)  the same for n <= kTailGen, lane i takes g0 + i, g0 + 32 + i, ... (the tail fill's batches)
 template <class D, int POOL, int THREADS>
 struct SmSched {
     SmCtl<POOL> &Q;
@@ -193,19 +193,24 @@ struct SmSched {
         base = __shfl_sync(0xffffffffu, base, 0);
         return flag ? (int)Q.freelist[ring_index(base + __popc(m & ((1u << lane) - 1u)))] : -1;
     }
-    // two new records per lane (run_gen2): both taken from the free ring and pushed to queue q, one atomic each for the whole warp
-    __device__ __forceinline__ void alloc_push2(int q, bool f0, bool f1, int &s0, int &s1) {
-        const unsigned m0 = __ballot_sync(0xffffffffu, f0), m1 = __ballot_sync(0xffffffffu, f1);
-        s0 = -1; s1 = -1;
-        const unsigned n0 = (unsigned)__popc(m0), n = n0 + (unsigned)__popc(m1);
+    // K new records per lane (run_gen_wide): all taken from the free ring and pushed to queue q, one atomic each for the whole warp
+    template <int K>
+    __device__ __forceinline__ void alloc_push(int q, const bool *f, int *s) {
+        unsigned m[K], n = 0;
+#pragma unroll
+        for (int h = 0; h < K; ++h) { m[h] = __ballot_sync(0xffffffffu, f[h]); n += (unsigned)__popc(m[h]); s[h] = -1; }
         if (n == 0u) return;
         unsigned from = 0, to = 0;
         if (lane == 0) { from = smem_add(&Q.free_head, n, lz); to = smem_add(&Q.q_tail[q], n, lz); }
         from = __shfl_sync(0xffffffffu, from, 0); to = __shfl_sync(0xffffffffu, to, 0);
         const unsigned below = (1u << lane) - 1u;
-        const unsigned r0 = (unsigned)__popc(m0 & below), r1 = n0 + (unsigned)__popc(m1 & below);
-        if (f0) { s0 = (int)Q.freelist[ring_index(from + r0)]; Q.queue[q][ring_index(to + r0)] = (uint16_t)s0; }
-        if (f1) { s1 = (int)Q.freelist[ring_index(from + r1)]; Q.queue[q][ring_index(to + r1)] = (uint16_t)s1; }
+        unsigned before = 0;
+#pragma unroll
+        for (int h = 0; h < K; ++h) {
+            const unsigned rank = before + (unsigned)__popc(m[h] & below);
+            if (f[h]) { s[h] = (int)Q.freelist[ring_index(from + rank)]; Q.queue[q][ring_index(to + rank)] = (uint16_t)s[h]; }
+            before += (unsigned)__popc(m[h]);
+        }
     }
     __device__ __forceinline__ void count_done(bool ended, uint32_t meta) {
         const unsigned m0 = __ballot_sync(0xffffffffu, ended && ((meta >> 9) & 1u) == 0u);
@@ -388,7 +393,7 @@ struct SmSched {
                     if (lane == 0 && *(volatile unsigned *)&Q.t_cursor[gen_slot] < limit) base = smem_add(&Q.t_cursor[gen_slot], (unsigned)kTailGen, lz);
                     base = __shfl_sync(0xffffffffu, base, 0);
                     if (base >= limit) break;
-                    if (kTailGen == 64) { SMW_BATCH(7, self().run_gen2(gen_slot, base, (int)min(64u, limit - base))); }
+                    if (kTailGen > 32) { SMW_BATCH(7, self().run_gen_wide(gen_slot, base, (int)min((unsigned)kTailGen, limit - base))); }
                     else { SMW_BATCH(7, self().run_gen(gen_slot, base, (int)min(32u, limit - base))); }
                 }
             }

@@ -116,14 +116,15 @@ struct SmWave : SmSched<SmWave<METHOD>, kSmPool, kSmThreads> {
         Base::count_stillborn(b, mine, alive);
     }
 
-    // n <= 64 samples, two per lane (g0 + lane, g0 + 32 + lane), straight-line: the tail fill's batches
-    __device__ __forceinline__ void run_gen2(int b, unsigned g0, int n) {
-        bool mine[2], alive[2];
-        uint32_t pixel[2], sample[2];
-        Rec r[2];
+    // n <= kTailGen samples, kTailGen / 32 per lane (g0 + lane, g0 + 32 + lane, ...), straight-line: the tail fill's batches
+    __device__ __forceinline__ void run_gen_wide(int b, unsigned g0, int n) {
+        constexpr int K = kTailGen / 32;
+        bool mine[K], alive[K];
+        uint32_t pixel[K], sample[K];
+        Rec r[K];
         const int item = Q.t_item[b];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < K; ++h) {
             const unsigned g = g0 + (unsigned)(lane + 32 * h);
             const int pl = (int)(g & (unsigned)(item_pixels - 1));
             sample[h] = (uint32_t)lp.sample_begin + (g >> log_p);
@@ -132,11 +133,12 @@ struct SmWave : SmSched<SmWave<METHOD>, kSmPool, kSmThreads> {
             if (mine[h]) ++paths;
             r[h].aux = (uint32_t)pl | ((uint32_t)b << 9);
         }
-        stage_gen2(*this, mine, pixel, sample, lp.width, lp.height, r, alive);
-        int slot[2];
-        Base::alloc_push2(SQ_PRIMARY, alive[0], alive[1], slot[0], slot[1]);
+        stage_gen_k<K>(*this, mine, pixel, sample, lp.width, lp.height, r, alive);
+        int slot[K];
+        Base::template alloc_push<K>(SQ_PRIMARY, alive, slot);
+        unsigned dead = 0;
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < K; ++h) {
             if (alive[h]) {
                 const int s = slot[h];
                 M.ox[s] = r[h].o.x; M.oy[s] = r[h].o.y; M.oz[s] = r[h].o.z;
@@ -146,8 +148,9 @@ struct SmWave : SmSched<SmWave<METHOD>, kSmPool, kSmThreads> {
                 M.xd[s] = r[h].xi_dist; M.xs[s] = r[h].xi_decide;
                 M.meta[s] = meta_pack(r[h].aux, r[h].src, 0u, 0u);
             }
-        const unsigned dead = __ballot_sync(0xffffffffu, lane < n && !alive[0]), dead1 = __ballot_sync(0xffffffffu, lane + 32 < n && !alive[1]);
-        if (lane == 0 && (dead | dead1)) smem_red(&Q.t_done[b], (unsigned)(__popc(dead) + __popc(dead1)), Base::lz);
+            dead += (unsigned)__popc(__ballot_sync(0xffffffffu, lane + 32 * h < n && !alive[h]));
+        }
+        if (lane == 0 && dead) smem_red(&Q.t_done[b], dead, Base::lz);
     }
 
     // ---- the stage batches: load the fields the stage reads, run it (vpt_stages.cuh), store what it changed, route ---------------------

@@ -98,9 +98,8 @@ struct SmWaveD : SmSched<SmWaveD, kSmdPool, kSmdThreads> {
         count_stillborn(b, mine, alive);
     }
 
-    __device__ __forceinline__ void run_gen2(int b, unsigned g0, int n) { // (no two-per-lane form in FP64: registers)
-        run_gen(b, g0, min(n, 32));
-        if (n > 32) run_gen(b, g0 + 32u, n - 32);
+    __device__ __forceinline__ void run_gen_wide(int b, unsigned g0, int n) { // (one sample per lane at a time in FP64: registers)
+        for (int h = 0; h < n; h += 32) run_gen(b, g0 + (unsigned)h, min(n - h, 32));
     }
 
     template <int STAGE>

@@ -41,11 +41,9 @@ __device__ __forceinline__ float transmit(float x) { return __expf(-x); }
 // ---- roulette for the next bounce (vptShadeMethods.h:1282; also at depth 0) + the draws that come with it --------------------------------
 // the record already holds the new origin / direction / throughput / depth; block 0 of the new bounce = roulette, light pick, distance, decision
 template <class C>
-__device__ __forceinline__ int roulette(C &c, bool act, Rec &r) {
-    c.last_step();
+__device__ __forceinline__ int roulette_with(C &c, bool act, Rec &r, float4 u) {
     bool alive = false;
     if (act) {
-        const float4 u = c.rnd(r, 0);
         alive = !(c.k.max_depth > 0 && (int)r.depth >= c.k.max_depth) && r.depth < (uint32_t)VPT_MAX_DEPTH && !(u.x < c.k.q);
         if (alive) {
             r.src = (uint32_t)c.S.emitters[min((int)(u.y * c.k.n_emitters), c.S.n_emitters - 1)]; // :1293-1304
@@ -53,6 +51,13 @@ __device__ __forceinline__ int roulette(C &c, bool act, Rec &r) {
         }
     }
     return alive ? SQ_PRIMARY : (act ? kDestFree : -1);
+}
+template <class C>
+__device__ __forceinline__ int roulette(C &c, bool act, Rec &r) {
+    c.last_step();
+    float4 u = make_float4(0, 0, 0, 0);
+    if (act) u = c.rnd(r, 0);
+    return roulette_with(c, act, r, u);
 }
 
 // camera ray of storage pixel `pixel` with jitter (j1, j2), rt.cpp:773,787 (storage row 0 is the top of the image)
@@ -90,20 +95,20 @@ __device__ __forceinline__ bool stage_gen(C &c, bool mine, uint32_t pixel, uint3
     return alive;
 }
 
-// Two camera samples per lane as straight-line code: the same operations on the same values as stage_gen, per sample, but nothing is
-// branched around -- the two Philox / camera chains are independent and interleave (the kernel is latency bound), and a lane whose sample
+// K camera samples per lane as straight-line code: the same operations on the same values as stage_gen, per sample, but nothing is
+// branched around -- the K Philox / camera chains are independent and interleave (the kernel is latency bound), and a lane whose sample
 // dies at the roulette (40 % at the default continue probability) would idle through its neighbours' work anyway.
-template <class C>
-__device__ __forceinline__ void stage_gen2(C &c, const bool *mine, const uint32_t *pixel, const uint32_t *sample, int width, int height, Rec *r, bool *alive) {
-    float4 u[2], j[2];
+template <int K, class C>
+__device__ __forceinline__ void stage_gen_k(C &c, const bool *mine, const uint32_t *pixel, const uint32_t *sample, int width, int height, Rec *r, bool *alive) {
+    float4 u[K], j[K];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) { r[h].pixel = pixel[h]; r[h].sample = sample[h]; r[h].depth = 0u; }
+    for (int h = 0; h < K; ++h) { r[h].pixel = pixel[h]; r[h].sample = sample[h]; r[h].depth = 0u; }
 #pragma unroll
-    for (int h = 0; h < 2; ++h) u[h] = c.rnd(r[h], 0);
+    for (int h = 0; h < K; ++h) u[h] = c.rnd(r[h], 0);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) j[h] = c.jitter(r[h]);
+    for (int h = 0; h < K; ++h) j[h] = c.jitter(r[h]);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < K; ++h) {
         alive[h] = mine[h] && !(u[h].x < c.k.q);
         r[h].d = camera_dir(c.k, pixel[h], width, height, j[h].x, j[h].y);
         r[h].o = mk(c.k.cam_o[0], c.k.cam_o[1], c.k.cam_o[2]);
@@ -280,11 +285,11 @@ __device__ __forceinline__ int stage_surf(C &c, bool act, Rec &r) {
     while (kFuse && n_area - a > 2) { // two area lights per pass while more than two are left (their cone numbers share one Philox block)
         const float4 ra = c.rnd(r, 2 + (a >> 1));
         const LightRay q0 = aim(a, ra.x, ra.y), q1 = aim(a + 1, ra.z, ra.w);
-        const F3 dirs[2] = {q0.wi, q1.wi};
-        bool hit[2]; float t[2]; int hid[2];
-        scan_sm_n<2>(c.S, o, dirs, hit, t, hid);
-        shade_light(q0, hit[0], hid[0]);
-        shade_light(q1, hit[1], hid[1]);
+        RaysN<2> rays;
+        rays.d[0] = q0.wi; rays.d[1] = q1.wi;
+        scan_sm_n<2>(c.S, o, rays);
+        shade_light(q0, rays.hit[0], rays.id[0]);
+        shade_light(q1, rays.hit[1], rays.id[1]);
         a += 2;
     }
     // the last pass: the remaining 0, 1 or 2 area lights and the BSDF-sampled ray of MISv2 (:124-167)
@@ -298,6 +303,10 @@ __device__ __forceinline__ int stage_surf(C &c, bool act, Rec &r) {
     }
     const float omc_last = n_area == 0 ? 1.0f : (left > 1 ? q1.omc_max : (left > 0 ? q0.omc_max : omc_tail)); // 1 - costhetaMax of the last light visited (:162); 1 = "cos 0"
     const float4 b1 = c.rnd(r, 1);
+    // Lambert: the next bounce's roulette block is drawn here, next to the vertex's own block -- two independent Philox chains side by side
+    // (+0.3 %; the microfacet stage has no registers to spare for it)
+    float4 un = make_float4(0, 0, 0, 0);
+    if (!FACET) { Rec rn = r; rn.depth += 1u; un = c.rnd(rn, 0); }
     // slots S_MIS = lanes 2, 3 of block 1
     const float xi1 = b1.z, xi2 = b1.w;
     F3 wi_l, wh = mk(0, 0, 1);
@@ -317,22 +326,21 @@ __device__ __forceinline__ int stage_surf(C &c, bool act, Rec &r) {
         }
     } else wi_l = cosine_local(xi1, xi2);
     const F3 wi_b = unit(to_world(fr, wi_l));
-    bool hit_b; float t_b; int hid_b;
+    bool hit_b; int hid_b;
     if (kFuse && left == 2) {
-        const F3 dirs[3] = {q0.wi, q1.wi, wi_b};
-        bool hit[3]; float t[3]; int hid[3];
-        scan_sm_n<3>(c.S, o, dirs, hit, t, hid);
-        shade_light(q0, hit[0], hid[0]);
-        shade_light(q1, hit[1], hid[1]);
-        hit_b = hit[2]; t_b = t[2]; hid_b = hid[2];
+        RaysN<3> rays;
+        rays.d[0] = q0.wi; rays.d[1] = q1.wi; rays.d[2] = wi_b;
+        scan_sm_n<3>(c.S, o, rays);
+        shade_light(q0, rays.hit[0], rays.id[0]);
+        shade_light(q1, rays.hit[1], rays.id[1]);
+        hit_b = rays.hit[2]; hid_b = rays.id[2];
     } else if (kFuse && left == 1) {
-        const F3 dirs[2] = {q0.wi, wi_b};
-        bool hit[2]; float t[2]; int hid[2];
-        scan_sm_n<2>(c.S, o, dirs, hit, t, hid);
-        shade_light(q0, hit[0], hid[0]);
-        hit_b = hit[1]; t_b = t[1]; hid_b = hid[1];
-    } else hit_b = c.scan(o, wi_b, t_b, hid_b);
-    (void)t_b;
+        RaysN<2> rays;
+        rays.d[0] = q0.wi; rays.d[1] = wi_b;
+        scan_sm_n<2>(c.S, o, rays);
+        shade_light(q0, rays.hit[0], rays.id[0]);
+        hit_b = rays.hit[1]; hid_b = rays.id[1];
+    } else { float t_b; hit_b = c.scan(o, wi_b, t_b, hid_b); }
     c.scans += act ? 1u : 0u;
     if (act && hit_b && c.S.mats[hid_b].emits) {
         const MatF &em = c.S.mats[hid_b];
@@ -356,6 +364,7 @@ __device__ __forceinline__ int stage_surf(C &c, bool act, Rec &r) {
     r.beta = had(beta, weight) * c.k.inv_cp; // :1326
     r.d = wi;
     r.depth += 1u;
+    if (!FACET) { c.last_step(); return roulette_with(c, act, r, un); }
     return roulette(c, act, r);
 }
 
