@@ -67,11 +67,11 @@ __global__ void __launch_bounds__(kThreadsPerBlock) render_f32_kernel(const __gr
 }
 
 // ---- SM-wide wavefront (vpt_smwave.cuh) -----------------------------------------------------------------------------------------
-template <int METHOD>
+template <int METHOD, int SLOTS>
 __global__ void __launch_bounds__(kSmThreads, 1) render_f32_smwave_kernel(const __grid_constant__ SceneF sc, const __grid_constant__ LaunchParams lp,
                                                                            const __grid_constant__ ConstsF cf, float *__restrict__ hdr, Counters *__restrict__ counters,
                                                                            int log_p, int n_owned_tiles, int n_items, int zero) {
-    SmShared &M = sm_shared();
+    SmShared<SLOTS> &M = sm_shared<SLOTS>();
     const int tid = (int)threadIdx.x;
     stage_scene(M.scene, sc, tid, kSmThreads);
     for (int i = tid; i < kSmPool; i += kSmThreads) M.meta[i] = 0u;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kSmThreads, 1) render_f32_smwave_kernel(const 
     }
     __syncthreads();
     stage_scene_tables(M.scene, tid, kSmThreads);
-    SmWave<METHOD> wf(M, cf, lp, log_p, n_owned_tiles, zero);
+    SmWave<METHOD, SLOTS> wf(M, cf, lp, log_p, n_owned_tiles, zero);
     wf.init(n_items);
     __syncthreads();
     wf.run(hdr, n_items, kSmFixInv);
@@ -146,36 +146,41 @@ cudaError_t philox_keys_end(KeySlot &K, cudaStream_t st) { // after the launch: 
 }
 } // namespace
 
-template <int METHOD>
-static int launch_smwave(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, cudaStream_t st, int n_owned_tiles) {
+template <int METHOD, int SLOTS>
+static int launch_smwave_slots(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, cudaStream_t st, int n_owned_tiles) {
     int dev = 0, n_sm = 0;
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
     if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
-    if ((e = cudaFuncSetAttribute(render_f32_smwave_kernel<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmShared))) != cudaSuccess) return (int)e;
-    // work item = 256 pixels at low sample counts (an item's samples last longer: fewer rounds without generation while the other item
-    // drains) when that still leaves every SM at least 8 items; else one 128-pixel tile (more items: the SMs finish closer together,
-    // +0.7 % at 1024 spp on 1024x768)
-#ifdef VPT_ITEM_LOG
-    const int log_p = VPT_ITEM_LOG;
-#else
-    const int log_p = (n_owned_tiles / 2 >= 8 * n_sm && lp.sample_end - lp.sample_begin < 512) ? 8 : 7;
-#endif
-    const int tiles_per_item = 1 << (log_p - 7);
-    const int n_items = (n_owned_tiles + tiles_per_item - 1) / tiles_per_item;
+    if ((e = cudaFuncSetAttribute(render_f32_smwave_kernel<METHOD, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmShared<SLOTS>))) != cudaSuccess) return (int)e;
+    const int log_p = 7; // work item: one 128-pixel tile
+    const int n_items = n_owned_tiles;
     const int grid = n_items < n_sm ? n_items : n_sm;
 #ifdef VPT_PHILOX_ARG_KEYS
-    render_f32_smwave_kernel<METHOD><<<grid, kSmThreads, sizeof(SmShared), st>>>(scene, lp, cf, hdr_dev, counters_dev, log_p, n_owned_tiles, n_items, 0);
+    render_f32_smwave_kernel<METHOD, SLOTS><<<grid, kSmThreads, sizeof(SmShared<SLOTS>), st>>>(scene, lp, cf, hdr_dev, counters_dev, log_p, n_owned_tiles, n_items, 0);
     return (int)cudaGetLastError();
 #else
     if (dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
     KeySlot &K = g_key_slots[dev];
     std::lock_guard<std::mutex> lock(K.m);
     if ((e = philox_keys_begin(K, st, lp.key0, lp.key1)) != cudaSuccess) return (int)e;
-    render_f32_smwave_kernel<METHOD><<<grid, kSmThreads, sizeof(SmShared), st>>>(scene, lp, cf, hdr_dev, counters_dev, log_p, n_owned_tiles, n_items, 0);
+    render_f32_smwave_kernel<METHOD, SLOTS><<<grid, kSmThreads, sizeof(SmShared<SLOTS>), st>>>(scene, lp, cf, hdr_dev, counters_dev, log_p, n_owned_tiles, n_items, 0);
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
     return (int)philox_keys_end(K, st);
 #endif
+}
+// Work items in flight per CTA (vpt_smsched.cuh): four below 384 samples per pixel, two from there on.  Measured on 1024x768, equi-angular:
+// 64 spp 7502 (four) against 4948 (two, and 6999 with two 256-pixel items), 256 spp 8455 against 8398, 512 spp 8510 against 8599,
+// 1024 spp 8532 against 8631 Mpaths/s.
+template <int METHOD>
+static int launch_smwave(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, cudaStream_t st, int n_owned_tiles) {
+#ifdef VPT_ITEM_SLOTS_RUN
+    const bool many = VPT_ITEM_SLOTS_RUN > 2;
+#else
+    const bool many = lp.sample_end - lp.sample_begin < 384;
+#endif
+    return many ? launch_smwave_slots<METHOD, kMaxItemSlots>(scene, lp, cf, hdr_dev, counters_dev, st, n_owned_tiles)
+                : launch_smwave_slots<METHOD, 2>(scene, lp, cf, hdr_dev, counters_dev, st, n_owned_tiles);
 }
 
 // ---- ray-marching reference solver (vpt_march.cuh): one thread per pixel ---------------------------------------------------------

@@ -31,22 +31,30 @@ namespace vpt {
 #define VPT_TAIL_GEN 64 // camera samples per tail-fill batch: 64 = two per lane (run_gen_wide), 32 = one per lane
 #endif
 constexpr int kTailGen = VPT_TAIL_GEN;
-constexpr int kSmMaxItemPixels = 256; // pixels per work item (power of two multiple of kTile)
+constexpr int kSmMaxItemPixels = 128; // pixels per work item (power of two multiple of kTile)
+// Work items in flight per CTA (template parameter SLOTS of the scheduler, chosen per launch): more of them keep the pool full at low sample
+// counts, where an item's samples are generated in a few rounds while its last paths take tens of rounds to finish (64 spp: four slots
+// +8 .. 10 % over two); fewer cost less in the plan and per batch (1024 spp: two slots +1.2 % over four).  3 KB of pixel sums per slot.
+constexpr int kMaxItemSlots = 4;
 // Claim order of a round's batches (one nibble per rank, SQ_COUNT = generation), longest stage first so that a round ends evenly:
 // SURF_F, SURF_L, PRIMARY, MED_AREA, MED_POINT, SURF_P, generation
 constexpr unsigned kRankStage = 0x6312045u;
 
-// meta word of a record: pixel-in-item (bits 0-8) | item slot (bit 9) | picked source (10-14) | hit object (15-19) | depth (20-31)
-static_assert(kMaxSpheres <= 32 && VPT_MAX_DEPTH <= 4095 && kSmMaxItemPixels <= 512, "meta word layout");
+// meta word of a record: pixel-in-item (bits 0-7) | item slot (bits 8-9) | picked source (10-14) | hit object (15-19) | depth (20-31)
+static_assert(kMaxSpheres <= 32 && VPT_MAX_DEPTH <= 4095 && kSmMaxItemPixels <= 256 && kSmMaxItemPixels >= kTile && kMaxItemSlots <= 4, "meta word layout");
+__device__ __forceinline__ uint32_t meta_slot(uint32_t meta) { return (meta >> 8) & 3u; }
+__device__ __forceinline__ uint32_t meta_pixel(uint32_t meta) { return meta & 0xffu; }
+__device__ __forceinline__ uint32_t meta_aux(int pixel_in_item, int item_slot) { return (uint32_t)pixel_in_item | ((uint32_t)item_slot << 8); }
 __device__ __forceinline__ uint32_t meta_pack(uint32_t aux, uint32_t src, uint32_t hid, uint32_t depth) { return (aux & 0x3ffu) | (src << 10) | (hid << 15) | (depth << 20); }
 
 // queues, pixel sums and control words of one CTA (the pipeline's shared-memory struct holds one, next to its records and its scene)
-template <int POOL>
+template <int POOL, int SLOTS>
 struct SmCtl {
     static_assert(POOL % 32 == 0 && POOL <= 65536, "queues hold 16-bit record indices, batches are 32 records");
+    static_assert(SLOTS >= 2 && SLOTS <= kMaxItemSlots, "item slots");
     uint16_t queue[SQ_COUNT][POOL];
     uint16_t freelist[POOL];
-    unsigned long long acc[2][kSmMaxItemPixels][3];
+    unsigned long long acc[SLOTS][kSmMaxItemPixels][3];
     // this round's batch table by rank (kRankStage): batch k belongs to the last rank with rb_first[rank] <= k and covers entries
     // [rb_begin + 32 j, min(rb_end, +32)), j = k - rb_first
     __align__(16) unsigned rb_first[8]; // [7] = number of batches of the round
@@ -64,9 +72,9 @@ struct SmCtl {
     __align__(16) unsigned q_tail[SQ_COUNT]; // [0..5]   push counters
     unsigned q_end[SQ_COUNT];                // [6..11]  entries below it have been handed out
     unsigned free_head, free_tail;           // [12,13]  the free-record ring: allocate at the head (only below the round's snapshot), release at the tail
-    int t_item[2];                           // [14,15]  work item of the slot, -1: slot idle
-    unsigned t_cursor[2], t_done[2];         // [16..19] camera samples generated / paths finished
-    unsigned ctl_pad[12];
+    int t_item[SLOTS];                       // [14 ..]  work item of the slot, -1: slot idle
+    unsigned t_cursor[SLOTS], t_done[SLOTS]; // camera samples generated / paths finished
+    unsigned ctl_pad[18 - 3 * SLOTS];
     int gen_slot, flush_slot, exit_flag;
 #ifdef VPT_SMWAVE_PROFILE
     long long dbg_arrive[32];
@@ -100,14 +108,15 @@ __device__ __forceinline__ void smem_red(unsigned *p, unsigned v, unsigned lane_
 #define SMW_ADD(i, v)
 #endif
 
-// The pipeline D derives from SmSched<D, POOL, THREADS> and provides
+// The pipeline D derives from SmSched<D, POOL, THREADS, SLOTS> and provides
 //   template <int STAGE> void run_stage(int slot)     one lane's record of a batch of stage STAGE (slot < 0: idle lane); loads the record, runs the
 //                                                     stage, stores what changed, calls route() / count_done() -- every lane of the warp must call both
 //   void run_gen(int item_slot, unsigned g0, int n)   n <= 32 new camera samples of the item in slot item_slot, lane i takes sample index g0 + i
 //   void run_gen_wide(int item_slot, unsigned g0, int n)  the same for n <= kTailGen, lane i takes g0 + i, g0 + 32 + i, ... (the tail fill's batches)
-template <class D, int POOL, int THREADS>
+template <class D, int POOL, int THREADS, int SLOTS>
 struct SmSched {
-    SmCtl<POOL> &Q;
+    using Ctl = SmCtl<POOL, SLOTS>;
+    Ctl &Q;
     const LaunchParams &lp;
     const int tid, lane;
     const unsigned lz; // lane * 0, opaque to the compiler (see smem_add)
@@ -121,7 +130,7 @@ struct SmSched {
     // round sees is below 2 * POOL and `counter mod POOL` is one compare and one subtract (POOL need not be a power of two).
     static __device__ __forceinline__ unsigned ring_index(unsigned counter) { return counter >= (unsigned)POOL ? counter - (unsigned)POOL : counter; }
 
-    __device__ SmSched(SmCtl<POOL> &Q_, const LaunchParams &lp_, int log_p_, int n_owned_, int zero)
+    __device__ SmSched(Ctl &Q_, const LaunchParams &lp_, int log_p_, int n_owned_, int zero)
         : Q(Q_), lp(lp_), tid((int)threadIdx.x), lane((int)threadIdx.x & 31), lz((threadIdx.x & 31u) * (unsigned)zero), log_p(log_p_),
           item_pixels(1 << log_p_), n_owned_tiles(n_owned_) {}
     __device__ __forceinline__ D &self() { return *static_cast<D *>(this); }
@@ -129,18 +138,18 @@ struct SmSched {
     // cooperative initialisation by the whole block (then __syncthreads)
     __device__ __forceinline__ void init(int n_items) {
         for (int i = tid; i < POOL; i += THREADS) Q.freelist[i] = (uint16_t)i;
-        for (int i = tid; i < 2 * kSmMaxItemPixels * 3; i += THREADS) (&Q.acc[0][0][0])[i] = 0ull;
+        for (int i = tid; i < SLOTS * kSmMaxItemPixels * 3; i += THREADS) (&Q.acc[0][0][0])[i] = 0ull;
         if (tid == 0) {
             for (int q = 0; q < SQ_COUNT; ++q) { Q.q_tail[q] = 0u; Q.q_end[q] = 0u; }
             Q.free_head = 0u; Q.free_tail = (unsigned)POOL;
-            for (int b = 0; b < 2; ++b) {
+            for (int b = 0; b < SLOTS; ++b) {
                 const int item = (int)blockIdx.x + b * (int)gridDim.x;
                 Q.t_item[b] = item < n_items ? item : -1; Q.t_cursor[b] = 0u; Q.t_done[b] = 0u;
             }
-            Q.next_item = (int)blockIdx.x + 2 * (int)gridDim.x;
+            Q.next_item = (int)blockIdx.x + SLOTS * (int)gridDim.x;
             Q.gen_slot = -1; Q.tail_limit = 0u; Q.round_no = 0u;
         }
-        for (int i = tid; i < SmCtl<POOL>::kDescMax; i += THREADS) Q.desc[i] = 0xffffffffu; // (no round carries the tag 2047 before the 2047th)
+        for (int i = tid; i < Ctl::kDescMax; i += THREADS) Q.desc[i] = 0xffffffffu; // (no round carries the tag 2047 before the 2047th)
     }
 
     // The claim for the NEXT batch is issued a few hundred cycles before the current one ends (at the start of its last step: the roulette's
@@ -159,7 +168,7 @@ struct SmSched {
         if (hi) smem_red(w + 1, hi);
     }
     // the fixed-point sums of the pixel a record belongs to (meta: pixel-in-item, item slot)
-    __device__ __forceinline__ unsigned long long *pixel_acc(uint32_t meta) { return Q.acc[(meta >> 9) & 1u][meta & 0x1ffu]; }
+    __device__ __forceinline__ unsigned long long *pixel_acc(uint32_t meta) { return Q.acc[meta_slot(meta)][meta_pixel(meta)]; }
 
     // ---- work items: item j = owned tiles [j * K, (j + 1) * K), K = item_pixels / kTile -----------------------------------------
     // (32-bit arithmetic: n_pixels is an int32, so tile and pixel indices fit; -1 = outside the image / not this rank's tile)
@@ -169,7 +178,7 @@ struct SmSched {
         const unsigned pixel = (owned * (unsigned)lp.tile_count + (unsigned)lp.tile_rank) * (unsigned)kTile + ((unsigned)pl & (unsigned)(kTile - 1));
         return pixel < (unsigned)lp.n_pixels ? (int)pixel : -1;
     }
-    __device__ __forceinline__ uint32_t pixel_of(uint32_t meta) const { return (uint32_t)item_pixel(Q.t_item[(meta >> 9) & 1u], (int)(meta & 0x1ffu)); }
+    __device__ __forceinline__ uint32_t pixel_of(uint32_t meta) const { return (uint32_t)item_pixel(Q.t_item[meta_slot(meta)], (int)meta_pixel(meta)); }
 
     // ---- queue / pool primitives (warp-aggregated shared-memory atomics) ------------------------------------------------------------
     // Route every lane's record in ONE step: dest = a stage queue (SQ_*), kDestFree (the record goes back to the free ring) or -1 (nothing).
@@ -213,11 +222,11 @@ struct SmSched {
         }
     }
     __device__ __forceinline__ void count_done(bool ended, uint32_t meta) {
-        const unsigned m0 = __ballot_sync(0xffffffffu, ended && ((meta >> 9) & 1u) == 0u);
-        const unsigned m1 = __ballot_sync(0xffffffffu, ended && ((meta >> 9) & 1u) == 1u);
-        if (lane == 0) {
-            if (m0) smem_red(&Q.t_done[0], (unsigned)__popc(m0), lz);
-            if (m1) smem_red(&Q.t_done[1], (unsigned)__popc(m1), lz);
+        if (SLOTS > 2 && !__any_sync(0xffffffffu, ended)) return;
+#pragma unroll
+        for (int b = 0; b < SLOTS; ++b) {
+            const unsigned m = __ballot_sync(0xffffffffu, ended && meta_slot(meta) == (uint32_t)b);
+            if (lane == 0 && m) smem_red(&Q.t_done[b], (unsigned)__popc(m), lz);
         }
     }
     // generation bookkeeping: samples of pixels outside the image and paths killed by the first roulette are finished already
@@ -250,27 +259,36 @@ struct SmSched {
     // Every other warp waits for this, so the dependent chain is kept short: ONE shared-memory load fetches all control words (lane i
     // reads word i), everything else is register shuffles, and every lane computes the few scalar decisions redundantly.
     __device__ __forceinline__ void plan_round(unsigned item_total) {
-        static_assert(offsetof(SmCtl<POOL>, t_done) - offsetof(SmCtl<POOL>, q_tail) == 18 * sizeof(unsigned), "plan_round reads the control words by index");
-        static_assert(offsetof(SmCtl<POOL>, free_tail) - offsetof(SmCtl<POOL>, q_tail) == 13 * sizeof(unsigned) &&
-                          offsetof(SmCtl<POOL>, freelist) - offsetof(SmCtl<POOL>, queue) == SQ_COUNT * POOL * sizeof(uint16_t),
+        static_assert(offsetof(Ctl, t_item) - offsetof(Ctl, q_tail) == 14 * sizeof(unsigned) &&
+                          offsetof(Ctl, t_done) - offsetof(Ctl, q_tail) == (14 + 2 * SLOTS) * sizeof(unsigned) && 14 + 3 * SLOTS <= 32,
+                      "plan_round reads the control words by index");
+        static_assert(offsetof(Ctl, free_tail) - offsetof(Ctl, q_tail) == 13 * sizeof(unsigned) &&
+                          offsetof(Ctl, freelist) - offsetof(Ctl, queue) == SQ_COUNT * POOL * sizeof(uint16_t),
                       "route() addresses the free ring as queue number SQ_COUNT");
-        unsigned v = (&Q.q_tail[0])[lane]; // words 0..19 are the control block, the padding behind it is never used
+        unsigned v = (&Q.q_tail[0])[lane]; // words 0 .. 13 + 3 * SLOTS are the control block, the padding behind it is never used
         { // keep the ring counters below 2 * POOL: lanes 0..5 / 6..11 hold a queue's pushed / handed-out marks, 12 / 13 the free ring's head / tail
             const unsigned low = __shfl_sync(0xffffffffu, v, lane < 6 ? lane + 6 : (lane == 13 ? 12 : lane)); // the smaller mark of the pair
             if (lane < 14 && low >= (unsigned)POOL) { v -= (unsigned)POOL; (&Q.q_tail[0])[lane] = v; }
         }
-        const int item0 = (int)__shfl_sync(0xffffffffu, v, 14), item1 = (int)__shfl_sync(0xffffffffu, v, 15);
-        unsigned cur0 = __shfl_sync(0xffffffffu, v, 16), cur1 = __shfl_sync(0xffffffffu, v, 17);
-        const unsigned done0 = __shfl_sync(0xffffffffu, v, 18), done1 = __shfl_sync(0xffffffffu, v, 19);
-        const unsigned n_free = __shfl_sync(0xffffffffu, v, 13) - __shfl_sync(0xffffffffu, v, 12);
         const int prev_gen = Q.gen_slot;
         const unsigned prev_limit = Q.tail_limit; // the tail fill overshoots its limit by the claims that found nothing
-        if (prev_gen == 0) cur0 = min(cur0, prev_limit);
-        if (prev_gen == 1) cur1 = min(cur1, prev_limit);
-        int flush = -1, gen = -1;
-        if (item1 >= 0) { if (cur1 == item_total) { if (done1 == item_total) flush = 1; } else gen = 1; }
-        if (item0 >= 0) { if (cur0 == item_total) { if (done0 == item_total) flush = 0; } else if (gen < 0 || item0 < item1) gen = 0; }
-        const unsigned gen_begin = gen == 0 ? cur0 : cur1;
+        const unsigned n_free = __shfl_sync(0xffffffffu, v, 13) - __shfl_sync(0xffffffffu, v, 12);
+        // the slot to write out (all samples generated, all paths finished; the lowest such slot, one per round) and the slot to generate
+        // from (the oldest item that still has samples)
+        unsigned cur[SLOTS];
+        int flush = -1, gen = -1, gen_item = 0x7fffffff;
+        unsigned gen_begin = 0;
+#pragma unroll
+        for (int b = SLOTS - 1; b >= 0; --b) {
+            const int item = (int)__shfl_sync(0xffffffffu, v, 14 + b);
+            cur[b] = __shfl_sync(0xffffffffu, v, 14 + SLOTS + b);
+            const unsigned done = __shfl_sync(0xffffffffu, v, 14 + 2 * SLOTS + b);
+            if (prev_gen == b) cur[b] = min(cur[b], prev_limit);
+            if (item >= 0) {
+                if (cur[b] == item_total) { if (done == item_total) flush = b; }
+                else if (item <= gen_item) { gen = b; gen_item = item; gen_begin = cur[b]; }
+            }
+        }
         const unsigned left = gen >= 0 ? item_total - gen_begin : 0u;
         // while new samples keep coming only full 32-record batches are handed out (the remainder waits for the next round);
         // once generation has stopped (an item drains) everything goes
@@ -305,7 +323,8 @@ struct SmSched {
             const unsigned after = gen_begin + n_gen;                       // the cursor after the planned generation batches
             const unsigned budget = (n_free - n_gen) & ~31u;                // free records the tail fill may use: one per sample, whole batches
             const unsigned limit = min(after + budget, item_total);         // (a last, partial batch of the item needs fewer records than it claims)
-            Q.t_cursor[0] = gen == 0 ? after : cur0; Q.t_cursor[1] = gen == 1 ? after : cur1;
+#pragma unroll
+            for (int b = 0; b < SLOTS; ++b) Q.t_cursor[b] = gen == b ? after : cur[b];
             Q.tail_limit = gen >= 0 ? limit : 0u;
             Q.flush_slot = flush; Q.gen_slot = gen; Q.round_claim = (unsigned)(THREADS / 32); Q.round_no = Q.round_no + 1u;
             Q.exit_flag = (total == 0u && flush < 0 && gen < 0) ? 1 : 0; // nothing queued, nothing to generate, nothing to write out
@@ -357,7 +376,7 @@ struct SmSched {
                 return (unsigned)rank | (n << 3) | ((rank == SQ_COUNT ? j : ring_index(start)) << 9) | tag;
             };
             { // every warp spells out its share of the table (the plan, on which all warps wait, stays short); a reader checks the round tag
-                constexpr int kPer = (SmCtl<POOL>::kDescMax + THREADS / 32 - 1) / (THREADS / 32);
+                constexpr int kPer = (Ctl::kDescMax + THREADS / 32 - 1) / (THREADS / 32);
                 const unsigned k = (unsigned)(tid >> 5) * (unsigned)kPer + (unsigned)lane;
                 if (lane < kPer && k < total) Q.desc[k] = make_desc(k);
             }

@@ -24,6 +24,7 @@ constexpr float kSmFixScale = 1073741824.0f; // 2^30
 constexpr double kSmFixInv = 1.0 / 1073741824.0;
 constexpr float kSmMaxContribution = 4294967296.0f; // 2^32: a contribution at or above it (or NaN) is dropped and counted (vpt_stats.nonfinite)
 
+template <int SLOTS>
 struct SmShared {
     SmScene scene; // first: scan_sm_call finds it at the start of the dynamic shared memory
     // ---- path records (SoA) ----
@@ -33,24 +34,25 @@ struct SmShared {
     uint32_t sample[kSmPool];
     uint32_t meta[kSmPool];                      // meta_pack(): pixel-in-item, item slot, picked source, hit object, depth
     float xd[kSmPool], xs[kSmPool];              // uniforms of slots 2 (distance) and 3 (decision) of the record's bounce
-    SmCtl<kSmPool> ctl;
+    SmCtl<kSmPool, SLOTS> ctl;
 };
-static_assert(sizeof(SmShared) <= 232448, "one CTA per SM: at most 227 KB of shared memory");
-__device__ __forceinline__ SmShared &sm_shared() { return *reinterpret_cast<SmShared *>(smwave_smem); }
+static_assert(sizeof(SmShared<kMaxItemSlots>) <= 232448, "one CTA per SM: at most 227 KB of shared memory");
+template <int SLOTS>
+__device__ __forceinline__ SmShared<SLOTS> &sm_shared() { return *reinterpret_cast<SmShared<SLOTS> *>(smwave_smem); }
 
 // The pipeline, and at the same time the stages' context (vpt_stages.cuh): random numbers from Philox, scans over the staged scene,
 // radiance into the work item's fixed-point sums, the claim for the next batch issued at a stage's last step (SmSched::last_step).
-template <int METHOD>
-struct SmWave : SmSched<SmWave<METHOD>, kSmPool, kSmThreads> {
-    using Base = SmSched<SmWave<METHOD>, kSmPool, kSmThreads>;
+template <int METHOD, int SLOTS>
+struct SmWave : SmSched<SmWave<METHOD, SLOTS>, kSmPool, kSmThreads, SLOTS> {
+    using Base = SmSched<SmWave<METHOD, SLOTS>, kSmPool, kSmThreads, SLOTS>;
     using Base::lane; using Base::lp; using Base::route; using Base::count_done; using Base::alloc; using Base::pixel_of; using Base::item_pixel;
     using Base::last_step; using Base::log_p; using Base::item_pixels; using Base::Q;
-    SmShared &M;
+    SmShared<SLOTS> &M;
     const SmScene &S;
     const ConstsF &k;
     unsigned events = 0, scans = 0, nonfinite = 0, paths = 0;
 
-    __device__ SmWave(SmShared &M_, const ConstsF &k_, const LaunchParams &lp_, int log_p_, int n_owned_, int zero)
+    __device__ SmWave(SmShared<SLOTS> &M_, const ConstsF &k_, const LaunchParams &lp_, int log_p_, int n_owned_, int zero)
         : Base(M_.ctl, lp_, log_p_, n_owned_, zero), M(M_), S(M_.scene), k(k_) {}
 
     // ---- the stages' context ------------------------------------------------------------------------------------------------------
@@ -101,7 +103,7 @@ struct SmWave : SmSched<SmWave<METHOD>, kSmPool, kSmThreads> {
         const int pixel = mine ? item_pixel(Q.t_item[b], pl) : -1;
         if (pixel >= 0) ++paths;
         Rec r;
-        r.aux = (uint32_t)pl | ((uint32_t)b << 9);
+        r.aux = meta_aux(pl, b);
         const bool alive = stage_gen(*this, pixel >= 0, (uint32_t)pixel, sample, lp.width, lp.height, r);
         const int slot = alloc(alive);
         if (alive) {
@@ -131,7 +133,7 @@ struct SmWave : SmSched<SmWave<METHOD>, kSmPool, kSmThreads> {
             const int px = lane + 32 * h < n ? item_pixel(item, pl) : -1;
             mine[h] = px >= 0; pixel[h] = mine[h] ? (uint32_t)px : 0u;
             if (mine[h]) ++paths;
-            r[h].aux = (uint32_t)pl | ((uint32_t)b << 9);
+            r[h].aux = meta_aux(pl, b);
         }
         stage_gen_k<K>(*this, mine, pixel, sample, lp.width, lp.height, r, alive);
         int slot[K];

@@ -24,6 +24,7 @@ namespace f64 {
 #endif
 constexpr int kSmdThreads = VPT_SMD_THREADS;
 constexpr int kSmdPool = 2048;
+constexpr int kSmdSlots = 4; // work items in flight (vpt_smsched.cuh): reference mode is used at low sample counts
 constexpr double kSmdFixScale = 17179869184.0;       // 2^34
 constexpr double kSmdFixInv = 1.0 / 17179869184.0;
 constexpr double kSmdMaxContribution = 268435456.0;  // 2^28: a contribution at or above it (or NaN) is dropped and counted (vpt_stats.nonfinite)
@@ -35,12 +36,12 @@ struct SmSharedD {
     double br[kSmdPool], bg[kSmdPool], bb[kSmdPool];
     uint32_t sample[kSmdPool];
     uint32_t meta[kSmdPool];
-    SmCtl<kSmdPool> ctl;
+    SmCtl<kSmdPool, kSmdSlots> ctl;
 };
 static_assert(sizeof(SmSharedD) <= 232448, "one CTA per SM: at most 227 KB of shared memory");
 
-struct SmWaveD : SmSched<SmWaveD, kSmdPool, kSmdThreads> {
-    using Base = SmSched<SmWaveD, kSmdPool, kSmdThreads>;
+struct SmWaveD : SmSched<SmWaveD, kSmdPool, kSmdThreads, kSmdSlots> {
+    using Base = SmSched<SmWaveD, kSmdPool, kSmdThreads, kSmdSlots>;
     SmSharedD &M;
     const Ctx &c;
     Tally tally{0u, 0u};
@@ -92,7 +93,7 @@ struct SmWaveD : SmSched<SmWaveD, kSmdPool, kSmdThreads> {
             M.dx[slot] = d.x; M.dy[slot] = d.y; M.dz[slot] = d.z;
             M.br[slot] = 1.0; M.bg[slot] = 1.0; M.bb[slot] = 1.0;
             M.sample[slot] = sample;
-            M.meta[slot] = meta_pack((uint32_t)pl | ((uint32_t)b << 9), 0u, 0u, 0u);
+            M.meta[slot] = meta_pack(meta_aux(pl, b), 0u, 0u, 0u);
         }
         route(alive ? SQ_PRIMARY : -1, slot);
         count_stillborn(b, mine, alive);
