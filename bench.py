@@ -257,7 +257,8 @@ def main():
     for _ in range(args.warmup):
         step()
     sync()
-    sampler = ClockSampler(local); sampler.start(); time.sleep(0.15)
+    visible = [t.strip() for t in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if t.strip()]  # nvidia-smi does not honour the mask: translate
+    sampler = ClockSampler(visible[local] if local < len(visible) else local); sampler.start(); time.sleep(0.15)
     kernel_events = []
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
