@@ -155,7 +155,6 @@ int launch_render_f64(const SceneD &scene, const LaunchParams &lp, float *hdr_de
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
     if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(render_f64_smwave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmSharedD))) != cudaSuccess) return (int)e;
-    // work item = 256 pixels when that still leaves every SM at least 8 items, else one 128-pixel tile (as the FP32 pipeline)
     const int log_p = 7; // work item: one 128-pixel tile
     const int tiles_per_item = 1 << (log_p - 7);
     const int n_items = (n_blocks + tiles_per_item - 1) / tiles_per_item;

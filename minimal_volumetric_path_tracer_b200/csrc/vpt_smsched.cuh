@@ -6,7 +6,7 @@
 // 42 % of all stall samples were `no_inst`: sixteen warps per SM, each in a different stage of a 62 KB kernel, thrash the 32 KB L1.5 /
 // 6 KB L0 instruction caches.  Here the warps of an SM share ONE pool of path records and move through the stages together:
 //   * one CTA per SM, grid = number of SMs (persistent); work items = groups of pixel tiles x all samples, handed out statically
-//     (item j -> CTA j % gridDim.x), two items in flight per CTA so that a draining item overlaps the next one;
+//     (item j -> CTA j % gridDim.x), SLOTS = two or four items in flight per CTA so that draining items overlap the next ones;
 //   * POOL path records in shared memory (layout: the pipeline's), one index queue (ring) per stage, one ring of free records.  A record
 //     carries NO radiance: every vertex's direct light goes straight into the pixel's fixed-point sum;
 //   * work proceeds in ROUNDS: at a barrier warp 0 snapshots every queue's tail (one load of the 20 control words, then shuffles) into a
