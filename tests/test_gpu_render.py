@@ -244,6 +244,22 @@ def test_c3_full_size_properties(gpu):
     assert np.all(np.abs(centre - ref_mean) < 5 * ref_sigma + 0.002 * ref_mean), (centre, ref_mean, ref_sigma)
 
 
+def test_item_slot_instantiations_agree(gpu):
+    """The product kernel keeps four work items in flight per SM below 384 samples per pixel and two from there on (two instantiations of the
+    scheduler, vpt_smsched.cuh).  Which one runs must not show in the image: a 512-spp frame in one launch (two slots) equals the sum of its
+    [0,256) and [256,512) sample ranges (four slots each) up to the fp32 store, and both equal the multi-kernel HBM wavefront -- which has no
+    items at all -- bit for bit; ragged frame (not a multiple of the 128-pixel tile), all four FP32 shade methods"""
+    for method in (0, 1, 2, 4):
+        p = gpu.default_params(width=250, height=131, spp=512, method=method, seed=11, output=gpu.OUTPUT_SUM)
+        whole, st = gpu.render(p, stats=True)
+        assert st.paths == 250 * 131 * 512
+        assert np.array_equal(whole, gpu.render(p.copy(kernel=gpu.KERNEL_WAVEFRONT_HBM)))
+        lo, hi = p.copy(sample_begin=0, sample_end=256), p.copy(sample_begin=256, sample_end=512)
+        a, b = gpu.render(lo), gpu.render(hi)
+        assert np.array_equal(a, gpu.render(lo.copy(kernel=gpu.KERNEL_WAVEFRONT_HBM))) and np.array_equal(b, gpu.render(hi.copy(kernel=gpu.KERNEL_WAVEFRONT_HBM)))
+        np.testing.assert_allclose(a.astype(np.float64) + b, whole, rtol=3e-7, atol=1e-6)
+
+
 def test_c5_frame_size_tiles_and_determinism(gpu):
     """BASELINE.json config 5's frame (3840x2160 = 64800 tiles of 128 pixels) at a reduced sample count: eight interleaved tile shards -- the
     8-GPU partition -- reassemble the one-GPU frame bit for bit, and sample shards add up"""
