@@ -152,6 +152,10 @@ int vpt_render_multi(const vpt_params *p, const vpt_sphere *spheres, int32_t n_s
  * hdr_rgb holds per-pixel MEAN radiance. */
 int vpt_tonemap(const float *hdr_rgb, int32_t width, int32_t height, uint8_t *rgb8_out);
 int vpt_write_ppm(const float *hdr_rgb, int32_t width, int32_t height, const char *path);
+/* The frame before the tonemap as a binary colour PFM ("PF", scale -1.0 = little-endian floats, rows bottom to top): the side output
+ * SURVEY.md 8(f)-1 asks for, so that two renders can be compared without the 8-bit clamp (the reference has no counterpart: it only
+ * keeps the clamped values, rt.cpp:800).  hdr_rgb as above (row 0 = top of the image). */
+int vpt_write_pfm(const float *hdr_rgb, int32_t width, int32_t height, const char *path);
 
 /* Unit kernels: one device thread per row evaluates the device implementation of one reference function, so that it
  * can be compared with the reference's C++ function on identical inputs (tolerance 1e-5 relative in FP32).

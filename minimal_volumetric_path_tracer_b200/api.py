@@ -78,6 +78,7 @@ def load_library(path=None):
     lib.vpt_render_multi.argtypes = [PP, PS, C.c_int32, C.POINTER(C.c_int32), C.c_int32, PF, PST]
     lib.vpt_tonemap.argtypes = [PF, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]
     lib.vpt_write_ppm.argtypes = [PF, C.c_int32, C.c_int32, C.c_char_p]
+    lib.vpt_write_pfm.argtypes = [PF, C.c_int32, C.c_int32, C.c_char_p]
     lib.vpt_unit.argtypes = [C.c_int32, PP, PS, C.c_int32, C.c_int32, PD, C.c_int32, PD, C.c_int32]
     lib.vpt_unit_strides.argtypes = [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.vpt_philox.argtypes = [C.c_int32, C.c_int32, PU32, PU32, PU32]
@@ -224,6 +225,27 @@ def write_ppm(hdr_mean, path):
     hdr = np.ascontiguousarray(hdr_mean, dtype=np.float32)
     h, w = hdr.shape[:2]
     _check(lib, lib.vpt_write_ppm(hdr.ctypes.data_as(C.POINTER(C.c_float)), w, h, os.fsencode(path)))
+
+
+def write_pfm(hdr_mean, path):
+    """The frame before the tonemap as a binary colour PFM (little-endian floats, bottom row first): vpt_write_pfm."""
+    lib = load_library()
+    hdr = np.ascontiguousarray(hdr_mean, dtype=np.float32)
+    h, w = hdr.shape[:2]
+    _check(lib, lib.vpt_write_pfm(hdr.ctypes.data_as(C.POINTER(C.c_float)), w, h, os.fsencode(path)))
+
+
+def read_pfm(path):
+    """(h, w, 3) float32 frame of a colour PFM, row 0 = top of the image (the layout of every frame in this package)"""
+    with open(path, "rb") as f:
+        if f.readline().strip() != b"PF":
+            raise ValueError("not a colour PFM: %s" % path)
+        w, h = (int(t) for t in f.readline().split())
+        scale = float(f.readline())
+        data = np.frombuffer(f.read(w * h * 12), dtype="<f4" if scale < 0 else ">f4")
+    if data.size != w * h * 3:
+        raise ValueError("truncated PFM: %s" % path)
+    return np.ascontiguousarray(data.reshape(h, w, 3)[::-1].astype(np.float32))
 
 
 class PinnedFrame:

@@ -26,6 +26,7 @@ def parse_args(argv):
     ap.add_argument("--ref", action="store_true", help="FP64 REF mode with the reference's rounding-decided behaviours")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("-o", "--output", default="image.ppm")
+    ap.add_argument("--pfm", default=None, help="also write the frame before the tonemap as a binary PFM (little-endian floats)")
     a = ap.parse_args(argv)
     try:
         w, h = (int(v) for v in a.size.lower().split("x"))
@@ -57,6 +58,8 @@ def main(argv=None):
         hdr, st = api.render(p, scene, stats=True)
     sys.stderr.write("\r%5.2f%%\n" % 100.0)
     api.write_ppm(hdr, a.output)
+    if a.pfm:
+        api.write_pfm(hdr, a.pfm)
     sys.stderr.write("paths %d  events %d  scans %d  kernel %.3f ms  (%.1f Mpaths/s)\n" % (st.paths, st.events, st.scene_scans, st.kernel_ms,
                                                                                       st.paths / (st.kernel_ms * 1e3)))
     print("elapsed time: %gs" % (time.time() - start))

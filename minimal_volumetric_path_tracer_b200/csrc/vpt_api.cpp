@@ -575,6 +575,17 @@ int vpt_write_ppm(const float *hdr_rgb, int32_t width, int32_t height, const cha
     return std::fclose(f) == 0 ? VPT_OK : VPT_ERR_IO;
 }
 
+int vpt_write_pfm(const float *hdr_rgb, int32_t width, int32_t height, const char *path) {
+    if (!hdr_rgb || !path || width <= 0 || height <= 0) return VPT_ERR_INVALID_ARGUMENT;
+    FILE *f = std::fopen(path, "wb");
+    if (!f) return VPT_ERR_IO;
+    std::fprintf(f, "PF\n%d %d\n-1.0\n", width, height);
+    bool ok = true;
+    for (int32_t row = height - 1; row >= 0 && ok; --row) // PFM stores the bottom row first; x86-64 and the GPU hosts are little-endian
+        ok = std::fwrite(hdr_rgb + (size_t)row * width * 3, sizeof(float), (size_t)width * 3, f) == (size_t)width * 3;
+    return (std::fclose(f) == 0 && ok) ? VPT_OK : VPT_ERR_IO;
+}
+
 // ---- unit kernels -----------------------------------------------------------------------------------------------------------------
 static const int kUnitStrides[VPT_UNIT_COUNT_][2] = {
     {7, 1}, {6, 3}, {6, 1}, {7, 1}, {2, 4}, {2, 3}, {9, 6}, {2, 1}, {5, 4}, {7, 4}, {13, 6}, {3, 3}, {10, 3}, {11, 3}, {19, 3}, {9, 6}, {8, 4}, {4, 3}, {127, 4}, {8, 4}, {11, 3}, {6, 7},

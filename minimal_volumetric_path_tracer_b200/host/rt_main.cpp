@@ -3,7 +3,7 @@
 // call through the C-ABI of include/vpt.h.  Everything the reference hard-codes is an optional flag here.
 //
 //   rt <spp> [--method free|equi|mis|march|mis-distance] [--march-step x] [--march-source i] [--scene file] [--size WxH] [--sigma-a x] [--sigma-s x] [--seed n] [--ref] [--gpus n]
-//            [--max-depth n] [--continue-prob x] [-o image.ppm]
+//            [--max-depth n] [--continue-prob x] [-o image.ppm] [--pfm image.pfm]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -15,7 +15,7 @@
 
 static int usage() {
     std::fprintf(stderr, "usage: rt <spp> [--method free|equi|mis|march|mis-distance] [--march-step x] [--march-source i] [--scene file] [--size WxH] [--sigma-a x] [--sigma-s x] [--seed n] [--ref] [--gpus n] "
-                         "[--max-depth n] [--continue-prob x] [-o image.ppm]\n");
+                         "[--max-depth n] [--continue-prob x] [-o image.ppm] [--pfm image.pfm]\n");
     return 2;
 }
 
@@ -25,7 +25,7 @@ int main(int argc, char **argv) {
     vpt_params p;
     vpt_default_params(&p);
     p.spp = std::atoi(argv[1]);
-    std::string out = "image.ppm", scene_path;
+    std::string out = "image.ppm", scene_path, pfm;
     int gpus = 1;
     for (int i = 2; i < argc; ++i) {
         const std::string a = argv[i];
@@ -45,6 +45,7 @@ int main(int argc, char **argv) {
         else if (a == "--ref") { p.precision = VPT_PRECISION_FP64_REF; p.quirks = VPT_QUIRKS_REFERENCE; }
         else if (a == "--gpus") gpus = std::atoi(val("--gpus"));
         else if (a == "-o") out = val("-o");
+        else if (a == "--pfm") pfm = val("--pfm");   // the frame before the tonemap, binary floats
         else return usage();
     }
     vpt_sphere scene[VPT_MAX_SPHERES];
@@ -67,6 +68,7 @@ int main(int argc, char **argv) {
     std::fprintf(stderr, "\r%5.2f%%\n", 100.0);
     rc = vpt_write_ppm(hdr.data(), p.width, p.height, out.c_str()); // rt.cpp:812-820
     if (rc != VPT_OK) { std::fprintf(stderr, "rt: cannot write %s\n", out.c_str()); return 1; }
+    if (!pfm.empty() && vpt_write_pfm(hdr.data(), p.width, p.height, pfm.c_str()) != VPT_OK) { std::fprintf(stderr, "rt: cannot write %s\n", pfm.c_str()); return 1; }
     const std::chrono::duration<double> elapsed = std::chrono::system_clock::now() - start;
     std::fprintf(stderr, "paths %llu  events %llu  scans %llu  kernel %.3f ms  (%.1f Mpaths/s)\n", (unsigned long long)st.paths,
                  (unsigned long long)st.events, (unsigned long long)st.scene_scans, st.kernel_ms, st.paths / (st.kernel_ms * 1e3));

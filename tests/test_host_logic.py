@@ -51,6 +51,24 @@ def test_ppm_is_byte_identical_to_a_file_written_by_the_reference_binary(vpt, tm
     assert out.read_bytes() == ref
 
 
+def test_pfm_side_output(vpt, tmp_path):
+    """the frame before the tonemap as a binary PFM.  Header, byte order, bottom row first -- checked byte by byte against
+    the format's definition -- and a round trip through read_pfm; negative values, values above one, NaN and infinity pass unclamped."""
+    rng = np.random.default_rng(3)
+    hdr = rng.uniform(-0.5, 40.0, size=(4, 7, 3)).astype(np.float32)
+    hdr[1, 2] = (np.inf, -0.0, np.nan)
+    path = tmp_path / "frame.pfm"
+    vpt.write_pfm(hdr, str(path))
+    raw = path.read_bytes()
+    head = b"PF\n7 4\n-1.0\n"
+    assert raw[:len(head)] == head and len(raw) == len(head) + 4 * 7 * 3 * 4
+    assert raw[len(head):] == hdr[::-1].astype("<f4").tobytes()          # rows bottom to top, little-endian floats
+    back = vpt.read_pfm(str(path))
+    assert back.shape == hdr.shape and back.tobytes() == hdr.tobytes()
+    with pytest.raises(vpt.VptError):
+        vpt.write_pfm(hdr, str(tmp_path / "no_such_dir" / "x.pfm"))
+
+
 def test_sample_shards_partition_the_range():
     from minimal_volumetric_path_tracer_b200 import distributed as d
     for spp in (1, 7, 64, 1024, 16384):
