@@ -67,11 +67,11 @@ __global__ void __launch_bounds__(kThreadsPerBlock) render_f32_kernel(const __gr
 }
 
 // ---- SM-wide wavefront (vpt_smwave.cuh) -----------------------------------------------------------------------------------------
-template <int METHOD, int SLOTS, int CTX>
+template <int METHOD, int SLOTS>
 __global__ void __launch_bounds__(kSmThreads, 1) render_f32_smwave_kernel(const __grid_constant__ SceneF sc, const __grid_constant__ LaunchParams lp,
                                                                            const __grid_constant__ ConstsF cf, float *__restrict__ hdr, Counters *__restrict__ counters,
                                                                            int log_p, int n_owned_tiles, int n_items, int zero) {
-    SmShared<SLOTS, CTX> &M = sm_shared<SLOTS, CTX>();
+    SmShared<SLOTS> &M = sm_shared<SLOTS>();
     const int tid = (int)threadIdx.x;
     stage_scene(M.scene, sc, tid, kSmThreads);
     for (int i = tid; i < kSmPool; i += kSmThreads) M.meta[i] = 0u;
@@ -81,16 +81,10 @@ __global__ void __launch_bounds__(kSmThreads, 1) render_f32_smwave_kernel(const 
     }
     __syncthreads();
     stage_scene_tables(M.scene, tid, kSmThreads);
-    SmWave<METHOD, SLOTS, CTX> wf(M, cf, lp, log_p, n_owned_tiles, zero);
-    if (CTX == 1) {
-        wf.init(n_items);
-        __syncthreads();
-        wf.run(hdr, n_items, kSmFixInv);
-    } else {
-        for (int c = CTX - 1; c >= 0; --c) { wf.Q = &M.ctl[c]; wf.init(n_items, c, CTX); }
-        __syncthreads();
-        wf.run2(M.ctl, hdr, n_items, kSmFixInv);
-    }
+    SmWave<METHOD, SLOTS> wf(M, cf, lp, log_p, n_owned_tiles, zero);
+    wf.init(n_items);
+    __syncthreads();
+    wf.run(hdr, n_items, kSmFixInv);
     if (!counters) return;
     unsigned long long ev = wf.events, scn = wf.scans, nf = wf.nonfinite, np = wf.paths;
     for (int off = 16; off > 0; off >>= 1) {
@@ -152,25 +146,25 @@ cudaError_t philox_keys_end(KeySlot &K, cudaStream_t st) { // after the launch: 
 }
 } // namespace
 
-template <int METHOD, int SLOTS, int CTX>
+template <int METHOD, int SLOTS>
 static int launch_smwave_slots(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, cudaStream_t st, int n_owned_tiles) {
     int dev = 0, n_sm = 0;
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
     if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
-    if ((e = cudaFuncSetAttribute(render_f32_smwave_kernel<METHOD, SLOTS, CTX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmShared<SLOTS, CTX>))) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(render_f32_smwave_kernel<METHOD, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmShared<SLOTS>))) != cudaSuccess) return (int)e;
     const int log_p = 7; // work item: one 128-pixel tile
     const int n_items = n_owned_tiles;
     const int grid = n_items < n_sm ? n_items : n_sm;
 #ifdef VPT_PHILOX_ARG_KEYS
-    render_f32_smwave_kernel<METHOD, SLOTS, CTX><<<grid, kSmThreads, sizeof(SmShared<SLOTS, CTX>), st>>>(scene, lp, cf, hdr_dev, counters_dev, log_p, n_owned_tiles, n_items, 0);
+    render_f32_smwave_kernel<METHOD, SLOTS><<<grid, kSmThreads, sizeof(SmShared<SLOTS>), st>>>(scene, lp, cf, hdr_dev, counters_dev, log_p, n_owned_tiles, n_items, 0);
     return (int)cudaGetLastError();
 #else
     if (dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
     KeySlot &K = g_key_slots[dev];
     std::lock_guard<std::mutex> lock(K.m);
     if ((e = philox_keys_begin(K, st, lp.key0, lp.key1)) != cudaSuccess) return (int)e;
-    render_f32_smwave_kernel<METHOD, SLOTS, CTX><<<grid, kSmThreads, sizeof(SmShared<SLOTS, CTX>), st>>>(scene, lp, cf, hdr_dev, counters_dev, log_p, n_owned_tiles, n_items, 0);
+    render_f32_smwave_kernel<METHOD, SLOTS><<<grid, kSmThreads, sizeof(SmShared<SLOTS>), st>>>(scene, lp, cf, hdr_dev, counters_dev, log_p, n_owned_tiles, n_items, 0);
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
     return (int)philox_keys_end(K, st);
 #endif
@@ -185,13 +179,8 @@ static int launch_smwave(const SceneF &scene, const LaunchParams &lp, const Cons
 #else
     const bool many = lp.sample_end - lp.sample_begin < 384;
 #endif
-#ifdef VPT_CTX2
-    return many ? launch_smwave_slots<METHOD, kMaxItemSlots, 1>(scene, lp, cf, hdr_dev, counters_dev, st, n_owned_tiles)
-                : launch_smwave_slots<METHOD, 2, 2>(scene, lp, cf, hdr_dev, counters_dev, st, n_owned_tiles);
-#else
-    return many ? launch_smwave_slots<METHOD, kMaxItemSlots, 1>(scene, lp, cf, hdr_dev, counters_dev, st, n_owned_tiles)
-                : launch_smwave_slots<METHOD, 2, 1>(scene, lp, cf, hdr_dev, counters_dev, st, n_owned_tiles);
-#endif
+    return many ? launch_smwave_slots<METHOD, kMaxItemSlots>(scene, lp, cf, hdr_dev, counters_dev, st, n_owned_tiles)
+                : launch_smwave_slots<METHOD, 2>(scene, lp, cf, hdr_dev, counters_dev, st, n_owned_tiles);
 }
 
 // ---- ray-marching reference solver (vpt_march.cuh): one thread per pixel ---------------------------------------------------------

@@ -31,9 +31,6 @@ namespace vpt {
 #define VPT_TAIL_GEN 64 // camera samples per tail-fill batch: 64 = two per lane (run_gen_wide), 32 = one per lane
 #endif
 constexpr int kTailGen = VPT_TAIL_GEN;
-#ifndef VPT_CTX2_WAIT
-#define VPT_CTX2_WAIT // run2: what a warp does between two looks at a round number that is not published yet (nothing: spin)
-#endif
 constexpr int kSmMaxItemPixels = 128; // pixels per work item (power of two multiple of kTile)
 // Work items in flight per CTA (template parameter SLOTS of the scheduler, chosen per launch): more of them keep the pool full at low sample
 // counts, where an item's samples are generated in a few rounds while its last paths take tens of rounds to finish (64 spp: four slots
@@ -79,7 +76,6 @@ struct SmCtl {
     unsigned t_cursor[SLOTS], t_done[SLOTS]; // camera samples generated / paths finished
     unsigned ctl_pad[18 - 3 * SLOTS];
     int gen_slot, flush_slot, exit_flag;
-    unsigned left;             // run2: warps that have left the current round (the last one plans the next)
 #ifdef VPT_SMWAVE_PROFILE
     long long dbg_arrive[32];
 #endif
@@ -120,8 +116,7 @@ __device__ __forceinline__ void smem_red(unsigned *p, unsigned v, unsigned lane_
 template <class D, int POOL, int THREADS, int SLOTS>
 struct SmSched {
     using Ctl = SmCtl<POOL, SLOTS>;
-    Ctl *Q;         // the context this warp works in: the pipeline's one control block, or (run2) one of its two
-    int *next_item; // the CTA's next unassigned work item (shared by the contexts)
+    Ctl &Q;
     const LaunchParams &lp;
     const int tid, lane;
     const unsigned lz; // lane * 0, opaque to the compiler (see smem_add)
@@ -129,7 +124,6 @@ struct SmSched {
     unsigned next_raw = 0; // lane 0: the next batch of the round, claimed while the tail of the current one is still running (last_step)
 #ifdef VPT_SMWAVE_PROFILE
     unsigned long long prof[24] = {};
-    long long in_batches = 0;
 #endif
     // Ring counters only grow between plans; every plan pulls a ring's two marks (pushed / handed out, free head / tail) back by the pool size
     // once the smaller one has passed it.  A ring never holds more than POOL entries and a round hands out at most POOL, so every counter a
@@ -137,32 +131,31 @@ struct SmSched {
     static __device__ __forceinline__ unsigned ring_index(unsigned counter) { return counter >= (unsigned)POOL ? counter - (unsigned)POOL : counter; }
 
     __device__ SmSched(Ctl &Q_, const LaunchParams &lp_, int log_p_, int n_owned_, int zero)
-        : Q(&Q_), next_item(&Q_.next_item), lp(lp_), tid((int)threadIdx.x), lane((int)threadIdx.x & 31), lz((threadIdx.x & 31u) * (unsigned)zero), log_p(log_p_),
+        : Q(Q_), lp(lp_), tid((int)threadIdx.x), lane((int)threadIdx.x & 31), lz((threadIdx.x & 31u) * (unsigned)zero), log_p(log_p_),
           item_pixels(1 << log_p_), n_owned_tiles(n_owned_) {}
     __device__ __forceinline__ D &self() { return *static_cast<D *>(this); }
 
     // cooperative initialisation by the whole block (then __syncthreads)
-    // (context c of n_ctx: its records are [c * POOL, (c + 1) * POOL), its first items blockIdx + (c * SLOTS + b) * gridDim)
-    __device__ __forceinline__ void init(int n_items, int c = 0, int n_ctx = 1) {
-        for (int i = tid; i < POOL; i += THREADS) Q->freelist[i] = (uint16_t)(c * POOL + i);
-        for (int i = tid; i < SLOTS * kSmMaxItemPixels * 3; i += THREADS) (&Q->acc[0][0][0])[i] = 0ull;
+    __device__ __forceinline__ void init(int n_items) {
+        for (int i = tid; i < POOL; i += THREADS) Q.freelist[i] = (uint16_t)i;
+        for (int i = tid; i < SLOTS * kSmMaxItemPixels * 3; i += THREADS) (&Q.acc[0][0][0])[i] = 0ull;
         if (tid == 0) {
-            for (int q = 0; q < SQ_COUNT; ++q) { Q->q_tail[q] = 0u; Q->q_end[q] = 0u; }
-            Q->free_head = 0u; Q->free_tail = (unsigned)POOL;
+            for (int q = 0; q < SQ_COUNT; ++q) { Q.q_tail[q] = 0u; Q.q_end[q] = 0u; }
+            Q.free_head = 0u; Q.free_tail = (unsigned)POOL;
             for (int b = 0; b < SLOTS; ++b) {
-                const int item = (int)blockIdx.x + (c * SLOTS + b) * (int)gridDim.x;
-                Q->t_item[b] = item < n_items ? item : -1; Q->t_cursor[b] = 0u; Q->t_done[b] = 0u;
+                const int item = (int)blockIdx.x + b * (int)gridDim.x;
+                Q.t_item[b] = item < n_items ? item : -1; Q.t_cursor[b] = 0u; Q.t_done[b] = 0u;
             }
-            Q->next_item = (int)blockIdx.x + n_ctx * SLOTS * (int)gridDim.x;
-            Q->gen_slot = -1; Q->tail_limit = 0u; Q->round_no = 0u; Q->left = 0u; Q->exit_flag = 0;
+            Q.next_item = (int)blockIdx.x + SLOTS * (int)gridDim.x;
+            Q.gen_slot = -1; Q.tail_limit = 0u; Q.round_no = 0u;
         }
-        for (int i = tid; i < Ctl::kDescMax; i += THREADS) Q->desc[i] = 0xffffffffu; // (no round carries the tag 2047 before the 2047th)
+        for (int i = tid; i < Ctl::kDescMax; i += THREADS) Q.desc[i] = 0xffffffffu; // (no round carries the tag 2047 before the 2047th)
     }
 
     // The claim for the NEXT batch is issued a few hundred cycles before the current one ends (at the start of its last step: the roulette's
     // Philox block or the final routing), so that the atomic's round trip is over when the claim loop needs it; early enough to hide the
     // latency, late enough not to commit a warp to work while others idle (claiming at the START of a batch measured 15 % slower).
-    __device__ __forceinline__ void last_step() { if (lane == 0) next_raw = smem_add(&Q->round_claim, 1u, lz); }
+    __device__ __forceinline__ void last_step() { if (lane == 0) next_raw = smem_add(&Q.round_claim, 1u, lz); }
 
     // 64-bit two's-complement add from native 32-bit shared-memory atomics (a 64-bit atomicAdd on shared memory is a CAS loop):
     // low word first, its carry goes into the high word; the sum modulo 2^64 does not depend on the order of the adds
@@ -175,7 +168,7 @@ struct SmSched {
         if (hi) smem_red(w + 1, hi);
     }
     // the fixed-point sums of the pixel a record belongs to (meta: pixel-in-item, item slot)
-    __device__ __forceinline__ unsigned long long *pixel_acc(uint32_t meta) { return Q->acc[meta_slot(meta)][meta_pixel(meta)]; }
+    __device__ __forceinline__ unsigned long long *pixel_acc(uint32_t meta) { return Q.acc[meta_slot(meta)][meta_pixel(meta)]; }
 
     // ---- work items: item j = owned tiles [j * K, (j + 1) * K), K = item_pixels / kTile -----------------------------------------
     // (32-bit arithmetic: n_pixels is an int32, so tile and pixel indices fit; -1 = outside the image / not this rank's tile)
@@ -185,7 +178,7 @@ struct SmSched {
         const unsigned pixel = (owned * (unsigned)lp.tile_count + (unsigned)lp.tile_rank) * (unsigned)kTile + ((unsigned)pl & (unsigned)(kTile - 1));
         return pixel < (unsigned)lp.n_pixels ? (int)pixel : -1;
     }
-    __device__ __forceinline__ uint32_t pixel_of(uint32_t meta) const { return (uint32_t)item_pixel(Q->t_item[meta_slot(meta)], (int)meta_pixel(meta)); }
+    __device__ __forceinline__ uint32_t pixel_of(uint32_t meta) const { return (uint32_t)item_pixel(Q.t_item[meta_slot(meta)], (int)meta_pixel(meta)); }
 
     // ---- queue / pool primitives (warp-aggregated shared-memory atomics) ------------------------------------------------------------
     // Route every lane's record in ONE step: dest = a stage queue (SQ_*), kDestFree (the record goes back to the free ring) or -1 (nothing).
@@ -197,17 +190,17 @@ struct SmSched {
         const int leader = __ffs(grp) - 1;
         unsigned base = 0;
         // counters: q_tail[0..5] are words 0..5 of the control block, free_tail is word 13; rings: queue[0..5] and, right behind them, freelist
-        if (lane == leader) base = smem_add(&Q->q_tail[0] + (dest == kDestFree ? 13 : dest), (unsigned)__popc(grp), lz);
+        if (lane == leader) base = smem_add(&Q.q_tail[0] + (dest == kDestFree ? 13 : dest), (unsigned)__popc(grp), lz);
         base = __shfl_sync(grp, base, leader);
-        (&Q->queue[0][0])[dest * POOL + (int)ring_index(base + __popc(grp & ((1u << lane) - 1u)))] = (uint16_t)slot;
+        (&Q.queue[0][0])[dest * POOL + (int)ring_index(base + __popc(grp & ((1u << lane) - 1u)))] = (uint16_t)slot;
     }
     __device__ __forceinline__ int alloc(bool flag) { // the round's snapshot guarantees enough free records below free_tail
         const unsigned m = __ballot_sync(0xffffffffu, flag);
         if (m == 0u) return -1;
         unsigned base = 0;
-        if (lane == 0) base = smem_add(&Q->free_head, (unsigned)__popc(m), lz);
+        if (lane == 0) base = smem_add(&Q.free_head, (unsigned)__popc(m), lz);
         base = __shfl_sync(0xffffffffu, base, 0);
-        return flag ? (int)Q->freelist[ring_index(base + __popc(m & ((1u << lane) - 1u)))] : -1;
+        return flag ? (int)Q.freelist[ring_index(base + __popc(m & ((1u << lane) - 1u)))] : -1;
     }
     // K new records per lane (run_gen_wide): all taken from the free ring and pushed to queue q, one atomic each for the whole warp
     template <int K>
@@ -217,14 +210,14 @@ struct SmSched {
         for (int h = 0; h < K; ++h) { m[h] = __ballot_sync(0xffffffffu, f[h]); n += (unsigned)__popc(m[h]); s[h] = -1; }
         if (n == 0u) return;
         unsigned from = 0, to = 0;
-        if (lane == 0) { from = smem_add(&Q->free_head, n, lz); to = smem_add(&Q->q_tail[q], n, lz); }
+        if (lane == 0) { from = smem_add(&Q.free_head, n, lz); to = smem_add(&Q.q_tail[q], n, lz); }
         from = __shfl_sync(0xffffffffu, from, 0); to = __shfl_sync(0xffffffffu, to, 0);
         const unsigned below = (1u << lane) - 1u;
         unsigned before = 0;
 #pragma unroll
         for (int h = 0; h < K; ++h) {
             const unsigned rank = before + (unsigned)__popc(m[h] & below);
-            if (f[h]) { s[h] = (int)Q->freelist[ring_index(from + rank)]; Q->queue[q][ring_index(to + rank)] = (uint16_t)s[h]; }
+            if (f[h]) { s[h] = (int)Q.freelist[ring_index(from + rank)]; Q.queue[q][ring_index(to + rank)] = (uint16_t)s[h]; }
             before += (unsigned)__popc(m[h]);
         }
     }
@@ -233,39 +226,38 @@ struct SmSched {
 #pragma unroll
         for (int b = 0; b < SLOTS; ++b) {
             const unsigned m = __ballot_sync(0xffffffffu, ended && meta_slot(meta) == (uint32_t)b);
-            if (lane == 0 && m) smem_red(&Q->t_done[b], (unsigned)__popc(m), lz);
+            if (lane == 0 && m) smem_red(&Q.t_done[b], (unsigned)__popc(m), lz);
         }
     }
     // generation bookkeeping: samples of pixels outside the image and paths killed by the first roulette are finished already
     __device__ __forceinline__ void count_stillborn(int item_slot, bool mine, bool alive) {
         const unsigned m = __ballot_sync(0xffffffffu, mine && !alive);
-        if (lane == 0 && m) smem_red(&Q->t_done[item_slot], (unsigned)__popc(m), lz);
+        if (lane == 0 && m) smem_red(&Q.t_done[item_slot], (unsigned)__popc(m), lz);
     }
 
     // ---- item bookkeeping ---------------------------------------------------------------------------------------------------------------
     // every thread: write the finished item's pixels and clear its accumulators; thread 0: load the next item into the slot
     __device__ __forceinline__ void flush_item(int b, float *__restrict__ hdr, int n_items, double fix_inv) {
-        const int item = Q->t_item[b];
+        const int item = Q.t_item[b];
         for (int pl = tid; pl < item_pixels; pl += THREADS) {
             const int pixel = item_pixel(item, pl);
             if (pixel >= 0) {
                 float *out = hdr + (size_t)pixel * 3;
-                for (int c = 0; c < 3; ++c) out[c] = (float)((double)(long long)Q->acc[b][pl][c] * fix_inv * lp.out_scale);
+                for (int c = 0; c < 3; ++c) out[c] = (float)((double)(long long)Q.acc[b][pl][c] * fix_inv * lp.out_scale);
             }
-            Q->acc[b][pl][0] = 0ull; Q->acc[b][pl][1] = 0ull; Q->acc[b][pl][2] = 0ull;
+            Q.acc[b][pl][0] = 0ull; Q.acc[b][pl][1] = 0ull; Q.acc[b][pl][2] = 0ull;
         }
         __syncthreads(); // everyone has read t_item[b]
         if (tid == 0) {
-            const int next = Q->next_item;
-            if (next < n_items) { Q->t_item[b] = next; Q->next_item = next + (int)gridDim.x; Q->t_cursor[b] = 0u; Q->t_done[b] = 0u; }
-            else Q->t_item[b] = -1;
+            const int next = Q.next_item;
+            if (next < n_items) { Q.t_item[b] = next; Q.next_item = next + (int)gridDim.x; Q.t_cursor[b] = 0u; Q.t_done[b] = 0u; }
+            else Q.t_item[b] = -1;
         }
     }
 
     // ---- one round: warp 0 snapshots the queues (lane = claim rank) and plans the generation --------------------------------------
     // Every other warp waits for this, so the dependent chain is kept short: ONE shared-memory load fetches all control words (lane i
     // reads word i), everything else is register shuffles, and every lane computes the few scalar decisions redundantly.
-    template <bool ASYNC>
     __device__ __forceinline__ void plan_round(unsigned item_total) {
         static_assert(offsetof(Ctl, t_item) - offsetof(Ctl, q_tail) == 14 * sizeof(unsigned) &&
                           offsetof(Ctl, t_done) - offsetof(Ctl, q_tail) == (14 + 2 * SLOTS) * sizeof(unsigned) && 14 + 3 * SLOTS <= 32,
@@ -273,13 +265,13 @@ struct SmSched {
         static_assert(offsetof(Ctl, free_tail) - offsetof(Ctl, q_tail) == 13 * sizeof(unsigned) &&
                           offsetof(Ctl, freelist) - offsetof(Ctl, queue) == SQ_COUNT * POOL * sizeof(uint16_t),
                       "route() addresses the free ring as queue number SQ_COUNT");
-        unsigned v = (&Q->q_tail[0])[lane]; // words 0 .. 13 + 3 * SLOTS are the control block, the padding behind it is never used
+        unsigned v = (&Q.q_tail[0])[lane]; // words 0 .. 13 + 3 * SLOTS are the control block, the padding behind it is never used
         { // keep the ring counters below 2 * POOL: lanes 0..5 / 6..11 hold a queue's pushed / handed-out marks, 12 / 13 the free ring's head / tail
             const unsigned low = __shfl_sync(0xffffffffu, v, lane < 6 ? lane + 6 : (lane == 13 ? 12 : lane)); // the smaller mark of the pair
-            if (lane < 14 && low >= (unsigned)POOL) { v -= (unsigned)POOL; (&Q->q_tail[0])[lane] = v; }
+            if (lane < 14 && low >= (unsigned)POOL) { v -= (unsigned)POOL; (&Q.q_tail[0])[lane] = v; }
         }
-        const int prev_gen = Q->gen_slot;
-        const unsigned prev_limit = Q->tail_limit; // the tail fill overshoots its limit by the claims that found nothing
+        const int prev_gen = Q.gen_slot;
+        const unsigned prev_limit = Q.tail_limit; // the tail fill overshoots its limit by the claims that found nothing
         const unsigned n_free = __shfl_sync(0xffffffffu, v, 13) - __shfl_sync(0xffffffffu, v, 12);
         // the slot to write out (all samples generated, all paths finished; the lowest such slot, one per round) and the slot to generate
         // from (the oldest item that still has samples)
@@ -307,7 +299,7 @@ struct SmSched {
             unsigned count = tail - handed;
             if (left != 0u) count &= ~31u;
             begin = handed; end = handed + count;
-            Q->q_end[q] = end;
+            Q.q_end[q] = end;
         }
         unsigned queued = end - begin;
 #pragma unroll
@@ -325,154 +317,17 @@ struct SmSched {
 #pragma unroll
         for (int off = 1; off < 8; off <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += u; }
         const unsigned first = incl - nb;
-        if (lane < 8) { Q->rb_first[lane] = first; Q->rb_begin[lane] = begin; Q->rb_end[lane] = end; }
+        if (lane < 8) { Q.rb_first[lane] = first; Q.rb_begin[lane] = begin; Q.rb_end[lane] = end; }
         const unsigned total = __shfl_sync(0xffffffffu, incl, 7);
         if (lane == 0) {
             const unsigned after = gen_begin + n_gen;                       // the cursor after the planned generation batches
             const unsigned budget = (n_free - n_gen) & ~31u;                // free records the tail fill may use: one per sample, whole batches
             const unsigned limit = min(after + budget, item_total);         // (a last, partial batch of the item needs fewer records than it claims)
 #pragma unroll
-            for (int b = 0; b < SLOTS; ++b) Q->t_cursor[b] = gen == b ? after : cur[b];
-            Q->tail_limit = gen >= 0 ? limit : 0u;
-            Q->flush_slot = flush; Q->gen_slot = gen; Q->round_claim = (unsigned)(THREADS / 32);
-            if (!ASYNC) Q->round_no = Q->round_no + 1u; // (run2 publishes the round number last: plan_publish)
-            Q->exit_flag = (total == 0u && flush < 0 && gen < 0) ? 1 : 0; // nothing queued, nothing to generate, nothing to write out
-        }
-    }
-
-    // ---- one round's batches: claim, run, route; then the tail fill.  ASYNC (run2): the planner has written the descriptor table -------
-    template <bool ASYNC>
-    __device__ __forceinline__ void run_round() {
-#ifdef VPT_SMWAVE_PROFILE
-#define SMW_BATCH(q, call) { const long long b0 = clock64(); call; const long long b1 = clock64(); prof[q] += b1 - b0; prof[8 + q] += 1; in_batches += b1 - b0; }
-#else
-#define SMW_BATCH(q, call) { call; }
-#endif
-        const unsigned total = Q->rb_first[7];
-        const int gen_slot = Q->gen_slot;
-        const unsigned gen_begin = Q->rb_begin[SQ_COUNT];
-        const unsigned tag = (*(volatile unsigned *)&Q->round_no & 0x7ffu) << 21;
-        // the batch table (rb_first / rb_begin / rb_end by rank) -> one descriptor per batch
-        const uint4 f0 = *reinterpret_cast<const uint4 *>(&Q->rb_first[0]), f1 = *reinterpret_cast<const uint4 *>(&Q->rb_first[4]);
-        auto make_desc = [&](unsigned k) -> unsigned {
-            const int rank = (k >= f0.y) + (k >= f0.z) + (k >= f0.w) + (k >= f1.x) + (k >= f1.y) + (k >= f1.z);
-            const unsigned j = k - Q->rb_first[rank], start = Q->rb_begin[rank] + (j << 5);
-            const unsigned n = min(32u, Q->rb_end[rank] - start);
-            return (unsigned)rank | (n << 3) | ((rank == SQ_COUNT ? j : ring_index(start)) << 9) | tag;
-        };
-        if (!ASYNC) { // every warp spells out its share of the table (the plan, on which all warps wait, stays short); a reader checks the round tag
-            constexpr int kPer = (Ctl::kDescMax + THREADS / 32 - 1) / (THREADS / 32);
-            const unsigned k = (unsigned)(tid >> 5) * (unsigned)kPer + (unsigned)lane;
-            if (lane < kPer && k < total) Q->desc[k] = make_desc(k);
-        }
-        // the first batch of a round needs no atomic and no table: warp w takes batch w, the claim counter starts behind those (plan_round)
-        unsigned kb = (unsigned)tid >> 5;
-        unsigned dsc = kb < total ? make_desc(kb) : 0u;
-        while (kb < total) {
-            const int rank = (int)(dsc & 7u), n = (int)((dsc >> 3) & 63u);
-            const unsigned idx = (dsc >> 9) & 0xfffu;
-            const unsigned start = gen_begin + (idx << 5);             // (generation batches only)
-            const unsigned e = ring_index(idx + (unsigned)lane);       // this lane's queue entry
-            switch (rank) {
-            case 0: SMW_BATCH(SQ_SURF_F, self().template run_stage<SQ_SURF_F>(lane < n ? (int)Q->queue[SQ_SURF_F][e] : -1)); break;
-            case 1: SMW_BATCH(SQ_SURF_L, self().template run_stage<SQ_SURF_L>(lane < n ? (int)Q->queue[SQ_SURF_L][e] : -1)); break;
-            case 2: SMW_BATCH(SQ_PRIMARY, self().template run_stage<SQ_PRIMARY>(lane < n ? (int)Q->queue[SQ_PRIMARY][e] : -1)); break;
-            case 3: SMW_BATCH(SQ_MED_AREA, self().template run_stage<SQ_MED_AREA>(lane < n ? (int)Q->queue[SQ_MED_AREA][e] : -1)); break;
-            case 4: SMW_BATCH(SQ_MED_POINT, self().template run_stage<SQ_MED_POINT>(lane < n ? (int)Q->queue[SQ_MED_POINT][e] : -1)); break;
-            case 5: SMW_BATCH(SQ_SURF_P, self().template run_stage<SQ_SURF_P>(lane < n ? (int)Q->queue[SQ_SURF_P][e] : -1)); break;
-            default: SMW_BATCH(6, self().run_gen(gen_slot, start, n)); last_step(); break;
-            }
-            // (claiming the next batch before running this one hides the atomic's latency but commits warps too early: measured slower)
-            // (taking ALL batches round-robin without atomics: 6750 against 7340 -- the dynamic claim is what balances 12 000-cycle SURF_L batches
-            // against 4 000-cycle ones)
-            kb = __shfl_sync(0xffffffffu, next_raw, 0);
-            if (kb < total) do { dsc = *(volatile unsigned *)&Q->desc[kb]; } while ((dsc ^ tag) >> 21); // (written thousands of cycles ago: never loops)
-        }
-        // tail fill: the round's batches are all claimed; instead of idling at the barrier generate camera samples up to the limit the
-        // plan set (one free record per sample is guaranteed), they are consumed in the next round.  One atomic per batch.
-        if (gen_slot >= 0) {
-            const unsigned limit = Q->tail_limit;
-            for (;;) {
-                unsigned base = limit;
-                if (lane == 0 && *(volatile unsigned *)&Q->t_cursor[gen_slot] < limit) base = smem_add(&Q->t_cursor[gen_slot], (unsigned)kTailGen, lz);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (base >= limit) break;
-                // (the last samples of a round in 32-sample batches, for a finer grain where the round ends: 8655 against 8686 -- the one-per-lane
-                // form is slower per sample than the gain in arrival spread)
-                if (kTailGen > 32) { SMW_BATCH(7, self().run_gen_wide(gen_slot, base, (int)min((unsigned)kTailGen, limit - base))); }
-                else { SMW_BATCH(7, self().run_gen(gen_slot, base, (int)min(32u, limit - base))); }
-            }
-        }
-    }
-
-    // ---- run2: two contexts (half pools) whose rounds alternate -- no CTA barrier ------------------------------------------------------
-    // Every warp works A(1), B(1), A(2), B(2), ...; the LAST warp to leave a context's round plans that context's next round (alone: flush,
-    // plan, descriptor table, then the round number as the release) while the other 23 are already inside the other context's batches, so
-    // the arrival spread and the plan of one context hide behind the batches of the other.  Each context keeps the rank order inside its
-    // round (stage coherence: instruction caches).
-    __device__ __forceinline__ void flush_item_warp(int b, float *__restrict__ hdr, int n_items, double fix_inv) {
-        const int item = Q->t_item[b];
-        for (int pl = lane; pl < item_pixels; pl += 32) {
-            const int pixel = item_pixel(item, pl);
-            if (pixel >= 0) {
-                float *out = hdr + (size_t)pixel * 3;
-                for (int c = 0; c < 3; ++c) out[c] = (float)((double)(long long)Q->acc[b][pl][c] * fix_inv * lp.out_scale);
-            }
-            Q->acc[b][pl][0] = 0ull; Q->acc[b][pl][1] = 0ull; Q->acc[b][pl][2] = 0ull;
-        }
-        __syncwarp();
-        if (lane == 0) {
-            const int next = atomicAdd(next_item, (int)gridDim.x);
-            if (next < n_items) { Q->t_item[b] = next; Q->t_cursor[b] = 0u; Q->t_done[b] = 0u; }
-            else Q->t_item[b] = -1;
-        }
-        __syncwarp();
-    }
-    // one whole warp, nobody else inside this context
-    __device__ __forceinline__ void plan_publish(unsigned item_total, float *__restrict__ hdr, int n_items, double fix_inv) {
-        plan_round<true>(item_total);
-        __syncwarp();
-        const int flush = *(volatile int *)&Q->flush_slot;
-        if (flush >= 0) flush_item_warp(flush, hdr, n_items, fix_inv);
-        const unsigned round = *(volatile unsigned *)&Q->round_no + 1u;
-        const unsigned total = *(volatile unsigned *)&Q->rb_first[7], tag = (round & 0x7ffu) << 21;
-        for (unsigned k = (unsigned)lane; k < total; k += 32u) {
-            int rank = 0;
-#pragma unroll
-            for (int r = 1; r <= SQ_COUNT; ++r) rank += (k >= *(volatile unsigned *)&Q->rb_first[r]);
-            const unsigned j = k - *(volatile unsigned *)&Q->rb_first[rank], start = *(volatile unsigned *)&Q->rb_begin[rank] + (j << 5);
-            const unsigned n = min(32u, *(volatile unsigned *)&Q->rb_end[rank] - start);
-            Q->desc[k] = (unsigned)rank | (n << 3) | ((rank == SQ_COUNT ? j : ring_index(start)) << 9) | tag;
-        }
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) *(volatile unsigned *)&Q->round_no = round;
-    }
-    __device__ __forceinline__ void run2(Ctl *ctl, float *__restrict__ hdr, int n_items, double fix_inv) {
-        constexpr unsigned W = THREADS / 32;
-        const unsigned item_total = (unsigned)item_pixels * (unsigned)(lp.sample_end - lp.sample_begin);
-        if ((tid >> 5) < 2) { Q = &ctl[tid >> 5]; plan_publish(item_total, hdr, n_items, fix_inv); } // round 1 of both contexts
-        __syncthreads();
-        unsigned want0 = 1u, want1 = 1u, finished = 0u;
-        for (int c = 0; finished != 3u; c ^= 1) {
-            if ((finished >> c) & 1u) continue;
-            Q = &ctl[c];
-            const unsigned want = c ? want1 : want0;
-            while (*(volatile unsigned *)&Q->round_no < want) { VPT_CTX2_WAIT; }
-            __threadfence_block();
-            if (*(volatile int *)&Q->exit_flag) { finished |= 1u << c; continue; }
-            run_round<true>();
-            __threadfence_block();
-            __syncwarp();
-            unsigned old = 0u;
-            if (lane == 0) old = smem_add(&Q->left, 1u, lz);
-            old = __shfl_sync(0xffffffffu, old, 0);
-            if (old == W - 1u) { // the last warp out: everybody's pushes of this round are visible
-                __threadfence_block();
-                if (lane == 0) Q->left = 0u;
-                plan_publish(item_total, hdr, n_items, fix_inv);
-            }
-            if (c) ++want1; else ++want0;
+            for (int b = 0; b < SLOTS; ++b) Q.t_cursor[b] = gen == b ? after : cur[b];
+            Q.tail_limit = gen >= 0 ? limit : 0u;
+            Q.flush_slot = flush; Q.gen_slot = gen; Q.round_claim = (unsigned)(THREADS / 32); Q.round_no = Q.round_no + 1u;
+            Q.exit_flag = (total == 0u && flush < 0 && gen < 0) ? 1 : 0; // nothing queued, nothing to generate, nothing to write out
         }
     }
 
@@ -482,30 +337,87 @@ struct SmSched {
         for (;;) {
             SMW_T(t0);
 #ifdef VPT_SMWAVE_PROFILE
-            if (lane == 0) Q->dbg_arrive[tid >> 5] = t0;
+            if (lane == 0) Q.dbg_arrive[tid >> 5] = t0;
 #endif
             __syncthreads(); // (A) the previous round's pushes / releases / counters are visible
             SMW_T(t1);
-            if (tid < 32) plan_round<false>(item_total);
+            if (tid < 32) plan_round(item_total);
             __syncthreads(); // (B) the plan is visible
             SMW_T(t2);
 #ifdef VPT_SMWAVE_PROFILE
             if (tid == 0) { // arrival spread at (A): last arrival minus mean arrival (x warps = idle warp-cycles), and last arrival -> (B) passed
                 long long last = 0, sum = 0;
-                for (int w = 0; w < THREADS / 32; ++w) { const long long a = Q->dbg_arrive[w]; last = a > last ? a : last; sum += a; }
+                for (int w = 0; w < THREADS / 32; ++w) { const long long a = Q.dbg_arrive[w]; last = a > last ? a : last; sum += a; }
                 prof[23] += (unsigned long long)(last * (THREADS / 32) - sum);
                 prof[22] += (unsigned long long)((t2 - last) * (THREADS / 32));
             }
 #endif
             SMW_ADD(16, t1 - t0); SMW_ADD(17, t2 - t1); SMW_ADD(20, tid == 0);
-            if (Q->exit_flag) break;
-            if (Q->flush_slot >= 0) flush_item(Q->flush_slot, hdr, n_items, fix_inv); // its records are all finished; the round below only touches the other item
+            if (Q.exit_flag) break;
+            if (Q.flush_slot >= 0) flush_item(Q.flush_slot, hdr, n_items, fix_inv); // its records are all finished; the round below only touches the other item
             SMW_T(t3);
             SMW_ADD(21, t3 - t2);
 #ifdef VPT_SMWAVE_PROFILE
-            in_batches = 0;
+            long long in_batches = 0;
+#define SMW_BATCH(q, call) { const long long b0 = clock64(); call; const long long b1 = clock64(); prof[q] += b1 - b0; prof[8 + q] += 1; in_batches += b1 - b0; }
+#else
+#define SMW_BATCH(q, call) { call; }
 #endif
-            run_round<false>();
+            const unsigned total = Q.rb_first[7];
+            const int gen_slot = Q.gen_slot;
+            const unsigned gen_begin = Q.rb_begin[SQ_COUNT];
+            const unsigned tag = (Q.round_no & 0x7ffu) << 21;
+            // the batch table (rb_first / rb_begin / rb_end by rank) -> one descriptor per batch
+            const uint4 f0 = *reinterpret_cast<const uint4 *>(&Q.rb_first[0]), f1 = *reinterpret_cast<const uint4 *>(&Q.rb_first[4]);
+            auto make_desc = [&](unsigned k) -> unsigned {
+                const int rank = (k >= f0.y) + (k >= f0.z) + (k >= f0.w) + (k >= f1.x) + (k >= f1.y) + (k >= f1.z);
+                const unsigned j = k - Q.rb_first[rank], start = Q.rb_begin[rank] + (j << 5);
+                const unsigned n = min(32u, Q.rb_end[rank] - start);
+                return (unsigned)rank | (n << 3) | ((rank == SQ_COUNT ? j : ring_index(start)) << 9) | tag;
+            };
+            { // every warp spells out its share of the table (the plan, on which all warps wait, stays short); a reader checks the round tag
+                constexpr int kPer = (Ctl::kDescMax + THREADS / 32 - 1) / (THREADS / 32);
+                const unsigned k = (unsigned)(tid >> 5) * (unsigned)kPer + (unsigned)lane;
+                if (lane < kPer && k < total) Q.desc[k] = make_desc(k);
+            }
+            // the first batch of a round needs no atomic and no table: warp w takes batch w, the claim counter starts behind those (plan_round)
+            unsigned kb = (unsigned)tid >> 5;
+            unsigned dsc = kb < total ? make_desc(kb) : 0u;
+            while (kb < total) {
+                const int rank = (int)(dsc & 7u), n = (int)((dsc >> 3) & 63u);
+                const unsigned idx = (dsc >> 9) & 0xfffu;
+                const unsigned start = gen_begin + (idx << 5);             // (generation batches only)
+                const unsigned e = ring_index(idx + (unsigned)lane);       // this lane's queue entry
+                switch (rank) {
+                case 0: SMW_BATCH(SQ_SURF_F, self().template run_stage<SQ_SURF_F>(lane < n ? (int)Q.queue[SQ_SURF_F][e] : -1)); break;
+                case 1: SMW_BATCH(SQ_SURF_L, self().template run_stage<SQ_SURF_L>(lane < n ? (int)Q.queue[SQ_SURF_L][e] : -1)); break;
+                case 2: SMW_BATCH(SQ_PRIMARY, self().template run_stage<SQ_PRIMARY>(lane < n ? (int)Q.queue[SQ_PRIMARY][e] : -1)); break;
+                case 3: SMW_BATCH(SQ_MED_AREA, self().template run_stage<SQ_MED_AREA>(lane < n ? (int)Q.queue[SQ_MED_AREA][e] : -1)); break;
+                case 4: SMW_BATCH(SQ_MED_POINT, self().template run_stage<SQ_MED_POINT>(lane < n ? (int)Q.queue[SQ_MED_POINT][e] : -1)); break;
+                case 5: SMW_BATCH(SQ_SURF_P, self().template run_stage<SQ_SURF_P>(lane < n ? (int)Q.queue[SQ_SURF_P][e] : -1)); break;
+                default: SMW_BATCH(6, self().run_gen(gen_slot, start, n)); last_step(); break;
+                }
+                // (claiming the next batch before running this one hides the atomic's latency but commits warps too early: measured slower)
+                // (taking ALL batches round-robin without atomics: 6750 against 7340 -- the dynamic claim is what balances 12 000-cycle SURF_L batches
+                // against 4 000-cycle ones)
+                kb = __shfl_sync(0xffffffffu, next_raw, 0);
+                if (kb < total) do { dsc = *(volatile unsigned *)&Q.desc[kb]; } while ((dsc ^ tag) >> 21); // (written thousands of cycles ago: never loops)
+            }
+            // tail fill: the round's batches are all claimed; instead of idling at the barrier generate camera samples up to the limit the
+            // plan set (one free record per sample is guaranteed), they are consumed in the next round.  One atomic per batch.
+            if (gen_slot >= 0) {
+                const unsigned limit = Q.tail_limit;
+                for (;;) {
+                    unsigned base = limit;
+                    if (lane == 0 && *(volatile unsigned *)&Q.t_cursor[gen_slot] < limit) base = smem_add(&Q.t_cursor[gen_slot], (unsigned)kTailGen, lz);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (base >= limit) break;
+                    // (the last samples of a round in 32-sample batches, for a finer grain where the round ends: 8655 against 8686 -- the one-per-lane
+                    // form is slower per sample than the gain in arrival spread)
+                    if (kTailGen > 32) { SMW_BATCH(7, self().run_gen_wide(gen_slot, base, (int)min((unsigned)kTailGen, limit - base))); }
+                    else { SMW_BATCH(7, self().run_gen(gen_slot, base, (int)min(32u, limit - base))); }
+                }
+            }
 #ifdef VPT_SMWAVE_PROFILE
             prof[18] += clock64() - t3 - in_batches;
 #endif

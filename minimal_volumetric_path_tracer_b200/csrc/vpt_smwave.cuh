@@ -24,7 +24,7 @@ constexpr float kSmFixScale = 1073741824.0f; // 2^30
 constexpr double kSmFixInv = 1.0 / 1073741824.0;
 constexpr float kSmMaxContribution = 4294967296.0f; // 2^32: a contribution at or above it (or NaN) is dropped and counted (vpt_stats.nonfinite)
 
-template <int SLOTS, int CTX = 1>
+template <int SLOTS>
 struct SmShared {
     SmScene scene; // first: scan_sm_call finds it at the start of the dynamic shared memory
     // ---- path records (SoA) ----
@@ -34,26 +34,26 @@ struct SmShared {
     uint32_t sample[kSmPool];
     uint32_t meta[kSmPool];                      // meta_pack(): pixel-in-item, item slot, picked source, hit object, depth
     float xd[kSmPool], xs[kSmPool];              // uniforms of slots 2 (distance) and 3 (decision) of the record's bounce
-    SmCtl<kSmPool / CTX, SLOTS> ctl[CTX]; // CTX = 2: two half pools whose rounds alternate (SmSched::run2)
+    SmCtl<kSmPool, SLOTS> ctl;
 };
-static_assert(sizeof(SmShared<kMaxItemSlots>) <= 232448 && sizeof(SmShared<2, 2>) <= 232448, "one CTA per SM: at most 227 KB of shared memory");
-template <int SLOTS, int CTX>
-__device__ __forceinline__ SmShared<SLOTS, CTX> &sm_shared() { return *reinterpret_cast<SmShared<SLOTS, CTX> *>(smwave_smem); }
+static_assert(sizeof(SmShared<kMaxItemSlots>) <= 232448, "one CTA per SM: at most 227 KB of shared memory");
+template <int SLOTS>
+__device__ __forceinline__ SmShared<SLOTS> &sm_shared() { return *reinterpret_cast<SmShared<SLOTS> *>(smwave_smem); }
 
 // The pipeline, and at the same time the stages' context (vpt_stages.cuh): random numbers from Philox, scans over the staged scene,
 // radiance into the work item's fixed-point sums, the claim for the next batch issued at a stage's last step (SmSched::last_step).
-template <int METHOD, int SLOTS, int CTX = 1>
-struct SmWave : SmSched<SmWave<METHOD, SLOTS, CTX>, kSmPool / CTX, kSmThreads, SLOTS> {
-    using Base = SmSched<SmWave<METHOD, SLOTS, CTX>, kSmPool / CTX, kSmThreads, SLOTS>;
+template <int METHOD, int SLOTS>
+struct SmWave : SmSched<SmWave<METHOD, SLOTS>, kSmPool, kSmThreads, SLOTS> {
+    using Base = SmSched<SmWave<METHOD, SLOTS>, kSmPool, kSmThreads, SLOTS>;
     using Base::lane; using Base::lp; using Base::route; using Base::count_done; using Base::alloc; using Base::pixel_of; using Base::item_pixel;
     using Base::last_step; using Base::log_p; using Base::item_pixels; using Base::Q;
-    SmShared<SLOTS, CTX> &M;
+    SmShared<SLOTS> &M;
     const SmScene &S;
     const ConstsF &k;
     unsigned events = 0, scans = 0, nonfinite = 0, paths = 0;
 
-    __device__ SmWave(SmShared<SLOTS, CTX> &M_, const ConstsF &k_, const LaunchParams &lp_, int log_p_, int n_owned_, int zero)
-        : Base(M_.ctl[0], lp_, log_p_, n_owned_, zero), M(M_), S(M_.scene), k(k_) {}
+    __device__ SmWave(SmShared<SLOTS> &M_, const ConstsF &k_, const LaunchParams &lp_, int log_p_, int n_owned_, int zero)
+        : Base(M_.ctl, lp_, log_p_, n_owned_, zero), M(M_), S(M_.scene), k(k_) {}
 
     // ---- the stages' context ------------------------------------------------------------------------------------------------------
     __device__ __forceinline__ float4 rnd(const Rec &r, uint32_t block) const {
@@ -100,7 +100,7 @@ struct SmWave : SmSched<SmWave<METHOD, SLOTS, CTX>, kSmPool / CTX, kSmThreads, S
         const unsigned g = g0 + (unsigned)lane;
         const int pl = (int)(g & (unsigned)(item_pixels - 1));
         const uint32_t sample = (uint32_t)lp.sample_begin + (g >> log_p);
-        const int pixel = mine ? item_pixel(Q->t_item[b], pl) : -1;
+        const int pixel = mine ? item_pixel(Q.t_item[b], pl) : -1;
         if (pixel >= 0) ++paths;
         Rec r;
         r.aux = meta_aux(pl, b);
@@ -124,7 +124,7 @@ struct SmWave : SmSched<SmWave<METHOD, SLOTS, CTX>, kSmPool / CTX, kSmThreads, S
         bool mine[K], alive[K];
         uint32_t pixel[K], sample[K];
         Rec r[K];
-        const int item = Q->t_item[b];
+        const int item = Q.t_item[b];
 #pragma unroll
         for (int h = 0; h < K; ++h) {
             const unsigned g = g0 + (unsigned)(lane + 32 * h);
@@ -152,7 +152,7 @@ struct SmWave : SmSched<SmWave<METHOD, SLOTS, CTX>, kSmPool / CTX, kSmThreads, S
             }
             dead += (unsigned)__popc(__ballot_sync(0xffffffffu, lane + 32 * h < n && !alive[h]));
         }
-        if (lane == 0 && dead) smem_red(&Q->t_done[b], dead, Base::lz);
+        if (lane == 0 && dead) smem_red(&Q.t_done[b], dead, Base::lz);
     }
 
     // ---- the stage batches: load the fields the stage reads, run it (vpt_stages.cuh), store what it changed, route ---------------------

@@ -75,7 +75,7 @@ struct SmWaveD : SmSched<SmWaveD, kSmdPool, kSmdThreads, kSmdSlots> {
         const unsigned g = g0 + (unsigned)lane;
         const int pl = (int)(g & (unsigned)(item_pixels - 1));
         const uint32_t sample = (uint32_t)lp.sample_begin + (g >> log_p);
-        const int pixel = mine ? item_pixel(Q->t_item[b], pl) : -1;
+        const int pixel = mine ? item_pixel(Q.t_item[b], pl) : -1;
         bool alive = false;
         Rng rng;
         if (pixel >= 0) {
