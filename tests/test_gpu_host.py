@@ -25,6 +25,21 @@ def test_cpp_host_writes_the_same_ppm_as_the_python_host(gpu, tmp_path):
     assert vals.size == 160 * 120 * 3 and vals.min() >= 0 and vals.max() <= 255 and vals.mean() > 5
 
 
+def test_pfm_side_output_of_both_hosts(gpu, tmp_path):
+    """--pfm: the frame before the tonemap.  Both hosts write the same floats for the same seed, they are the frame vpt_render returns,
+    and tonemapping them gives the PPM written next to them"""
+    from minimal_volumetric_path_tracer_b200 import build, cli
+    args = ["8", "--size", "96x64", "--method", "equi", "--seed", "7"]
+    r = subprocess.run([build.RT] + args + ["-o", "c.ppm", "--pfm", "c.pfm"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert cli.main(args + ["-o", str(tmp_path / "p.ppm"), "--pfm", str(tmp_path / "p.pfm")]) == 0
+    a, b = gpu.read_pfm(str(tmp_path / "c.pfm")), gpu.read_pfm(str(tmp_path / "p.pfm"))
+    assert a.shape == (64, 96, 3) and np.array_equal(a, b)
+    assert np.array_equal(a, gpu.render(gpu.default_params(width=96, height=64, spp=8, method=1, seed=7)))
+    vals = np.array((tmp_path / "c.ppm").read_text().split()[4:], dtype=int)
+    assert np.array_equal(gpu.tonemap(a).reshape(-1), vals)
+
+
 def test_ref_flag_runs_fp64(gpu, tmp_path):
     from minimal_volumetric_path_tracer_b200 import build
     r = subprocess.run([build.RT, "2", "--size", "64x48", "--ref", "-o", "ref.ppm"], cwd=tmp_path, capture_output=True, text=True)
