@@ -123,7 +123,9 @@ __global__ void __launch_bounds__(kSmdThreads, 1) render_f64_smwave_kernel(const
     for (int i = tid; i < kSmdPool; i += kSmdThreads) M.meta[i] = 0u;
     if (tid == 0) { M.ox[0] = M.oy[0] = M.oz[0] = 0.0; M.dx[0] = M.dy[0] = 0.0; M.dz[0] = 1.0; M.br[0] = M.bg[0] = M.bb[0] = 0.0; M.sample[0] = 0u; }
     stage_scene(sc, M.spheres); // (ends with __syncthreads)
-    const Ctx c = make_ctx(sc, M.spheres, lp);
+    if (tid == 0) M.ctx = make_ctx(sc, M.spheres, lp);
+    __syncthreads();
+    const Ctx &c = M.ctx;
     SmWaveD wf(M, c, lp, log_p, n_owned_tiles, zero);
     wf.init(n_items);
     __syncthreads();

@@ -31,6 +31,7 @@ constexpr double kSmdMaxContribution = 268435456.0;  // 2^28: a contribution at 
 
 struct SmSharedD {
     SphereD spheres[kMaxSpheres];
+    Ctx ctx; // ONE copy per CTA: the out-of-line building blocks take it by reference, and a per-thread copy would live in local memory
     double ox[kSmdPool], oy[kSmdPool], oz[kSmdPool];
     double dx[kSmdPool], dy[kSmdPool], dz[kSmdPool]; // direction; medium vertex between PRIMARY and MED: dx = transmittance, dy = distance pdf
     double br[kSmdPool], bg[kSmdPool], bb[kSmdPool];
