@@ -605,7 +605,7 @@ struct VertexPlan { // what the first part hands to the second
 // part 1: scene scan, light pick, distance sampling, surface-or-medium decision.  Lc: radiance this part contributes (a directly seen
 // emitter at depth 0, :1308-1313), before it the caller's p.L is untouched.
 template <class RngT>
-VPT_F64_OUTLINE int vertex_primary(const Ctx &c, const Path &p, RngT &rng, Tally &tl, VertexPlan &vp, D3 &Lc) {
+__device__ __forceinline__ int vertex_primary_inl(const Ctx &c, const Path &p, RngT &rng, Tally &tl, VertexPlan &vp, D3 &Lc) {
     ++tl.events;
     Lc = mk(0, 0, 0);
     double t;
@@ -658,7 +658,7 @@ VPT_F64_OUTLINE int vertex_primary(const Ctx &c, const Path &p, RngT &rng, Tally
 
 // part 2, surface vertex: pLight + MISv2 + bdsf (:1316-1327).  Lc: the vertex's direct light; p becomes the scattered ray.
 template <class RngT>
-VPT_F64_OUTLINE void vertex_surface(const Ctx &c, Path &p, const VertexPlan &vp, RngT &rng, Tally &tl, D3 &Lc) {
+__device__ __forceinline__ void vertex_surface_inl(const Ctx &c, Path &p, const VertexPlan &vp, RngT &rng, Tally &tl, D3 &Lc) {
     const SphereD &obj = c.s[vp.id];
     const D3 xs = vp.x;
     const D3 n = unit(xs - pos(obj));
@@ -679,7 +679,7 @@ VPT_F64_OUTLINE void vertex_surface(const Ctx &c, Path &p, const VertexPlan &vp,
 
 // part 2, medium vertex: (free)SingleScattering + isotropicPhaseSample (:1330-1337 / :1120-1135)
 template <class RngT>
-VPT_F64_OUTLINE void vertex_medium(const Ctx &c, Path &p, const VertexPlan &vp, RngT &rng, Tally &tl, D3 &Lc) {
+__device__ __forceinline__ void vertex_medium_inl(const Ctx &c, Path &p, const VertexPlan &vp, RngT &rng, Tally &tl, D3 &Lc) {
     const D3 xt = vp.x;
     const double prob_source = 1.0 / c.n_emitters;
     if (c.method == 0) {
@@ -697,6 +697,13 @@ VPT_F64_OUTLINE void vertex_medium(const Ctx &c, Path &p, const VertexPlan &vp, 
         p.o = xt; p.d = phase_sample(xi1, xi2);
     }
 }
+// the same parts out of line (the sequential kernels and the unit kernels, which run them back to back inside one loop)
+template <class RngT>
+VPT_F64_OUTLINE int vertex_primary(const Ctx &c, const Path &p, RngT &rng, Tally &tl, VertexPlan &vp, D3 &Lc) { return vertex_primary_inl(c, p, rng, tl, vp, Lc); }
+template <class RngT>
+VPT_F64_OUTLINE void vertex_surface(const Ctx &c, Path &p, const VertexPlan &vp, RngT &rng, Tally &tl, D3 &Lc) { vertex_surface_inl(c, p, vp, rng, tl, Lc); }
+template <class RngT>
+VPT_F64_OUTLINE void vertex_medium(const Ctx &c, Path &p, const VertexPlan &vp, RngT &rng, Tally &tl, D3 &Lc) { vertex_medium_inl(c, p, vp, rng, tl, Lc); }
 
 // the whole vertex; returns false when the path ends here
 template <class RngT>

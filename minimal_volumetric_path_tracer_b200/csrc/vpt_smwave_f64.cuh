@@ -122,7 +122,7 @@ struct SmWaveD : SmSched<SmWaveD, kSmdPool, kSmdThreads, kSmdSlots> {
             if (act) {
                 VertexPlan vp;
                 D3 Lc;
-                const int kind = vertex_primary(c, p, rng, tally, vp, Lc);
+                const int kind = vertex_primary_inl(c, p, rng, tally, vp, Lc);
                 if (kind == V_END) { add(meta, Lc); dest = kDestFree; }
                 else {
                     M.ox[s] = vp.x.x; M.oy[s] = vp.x.y; M.oz[s] = vp.x.z;
@@ -140,8 +140,8 @@ struct SmWaveD : SmSched<SmWaveD, kSmdPool, kSmdThreads, kSmdSlots> {
                 VertexPlan vp;
                 vp.source = (int)((meta >> 10) & 31u); vp.id = (int)((meta >> 15) & 31u); vp.x = p.o;
                 D3 Lc;
-                if (STAGE == SQ_MED_POINT || STAGE == SQ_MED_AREA) { vp.T = p.d.x; vp.pdf_medium = p.d.y; vertex_medium(c, p, vp, rng, tally, Lc); }
-                else { vp.T = 0; vp.pdf_medium = 1; vertex_surface(c, p, vp, rng, tally, Lc); }
+                if (STAGE == SQ_MED_POINT || STAGE == SQ_MED_AREA) { vp.T = p.d.x; vp.pdf_medium = p.d.y; vertex_medium_inl(c, p, vp, rng, tally, Lc); }
+                else { vp.T = 0; vp.pdf_medium = 1; vertex_surface_inl(c, p, vp, rng, tally, Lc); }
                 add(meta, Lc);
             }
             last_step();
