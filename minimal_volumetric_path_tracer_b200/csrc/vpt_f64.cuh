@@ -16,7 +16,14 @@
 // every call site the wavefront kernel was 698 KB of SASS and spent 34 % of its warp-state samples waiting for instructions (`no_inst`)
 // and 50 % at the round barrier behind the warps that did (profiles/r2_summary.md).  A call does not change an IEEE operation.
 #define VPT_F64_OUTLINE static __device__ __noinline__
-
+// Building blocks with ONE call site per stage of the SM pipeline are inlined into it (their by-reference arguments stay in registers):
+// the vertex parts 899 -> 1066 Mpaths/s, medium_direct + bsdf_sample + point_light_direct 1071 -> 1130 (surface_direct_mis / light_sampled_direct as well:
+// 1068 / 1054 against 1100 -- spills).  -DVPT_F64_OUTLINE_STAGE_BLOCKS puts them out of line again.
+#ifdef VPT_F64_OUTLINE_STAGE_BLOCKS
+#define VPT_F64_STAGE_BLOCK VPT_F64_OUTLINE
+#else
+#define VPT_F64_STAGE_BLOCK static __device__ __forceinline__
+#endif
 namespace vpt {
 namespace f64 {
 
@@ -390,7 +397,7 @@ VPT_F64_OUTLINE double multiple_t(const Ctx &c, D3 x1, D3 x2, double sigma_t) {
 
 // pLight, vptShadeMethods.h:62-91.  Without material-3 spheres visibilityVPT == visibility: the second branch (:70-74) would repeat the
 // scan with the same answer and is skipped.
-VPT_F64_OUTLINE D3 point_light_direct(const Ctx &c, const SphereD &obj, D3 x, D3 n, D3 wray, D3 I, D3 light, double alpha, Tally &tl) {
+VPT_F64_STAGE_BLOCK D3 point_light_direct(const Ctx &c, const SphereD &obj, D3 x, D3 n, D3 wray, D3 I, D3 light, double alpha, Tally &tl) {
     D3 Le = mk(0, 0, 0);
     if (visible(c, light, x, tl)) Le = I * (1 / dot(light - x, light - x));
     else if (c.n_volumes > 0 && visible_vpt(c, light, x, tl)) {
@@ -412,7 +419,7 @@ VPT_F64_OUTLINE D3 point_light_direct(const Ctx &c, const SphereD &obj, D3 x, D3
 
 // bdsf, vptShadeMethods.h:16-59
 template <class RngT>
-VPT_F64_OUTLINE D3 bsdf_sample(const SphereD &obj, D3 &wi_out, D3 wray, D3 n, double &pdf, RngT &rng) {
+VPT_F64_STAGE_BLOCK D3 bsdf_sample(const SphereD &obj, D3 &wi_out, D3 wray, D3 n, double &pdf, RngT &rng) {
     const D3 wo = wray * -1;
     if (obj.material == 2) { // :26-46 (ONE draw)
         const D3 wt = unit(refract_dielectric(1.0, 1.5, wo, n));
@@ -442,7 +449,7 @@ VPT_F64_OUTLINE D3 bsdf_sample(const SphereD &obj, D3 &wi_out, D3 wray, D3 n, do
 
 // freeSingleScattering (volumetricBasicFunctions.h:284-340) / singleScattering (:225-281)
 template <class RngT>
-VPT_F64_OUTLINE D3 medium_direct(const Ctx &c, D3 xt, int source, double prob_source, bool equi, double T_xt, RngT &rng, Tally &tl) {
+VPT_F64_STAGE_BLOCK D3 medium_direct(const Ctx &c, D3 xt, int source, double prob_source, bool equi, double T_xt, RngT &rng, Tally &tl) {
     const SphereD &src = c.s[source];
     D3 Ld = mk(0, 0, 0);
     if (src.r == 0) {
@@ -682,15 +689,15 @@ template <class RngT>
 __device__ __forceinline__ void vertex_medium_inl(const Ctx &c, Path &p, const VertexPlan &vp, RngT &rng, Tally &tl, D3 &Lc) {
     const D3 xt = vp.x;
     const double prob_source = 1.0 / c.n_emitters;
-    if (c.method == 0) {
-        const D3 Ld = medium_direct(c, xt, vp.source, prob_source, false, 0.0, rng, tl);
+    const bool equi = c.method != 0;
+    const D3 Ld = medium_direct(c, xt, vp.source, prob_source, equi, equi ? vp.T : 0.0, rng, tl);
+    if (!equi) {
         const double xi1 = rng.next_f64(S_PHASE), xi2 = rng.next_f64(S_PHASE + 1);
         Lc = had(Ld, p.beta) * (c.sigma_s / c.sigma_t) * (1 / c.cp);
         p.beta = p.beta * (c.sigma_s / c.sigma_t) * (1 / c.cp);
         p.o = xt; p.d = phase_sample(xi1, xi2);
     } else {
         const double T = vp.T;
-        const D3 Ld = medium_direct(c, xt, vp.source, prob_source, true, T, rng, tl);
         const double xi1 = rng.next_f64(S_PHASE), xi2 = rng.next_f64(S_PHASE + 1);
         Lc = had(Ld * (1 / vp.pdf_medium) * (1 / c.cp), p.beta);
         p.beta = p.beta * c.sigma_s * T * (1 / c.cp) * (1 / vp.pdf_medium);
