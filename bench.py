@@ -352,7 +352,7 @@ def main():
             traffic = None
     roofline = {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
                 "traffic": traffic, "algorithmic_hbm_bytes": d2h,
-                "kernel": ("render_f32_smwave_kernel<%d, %d, 1>" % (cfg["method"], 4 if (mine.sample_end - mine.sample_begin) < 384 else 2)) if args.precision == "fp32" else "render_f64_smwave_kernel", "kernel_ms_per_launch": kernel_ms,
+                "kernel": ("render_f32_smwave_kernel<%d, %d, 1>" % (cfg["method"], 6 if (mine.sample_end - mine.sample_begin) < 96 else 4 if (mine.sample_end - mine.sample_begin) < 384 else 2)) if args.precision == "fp32" else "render_f64_smwave_kernel", "kernel_ms_per_launch": kernel_ms,
                 "flop_per_path": fpp, "flop_per_path_formula": fpp_formula, "scans_per_path": scans_pp, "events_per_path": events_pp,
                 "frac_formula": per_gpu_paths / (kernel_ms * 1e-3) * fpp_formula / 1e12 / peak_tflops,
                 "peak_source": "measured live: vpt_measure_fp32_peak FFMA chains (MEASURED_PEAKS.json has no FP32 entry; nominal 74.4)",

@@ -169,18 +169,20 @@ static int launch_smwave_slots(const SceneF &scene, const LaunchParams &lp, cons
     return (int)philox_keys_end(K, st);
 #endif
 }
-// Work items in flight per CTA (vpt_smsched.cuh): four below 384 samples per pixel, two from there on.  Measured on 1024x768, equi-angular:
-// 64 spp 7502 (four) against 4948 (two, and 6999 with two 256-pixel items), 256 spp 8455 against 8398, 512 spp 8510 against 8599,
-// 1024 spp 8532 against 8631 Mpaths/s.
+// Work items in flight per CTA (vpt_smsched.cuh): six below 96 samples per pixel, four below 384, two from there on.  Measured on 1024x768,
+// equi-angular, Mpaths/s with 2 / 4 / 6 items: 16 spp - / 3221 / 4102, 32 spp 3196 / 5112 / 6461, 64 spp 4948 / 7640 / 8089 (two 256-pixel
+// items: 6999), 128 spp 6971 / 8461 / 8311, 256 spp 8398 / 8559 / 8408, 512 spp 8599 / 8510 / -, 1024 spp 8631 / 8532 / -.
 template <int METHOD>
 static int launch_smwave(const SceneF &scene, const LaunchParams &lp, const ConstsF &cf, float *hdr_dev, Counters *counters_dev, cudaStream_t st, int n_owned_tiles) {
 #ifdef VPT_ITEM_SLOTS_RUN
-    const bool many = VPT_ITEM_SLOTS_RUN > 2;
+    const int slots = VPT_ITEM_SLOTS_RUN;
 #else
-    const bool many = lp.sample_end - lp.sample_begin < 384;
+    const int spp = lp.sample_end - lp.sample_begin;
+    const int slots = spp < 96 ? 6 : (spp < 384 ? 4 : 2);
 #endif
-    return many ? launch_smwave_slots<METHOD, kMaxItemSlots>(scene, lp, cf, hdr_dev, counters_dev, st, n_owned_tiles)
-                : launch_smwave_slots<METHOD, 2>(scene, lp, cf, hdr_dev, counters_dev, st, n_owned_tiles);
+    if (slots > 4) return launch_smwave_slots<METHOD, 6>(scene, lp, cf, hdr_dev, counters_dev, st, n_owned_tiles);
+    if (slots > 2) return launch_smwave_slots<METHOD, 4>(scene, lp, cf, hdr_dev, counters_dev, st, n_owned_tiles);
+    return launch_smwave_slots<METHOD, 2>(scene, lp, cf, hdr_dev, counters_dev, st, n_owned_tiles);
 }
 
 // ---- ray-marching reference solver (vpt_march.cuh): one thread per pixel ---------------------------------------------------------

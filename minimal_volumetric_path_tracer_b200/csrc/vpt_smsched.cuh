@@ -34,17 +34,21 @@ constexpr int kTailGen = VPT_TAIL_GEN;
 constexpr int kSmMaxItemPixels = 128; // pixels per work item (power of two multiple of kTile)
 // Work items in flight per CTA (template parameter SLOTS of the scheduler, chosen per launch): more of them keep the pool full at low sample
 // counts, where an item's samples are generated in a few rounds while its last paths take tens of rounds to finish (64 spp: four slots
-// +8 .. 10 % over two); fewer cost less in the plan and per batch (1024 spp: two slots +1.2 % over four).  3 KB of pixel sums per slot.
-constexpr int kMaxItemSlots = 4;
+// +8 .. 10 % over two, six another +6 %; 16 spp: six +27 % over four); fewer cost less in the plan and per batch (1024 spp: two slots
+// +1.2 % over four).  3 KB of pixel sums per slot.
+#ifndef VPT_MAX_ITEM_SLOTS
+#define VPT_MAX_ITEM_SLOTS 6
+#endif
+constexpr int kMaxItemSlots = VPT_MAX_ITEM_SLOTS; // (the plan reads 14 + 3 * SLOTS control words with one load of the warp: at most 6)
 // Claim order of a round's batches (one nibble per rank, SQ_COUNT = generation), longest stage first so that a round ends evenly:
 // SURF_F, SURF_L, PRIMARY, MED_AREA, MED_POINT, SURF_P, generation
 constexpr unsigned kRankStage = 0x6312045u;
 
-// meta word of a record: pixel-in-item (bits 0-7) | item slot (bits 8-9) | picked source (10-14) | hit object (15-19) | depth (20-31)
-static_assert(kMaxSpheres <= 32 && VPT_MAX_DEPTH <= 4095 && kSmMaxItemPixels <= 256 && kSmMaxItemPixels >= kTile && kMaxItemSlots <= 4, "meta word layout");
-__device__ __forceinline__ uint32_t meta_slot(uint32_t meta) { return (meta >> 8) & 3u; }
-__device__ __forceinline__ uint32_t meta_pixel(uint32_t meta) { return meta & 0xffu; }
-__device__ __forceinline__ uint32_t meta_aux(int pixel_in_item, int item_slot) { return (uint32_t)pixel_in_item | ((uint32_t)item_slot << 8); }
+// meta word of a record: pixel-in-item (bits 0-6) | item slot (bits 7-9) | picked source (10-14) | hit object (15-19) | depth (20-31)
+static_assert(kMaxSpheres <= 32 && VPT_MAX_DEPTH <= 4095 && kSmMaxItemPixels <= 128 && kSmMaxItemPixels >= kTile && kMaxItemSlots <= 8, "meta word layout");
+__device__ __forceinline__ uint32_t meta_slot(uint32_t meta) { return (meta >> 7) & 7u; }
+__device__ __forceinline__ uint32_t meta_pixel(uint32_t meta) { return meta & 0x7fu; }
+__device__ __forceinline__ uint32_t meta_aux(int pixel_in_item, int item_slot) { return (uint32_t)pixel_in_item | ((uint32_t)item_slot << 7); }
 __device__ __forceinline__ uint32_t meta_pack(uint32_t aux, uint32_t src, uint32_t hid, uint32_t depth) { return (aux & 0x3ffu) | (src << 10) | (hid << 15) | (depth << 20); }
 
 // queues, pixel sums and control words of one CTA (the pipeline's shared-memory struct holds one, next to its records and its scene)
@@ -74,7 +78,7 @@ struct SmCtl {
     unsigned free_head, free_tail;           // [12,13]  the free-record ring: allocate at the head (only below the round's snapshot), release at the tail
     int t_item[SLOTS];                       // [14 ..]  work item of the slot, -1: slot idle
     unsigned t_cursor[SLOTS], t_done[SLOTS]; // camera samples generated / paths finished
-    unsigned ctl_pad[18 - 3 * SLOTS];
+    unsigned ctl_pad[19 - 3 * SLOTS];
     int gen_slot, flush_slot, exit_flag;
 #ifdef VPT_SMWAVE_PROFILE
     long long dbg_arrive[32];

@@ -245,19 +245,25 @@ def test_c3_full_size_properties(gpu):
 
 
 def test_item_slot_instantiations_agree(gpu):
-    """The product kernel keeps four work items in flight per SM below 384 samples per pixel and two from there on (two instantiations of the
-    scheduler, vpt_smsched.cuh).  Which one runs must not show in the image: a 512-spp frame in one launch (two slots) equals the sum of its
-    [0,256) and [256,512) sample ranges (four slots each) up to the fp32 store, and both equal the multi-kernel HBM wavefront -- which has no
-    items at all -- bit for bit; ragged frame (not a multiple of the 128-pixel tile), all four FP32 shade methods"""
+    """The product kernel keeps six work items in flight per SM below 96 samples per pixel, four below 384 and two from there on (three
+    instantiations of the scheduler, vpt_smsched.cuh).  Which one runs must not show in the image: a 512-spp frame in one launch (two slots)
+    equals the sum of its [0,256) and [256,512) sample ranges (four slots each) and the sum of its eight 64-sample ranges (six slots each) up
+    to the fp32 store, and every one of these launches equals the multi-kernel HBM wavefront -- which has no items at all -- bit for bit;
+    ragged frame (not a multiple of the 128-pixel tile), all four FP32 shade methods"""
     for method in (0, 1, 2, 4):
         p = gpu.default_params(width=250, height=131, spp=512, method=method, seed=11, output=gpu.OUTPUT_SUM)
         whole, st = gpu.render(p, stats=True)
         assert st.paths == 250 * 131 * 512
         assert np.array_equal(whole, gpu.render(p.copy(kernel=gpu.KERNEL_WAVEFRONT_HBM)))
-        lo, hi = p.copy(sample_begin=0, sample_end=256), p.copy(sample_begin=256, sample_end=512)
-        a, b = gpu.render(lo), gpu.render(hi)
-        assert np.array_equal(a, gpu.render(lo.copy(kernel=gpu.KERNEL_WAVEFRONT_HBM))) and np.array_equal(b, gpu.render(hi.copy(kernel=gpu.KERNEL_WAVEFRONT_HBM)))
-        np.testing.assert_allclose(a.astype(np.float64) + b, whole, rtol=3e-7, atol=1e-6)
+        for n_parts in (2, 8):
+            per = 512 // n_parts
+            total = np.zeros(whole.shape, dtype=np.float64)
+            for k in range(n_parts):
+                q = p.copy(sample_begin=k * per, sample_end=(k + 1) * per)
+                part = gpu.render(q)
+                assert np.array_equal(part, gpu.render(q.copy(kernel=gpu.KERNEL_WAVEFRONT_HBM))), (method, n_parts, k)
+                total += part
+            np.testing.assert_allclose(total, whole, rtol=6e-7, atol=1e-6)
 
 
 def test_c5_frame_size_tiles_and_determinism(gpu):
