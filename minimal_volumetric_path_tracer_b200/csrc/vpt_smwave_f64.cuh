@@ -24,7 +24,10 @@ namespace f64 {
 #endif
 constexpr int kSmdThreads = VPT_SMD_THREADS;
 constexpr int kSmdPool = 2048;
-constexpr int kSmdSlots = 4; // work items in flight (vpt_smsched.cuh): reference mode is used at low sample counts
+#ifndef VPT_SMD_SLOTS
+#define VPT_SMD_SLOTS 4 // (six: 16 spp 715 against 577 Mpaths/s, but 64 spp 1082 against 1097 and 256 spp 1103 against 1126)
+#endif
+constexpr int kSmdSlots = VPT_SMD_SLOTS; // work items in flight (vpt_smsched.cuh): reference mode is used at low sample counts
 constexpr double kSmdFixScale = 17179869184.0;       // 2^34
 constexpr double kSmdFixInv = 1.0 / 17179869184.0;
 constexpr double kSmdMaxContribution = 268435456.0;  // 2^28: a contribution at or above it (or NaN) is dropped and counted (vpt_stats.nonfinite)
